@@ -1,0 +1,680 @@
+// ps_capi.cu — the C ABI of libps_b200.so (include/ps_b200.h): handle management, host<->device
+// marshalling between the ABI layout (per-field, xyz-interleaved) and the per-world planar layout
+// the step kernel stages into shared memory, and the kernel launches.
+//
+// There is no CPU path in this file: every entry point that computes runs a CUDA kernel or fails
+// with PS_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ps_b200.h"
+#include "ps_step_kernel.cuh"
+
+using namespace psk;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_device = -1;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(x)                                                                                              \
+    do {                                                                                                   \
+        cudaError_t e_ = (x);                                                                              \
+        if (e_ != cudaSuccess) return fail(PS_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// host-side description of the batch in ABI layout (kept for add_body / reset / candidates)
+struct HostBodies {
+    std::vector<int32_t> off;
+    std::vector<int32_t> shape;
+    std::vector<double> dims, mass, iinv, pos, vel, rot, L, force, torque, e, muk, mus;
+    int n() const { return (int)mass.size(); }
+};
+struct HostJoints {
+    std::vector<int32_t> world, a, b;
+    std::vector<double> la, lb;
+};
+
+struct Batch {
+    int device = 0;
+    ps_step_config cfg{};
+    HostBodies init, cur;  // `cur` holds parameters (+ possibly added bodies); dynamic state lives on the device
+    HostJoints joints;
+    int n_worlds = 0, n_bodies = 0, n_dynamic = 0, max_n = 0;
+    int k_cap = 0, ks_cap = 0;
+    size_t smem = 0;
+    // device
+    double* d_dyn = nullptr;
+    double* d_par = nullptr;
+    double* d_stage = nullptr;  // 18 doubles/body staging in ABI layout: pos | vel | rot | L
+    int* d_off = nullptr;
+    WorldStats* d_stats = nullptr;
+    int *d_joff = nullptr, *d_ja = nullptr, *d_jb = nullptr;
+    double *d_jla = nullptr, *d_jlb = nullptr;
+    unsigned char* d_jlast = nullptr;
+    RecPair* d_rec_pairs = nullptr;
+    RecContact* d_rec_contacts = nullptr;
+    int* d_rec_counts = nullptr;
+    int rec_pair_cap = 0, rec_contact_cap = 0;
+    ps_stats* d_stats_sum = nullptr;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+};
+
+// ---- layout kernels ------------------------------------------------------------------------------
+// ABI (pos[3n] vel[3n] rot[9n] L[3n]) <-> per-world planar dyn
+__global__ void pack_dyn_kernel(const int* __restrict__ off, int w0, int w1, const double* __restrict__ pos,
+                                const double* __restrict__ vel, const double* __restrict__ rot,
+                                const double* __restrict__ L, double* __restrict__ dyn, int body0)
+{
+    // one thread per (world-local) body in [off[w0], off[w1])
+    int g = blockIdx.x * blockDim.x + threadIdx.x + off[w0];
+    if (g >= off[w1]) return;
+    // binary search of the world
+    int lo = w0, hi = w1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= g) lo = mid; else hi = mid;
+    }
+    int o = off[lo], N = off[lo + 1] - o, b = g - o;
+    double* d = dyn + (size_t)o * kDynF;
+    int s = g - body0;  // index into the caller arrays (which start at world w0)
+    for (int k = 0; k < 3; k++) {
+        d[k * N + b] = pos[3 * s + k];
+        d[(3 + k) * N + b] = vel[3 * s + k];
+        d[(15 + k) * N + b] = L[3 * s + k];
+    }
+    for (int k = 0; k < 9; k++) d[(6 + k) * N + b] = rot[9 * s + k];
+}
+__global__ void unpack_dyn_kernel(const int* __restrict__ off, int w0, int w1, double* __restrict__ pos,
+                                  double* __restrict__ vel, double* __restrict__ rot, double* __restrict__ L,
+                                  const double* __restrict__ dyn, int body0)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x + off[w0];
+    if (g >= off[w1]) return;
+    int lo = w0, hi = w1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= g) lo = mid; else hi = mid;
+    }
+    int o = off[lo], N = off[lo + 1] - o, b = g - o;
+    const double* d = dyn + (size_t)o * kDynF;
+    int s = g - body0;
+    for (int k = 0; k < 3; k++) {
+        if (pos) pos[3 * s + k] = d[k * N + b];
+        if (vel) vel[3 * s + k] = d[(3 + k) * N + b];
+        if (L) L[3 * s + k] = d[(15 + k) * N + b];
+    }
+    if (rot)
+        for (int k = 0; k < 9; k++) rot[9 * s + k] = d[(6 + k) * N + b];
+}
+
+// Simulator.ApplyImpulse -> RigidBodyMotion.applyImpulse (RigidBody.fs:194-197)
+__global__ void apply_impulse_kernel(double* dyn, const double* par, const int* off, int w, int b, double jx, double jy,
+                                     double jz, double ox, double oy, double oz)
+{
+    int o = off[w], N = off[w + 1] - o;
+    Dyn d;
+    Par p;
+    ld_dyn(dyn + (size_t)o * kDynF, N, b, d);
+    ld_par(par + (size_t)o * kParF, N, b, p);
+    apply_impulse(d, p, mk(ox, oy, oz), mk(jx, jy, jz));
+    st_dyn(dyn + (size_t)o * kDynF, N, b, d);
+}
+
+// K6: per-world counters -> one ps_stats (integer sums + max)
+__global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const double* par, int n_worlds, ps_stats* out)
+{
+    unsigned long long steps = 0, tested = 0, hits = 0, contacts = 0, fallback = 0, overflow = 0, exc = 0, nanw = 0, bsteps = 0;
+    double mp = 0.0;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_worlds; w += gridDim.x * blockDim.x) {
+        const WorldStats& s = ws[w];
+        steps += s.steps; tested += s.tested; hits += s.hits; contacts += s.contacts;
+        fallback += s.fallback; overflow += s.overflow; exc += s.ref_exc; nanw += s.nan_flag ? 1 : 0;
+        mp = fmax(mp, s.max_pen);
+        int o = off[w], N = off[w + 1] - o, dynb = 0;
+        const double* p = par + (size_t)o * kParF;
+        for (int b = 0; b < N; b++) dynb += (p[b] != 0.0);
+        bsteps += s.steps * (unsigned long long)dynb;
+    }
+    atomicAdd((unsigned long long*)&out->steps, steps);
+    atomicAdd((unsigned long long*)&out->body_steps, bsteps);
+    atomicAdd((unsigned long long*)&out->pairs_tested, tested);
+    atomicAdd((unsigned long long*)&out->pairs_colliding, hits);
+    atomicAdd((unsigned long long*)&out->contacts, contacts);
+    atomicAdd((unsigned long long*)&out->fallback_steps, fallback);
+    atomicAdd((unsigned long long*)&out->nan_worlds, nanw);
+    atomicAdd((unsigned long long*)&out->contact_overflow, overflow);
+    atomicAdd((unsigned long long*)&out->reference_exceptions, exc);
+    atomicMax((unsigned long long*)&out->max_penetration, (unsigned long long)__double_as_longlong(mp));
+}
+
+// ---- helpers ---------------------------------------------------------------------------------------
+template <class T>
+void dfree(T*& p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+void free_device(Batch* B)
+{
+    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats);
+    dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
+    dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
+}
+
+int validate_bodies(const HostBodies& h)
+{
+    int nw = (int)h.off.size() - 1;
+    for (int w = 0; w < nw; w++) {
+        int N = h.off[w + 1] - h.off[w];
+        if (N < 0) return fail(PS_ERR_INVALID_ARGUMENT, "world_offset must be non-decreasing (world %d)", w);
+        if (N > 1024) return fail(PS_ERR_INVALID_ARGUMENT, "world %d has %d bodies; the per-world stepper takes at most 1024", w, N);
+    }
+    for (int i = 0; i < h.n(); i++) {
+        if (h.shape[i] != 0 && h.shape[i] != 1) return fail(PS_ERR_INVALID_ARGUMENT, "body %d: shape must be 0 (sphere) or 1 (box)", i);
+        for (int k = 0; k < 3; k++)
+            if (h.dims[3 * i + k] < 0.0) return fail(PS_ERR_INVALID_ARGUMENT, "body %d: Must be positive (size)", i);  // throwIfNegative
+        if (h.e[i] < 0.0 || h.e[i] > 1.0) return fail(PS_ERR_INVALID_ARGUMENT, "body %d: elasticityCoeff Invalid value", i);
+        if (h.muk[i] < 0.0 || h.mus[i] < 0.0) return fail(PS_ERR_INVALID_ARGUMENT, "body %d: staticFrictionCoeff Invalid value", i);
+    }
+    return PS_OK;
+}
+
+// upload parameters + (optionally) dynamic state of B->cur, (re)allocating device buffers
+int upload(Batch* B, bool with_state)
+{
+    const HostBodies& h = B->cur;
+    CK(cudaSetDevice(B->device));
+    free_device(B);
+    B->n_worlds = (int)h.off.size() - 1;
+    B->n_bodies = h.n();
+    B->max_n = 0;
+    B->n_dynamic = 0;
+    for (int w = 0; w < B->n_worlds; w++) B->max_n = std::max(B->max_n, h.off[w + 1] - h.off[w]);
+    for (int i = 0; i < B->n_bodies; i++) B->n_dynamic += std::isinf(h.mass[i]) ? 0 : 1;
+    B->k_cap = std::min(60000, std::max(64, 10 * B->max_n));
+    B->ks_cap = std::min(B->k_cap, std::max(16, 3 * B->max_n));
+    B->smem = smem_bytes(B->max_n, B->k_cap, B->ks_cap);
+    int dev_max = 0;
+    CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, B->device));
+    if ((long long)B->smem > dev_max)
+        return fail(PS_ERR_INVALID_ARGUMENT, "largest world (%d bodies) needs %zu B of shared memory; device allows %d", B->max_n, B->smem, dev_max);
+    CK(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem));
+
+    size_t nb = (size_t)std::max(1, B->n_bodies);
+    CK(cudaMalloc(&B->d_dyn, nb * kDynF * sizeof(double)));
+    CK(cudaMalloc(&B->d_par, nb * kParF * sizeof(double)));
+    CK(cudaMalloc(&B->d_stage, nb * kDynF * sizeof(double)));
+    CK(cudaMalloc(&B->d_off, (size_t)(B->n_worlds + 1) * sizeof(int)));
+    CK(cudaMalloc(&B->d_stats, (size_t)std::max(1, B->n_worlds) * sizeof(WorldStats)));
+    CK(cudaMalloc(&B->d_stats_sum, sizeof(ps_stats)));
+    CK(cudaMemsetAsync(B->d_stats, 0, (size_t)std::max(1, B->n_worlds) * sizeof(WorldStats), B->stream));
+    CK(cudaMemcpyAsync(B->d_off, h.off.data(), (size_t)(B->n_worlds + 1) * sizeof(int), cudaMemcpyHostToDevice, B->stream));
+
+    // parameters -> per-world planar (plane 0 = 1.0/mass, IEEE division as on the reference's `v / mass`)
+    std::vector<double> par(nb * kParF, 0.0);
+    for (int w = 0; w < B->n_worlds; w++) {
+        int o = h.off[w], N = h.off[w + 1] - o;
+        double* p = par.data() + (size_t)o * kParF;
+        for (int b = 0; b < N; b++) {
+            int g = o + b;
+            p[b] = 1.0 / h.mass[g];
+            for (int k = 0; k < 3; k++) {
+                p[(1 + k) * N + b] = h.iinv[3 * g + k];
+                p[(4 + k) * N + b] = h.force[3 * g + k];
+                p[(7 + k) * N + b] = h.torque[3 * g + k];
+                p[(12 + k) * N + b] = h.dims[3 * g + k];
+            }
+            p[10 * N + b] = h.e[g];
+            p[11 * N + b] = h.muk[g];
+            p[15 * N + b] = (double)h.shape[g];
+        }
+    }
+    CK(cudaMemcpyAsync(B->d_par, par.data(), nb * kParF * sizeof(double), cudaMemcpyHostToDevice, B->stream));
+    CK(cudaStreamSynchronize(B->stream));  // `par` is a local
+
+    // joints grouped per world
+    const HostJoints& J = B->joints;
+    int nj = (int)J.a.size();
+    if (nj > 0) {
+        std::vector<int> order(nj);
+        for (int q = 0; q < nj; q++) order[q] = q;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return J.world[x] < J.world[y]; });
+        std::vector<int> joff(B->n_worlds + 1, 0), ja(nj), jb(nj);
+        std::vector<double> la(3 * nj), lb(3 * nj);
+        std::vector<unsigned char> last(nj, 0);
+        for (int q = 0; q < nj; q++) joff[J.world[order[q]] + 1]++;
+        for (int w = 0; w < B->n_worlds; w++) {
+            if (joff[w + 1] > kThreads) return fail(PS_ERR_INVALID_ARGUMENT, "world %d has %d joints; at most %d per world", w, joff[w + 1], kThreads);
+            joff[w + 1] += joff[w];
+        }
+        for (int q = 0; q < nj; q++) {
+            int s = order[q];
+            ja[q] = J.a[s]; jb[q] = J.b[s];
+            for (int k = 0; k < 3; k++) { la[3 * q + k] = J.la[3 * s + k]; lb[3 * q + k] = J.lb[3 * s + k]; }
+        }
+        // write-back is in joint-list order, the last writer wins (JointsRestorer.fs:18-26)
+        for (int w = 0; w < B->n_worlds; w++) {
+            std::vector<int> seen(h.off[w + 1] - h.off[w], 0);
+            for (int q = joff[w + 1] - 1; q >= joff[w]; q--) {
+                if (!seen[ja[q]]) { last[q] |= 1; seen[ja[q]] = 1; }
+                if (!seen[jb[q]]) { last[q] |= 2; seen[jb[q]] = 1; }
+            }
+        }
+        CK(cudaMalloc(&B->d_joff, joff.size() * sizeof(int)));
+        CK(cudaMalloc(&B->d_ja, nj * sizeof(int)));
+        CK(cudaMalloc(&B->d_jb, nj * sizeof(int)));
+        CK(cudaMalloc(&B->d_jla, 3 * nj * sizeof(double)));
+        CK(cudaMalloc(&B->d_jlb, 3 * nj * sizeof(double)));
+        CK(cudaMalloc(&B->d_jlast, nj));
+        CK(cudaMemcpy(B->d_joff, joff.data(), joff.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B->d_ja, ja.data(), nj * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B->d_jb, jb.data(), nj * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B->d_jla, la.data(), 3 * nj * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B->d_jlb, lb.data(), 3 * nj * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B->d_jlast, last.data(), nj, cudaMemcpyHostToDevice));
+    }
+    if (B->cfg.record_contacts) {
+        B->rec_pair_cap = std::max(16, 6 * B->max_n);
+        B->rec_contact_cap = std::max(64, 24 * B->max_n);
+        size_t nw = (size_t)std::max(1, B->n_worlds);
+        CK(cudaMalloc(&B->d_rec_pairs, nw * B->rec_pair_cap * sizeof(RecPair)));
+        CK(cudaMalloc(&B->d_rec_contacts, nw * B->rec_contact_cap * sizeof(RecContact)));
+        CK(cudaMalloc(&B->d_rec_counts, nw * 2 * sizeof(int)));
+        CK(cudaMemset(B->d_rec_counts, 0, nw * 2 * sizeof(int)));
+    }
+    if (with_state && B->n_bodies > 0) {
+        int rc = ps_batch_set_state(B, 0, B->n_worlds, h.pos.data(), h.vel.data(), h.rot.data(), h.L.data());
+        if (rc) return rc;
+    }
+    return PS_OK;
+}
+
+void copy_view(HostBodies& h, const ps_bodies_view* v)
+{
+    int nw = v->n_worlds;
+    h.off.assign(v->world_offset, v->world_offset + nw + 1);
+    int n = h.off[nw];
+    auto cp = [&](std::vector<double>& dst, const double* src, int per) { dst.assign(src, src + (size_t)per * n); };
+    h.shape.assign(v->shape, v->shape + n);
+    cp(h.dims, v->dims, 3); cp(h.mass, v->mass, 1); cp(h.iinv, v->inertia_inv, 3);
+    cp(h.pos, v->pos, 3); cp(h.vel, v->vel, 3); cp(h.rot, v->rot, 9); cp(h.L, v->ang_mom, 3);
+    cp(h.force, v->force, 3); cp(h.torque, v->torque, 3); cp(h.e, v->elasticity, 1); cp(h.muk, v->mu_kinetic, 1);
+    if (v->mu_static) cp(h.mus, v->mu_static, 1); else h.mus.assign(n, 0.0);
+}
+
+int check_view(const ps_bodies_view* v)
+{
+    if (!v) return fail(PS_ERR_INVALID_ARGUMENT, "bodies view is null");
+    if (v->n_worlds < 0 || !v->world_offset) return fail(PS_ERR_INVALID_ARGUMENT, "n_worlds/world_offset invalid");
+    if (v->world_offset[0] != 0) return fail(PS_ERR_INVALID_ARGUMENT, "world_offset[0] must be 0");
+    for (int w = 0; w < v->n_worlds; w++)
+        if (v->world_offset[w + 1] < v->world_offset[w]) return fail(PS_ERR_INVALID_ARGUMENT, "world_offset must be non-decreasing");
+    if (v->world_offset[v->n_worlds] > 0 &&
+        (!v->shape || !v->dims || !v->mass || !v->inertia_inv || !v->pos || !v->vel || !v->rot || !v->ang_mom || !v->force ||
+         !v->torque || !v->elasticity || !v->mu_kinetic))
+        return fail(PS_ERR_INVALID_ARGUMENT, "a body array is null");
+    return PS_OK;
+}
+
+}  // namespace
+
+// ====================================================================================================
+extern "C" {
+
+int ps_version(void) { return 100; }
+const char* ps_last_error(void) { return g_err.c_str(); }
+
+int ps_init(int32_t device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(PS_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+    if (device >= n) return fail(PS_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", device, n);
+    if (device >= 0) {
+        CK(cudaSetDevice(device));
+        g_device = device;
+    } else {
+        CK(cudaGetDevice(&g_device));
+    }
+    return PS_OK;
+}
+
+int ps_batch_create(void** handle, const ps_bodies_view* bodies, const ps_joints_view* joints, const ps_step_config* config)
+{
+    if (!handle || !config) return fail(PS_ERR_INVALID_ARGUMENT, "handle/config is null");
+    *handle = nullptr;
+    int rc = check_view(bodies);
+    if (rc) return rc;
+    if (config->solver_iterations < 0) return fail(PS_ERR_INVALID_ARGUMENT, "solver_iterations must be >= 0");
+    if (config->broadphase_kind != 0) return fail(PS_ERR_INVALID_ARGUMENT, "only the Dummy candidate order (broadphase_kind 0) runs on the device");
+    if (!(config->dt == config->dt)) return fail(PS_ERR_INVALID_ARGUMENT, "dt is NaN");
+    if (g_device < 0) {
+        rc = ps_init(-1);
+        if (rc) return rc;
+    }
+    Batch* B = new Batch();
+    B->device = g_device;
+    B->cfg = *config;
+    copy_view(B->init, bodies);
+    rc = validate_bodies(B->init);
+    if (rc) { delete B; return rc; }
+    if (joints && joints->n_joints > 0) {
+        int nj = joints->n_joints;
+        B->joints.world.assign(joints->world, joints->world + nj);
+        B->joints.a.assign(joints->body_a, joints->body_a + nj);
+        B->joints.b.assign(joints->body_b, joints->body_b + nj);
+        B->joints.la.assign(joints->anchor_a, joints->anchor_a + 3 * nj);
+        B->joints.lb.assign(joints->anchor_b, joints->anchor_b + 3 * nj);
+        for (int q = 0; q < nj; q++) {
+            int w = B->joints.world[q];
+            if (w < 0 || w >= bodies->n_worlds) { delete B; return fail(PS_ERR_OUT_OF_RANGE, "joint %d: world %d", q, w); }
+            int N = B->init.off[w + 1] - B->init.off[w];
+            int a = B->joints.a[q], b = B->joints.b[q];
+            if (a < 0 || b < 0 || a >= N || b >= N) { delete B; return fail(PS_ERR_OUT_OF_RANGE, "joint %d: body id out of range", q); }
+            // changePhysicalObjects pairs id-sorted objects with pair-ordered results (Q15): a > b would swap
+            // the two bodies; that is rejected instead of reproduced.
+            if (a >= b) { delete B; return fail(PS_ERR_INVALID_ARGUMENT, "joint %d: body_a must be < body_b", q); }
+        }
+    }
+    B->cur = B->init;
+    if (cudaSetDevice(B->device) != cudaSuccess || cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete B;
+        return fail(PS_ERR_CUDA, "cannot create a stream on device %d", g_device);
+    }
+    rc = upload(B, true);
+    if (rc) {
+        free_device(B);
+        cudaStreamDestroy(B->stream);
+        delete B;
+        return rc;
+    }
+    *handle = B;
+    return PS_OK;
+}
+
+int ps_batch_destroy(void* handle)
+{
+    if (!handle) return PS_OK;
+    Batch* B = (Batch*)handle;
+    cudaSetDevice(B->device);
+    cudaStreamSynchronize(B->stream);
+    free_device(B);
+    cudaStreamDestroy(B->stream);
+    delete B;
+    return PS_OK;
+}
+
+static int launch_step(Batch* B, int n_steps, cudaStream_t st)
+{
+    if (n_steps < 0) return fail(PS_ERR_INVALID_ARGUMENT, "n_steps must be >= 0");
+    if (n_steps == 0 || B->n_worlds == 0) return PS_OK;
+    KArgs a{};
+    a.dyn = B->d_dyn; a.par = B->d_par; a.off = B->d_off; a.stats = B->d_stats;
+    a.n_worlds = B->n_worlds; a.n_steps = n_steps;
+    a.sp.eps = B->cfg.epsilon; a.sp.baumgarte = B->cfg.baumgarte; a.sp.slop = B->cfg.allowed_penetration;
+    a.sp.max_corr = B->cfg.max_correction_velocity; a.sp.dt = B->cfg.dt;
+    a.sp.iterations = B->cfg.solver_iterations; a.sp.friction = B->cfg.enable_friction; a.sp.integrator = B->cfg.integrator_kind;
+    a.exact_all_pairs = B->cfg.exact_all_pairs;
+    a.restore_joints = B->cfg.restore_joints;
+    a.joff = B->d_joff; a.ja = B->d_ja; a.jb = B->d_jb; a.jla = B->d_jla; a.jlb = B->d_jlb; a.jlast = B->d_jlast;
+    a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
+    a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
+    a.max_n = B->max_n; a.k_cap = B->k_cap; a.ks_cap = B->ks_cap;
+    step_kernel<<<B->n_worlds, kThreads, B->smem, st>>>(a);
+    CK(cudaGetLastError());
+    B->launches++;
+    return PS_OK;
+}
+
+int ps_batch_step(void* handle, int32_t n_steps)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    CK(cudaSetDevice(B->device));
+    int rc = launch_step(B, n_steps, B->stream);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(B->stream));
+    return PS_OK;
+}
+int ps_batch_step_async(void* handle, int32_t n_steps, void* cuda_stream)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    CK(cudaSetDevice(B->device));
+    return launch_step(B, n_steps, cuda_stream ? (cudaStream_t)cuda_stream : B->stream);
+}
+int ps_batch_synchronize(void* handle)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    return PS_OK;
+}
+
+static int check_range(Batch* B, int w0, int w1)
+{
+    if (w0 < 0 || w1 > B->n_worlds || w0 > w1) return fail(PS_ERR_OUT_OF_RANGE, "world range [%d,%d) outside [0,%d)", w0, w1, B->n_worlds);
+    return PS_OK;
+}
+
+int ps_batch_get_state_device(void* handle, int32_t w0, int32_t w1, double* d_pos, double* d_vel, double* d_rot,
+                              double* d_ang_mom, void* cuda_stream)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    int rc = check_range(B, w0, w1);
+    if (rc) return rc;
+    CK(cudaSetDevice(B->device));
+    int b0 = B->cur.off[w0], n = B->cur.off[w1] - b0;
+    if (n == 0) return PS_OK;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : B->stream;
+    unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_off, w0, w1, d_pos, d_vel, d_rot, d_ang_mom, B->d_dyn, b0);
+    CK(cudaGetLastError());
+    return PS_OK;
+}
+
+int ps_batch_get_state(void* handle, int32_t w0, int32_t w1, double* pos, double* vel, double* rot, double* ang_mom)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    int rc = check_range(B, w0, w1);
+    if (rc) return rc;
+    CK(cudaSetDevice(B->device));
+    int b0 = B->cur.off[w0], n = B->cur.off[w1] - b0;
+    if (n == 0) return PS_OK;
+    double* sp = B->d_stage + (size_t)b0 * kDynF;  // this range's staging slice: pos | vel | rot | L
+    double *dp = sp, *dv = sp + 3 * (size_t)n, *dr = sp + 6 * (size_t)n, *dl = sp + 15 * (size_t)n;
+    unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, B->stream>>>(B->d_off, w0, w1, pos ? dp : nullptr, vel ? dv : nullptr,
+                                                               rot ? dr : nullptr, ang_mom ? dl : nullptr, B->d_dyn, b0);
+    CK(cudaGetLastError());
+    if (pos) CK(cudaMemcpyAsync(pos, dp, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, B->stream));
+    if (vel) CK(cudaMemcpyAsync(vel, dv, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, B->stream));
+    if (rot) CK(cudaMemcpyAsync(rot, dr, 9 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, B->stream));
+    if (ang_mom) CK(cudaMemcpyAsync(ang_mom, dl, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, B->stream));
+    CK(cudaStreamSynchronize(B->stream));
+    return PS_OK;
+}
+
+int ps_batch_set_state(void* handle, int32_t w0, int32_t w1, const double* pos, const double* vel, const double* rot,
+                       const double* ang_mom)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    int rc = check_range(B, w0, w1);
+    if (rc) return rc;
+    if (!pos || !vel || !rot || !ang_mom) return fail(PS_ERR_INVALID_ARGUMENT, "state array is null");
+    CK(cudaSetDevice(B->device));
+    int b0 = B->cur.off[w0], n = B->cur.off[w1] - b0;
+    if (n == 0) return PS_OK;
+    double* sp = B->d_stage + (size_t)b0 * kDynF;
+    double *dp = sp, *dv = sp + 3 * (size_t)n, *dr = sp + 6 * (size_t)n, *dl = sp + 15 * (size_t)n;
+    CK(cudaMemcpyAsync(dp, pos, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, B->stream));
+    CK(cudaMemcpyAsync(dv, vel, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, B->stream));
+    CK(cudaMemcpyAsync(dr, rot, 9 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, B->stream));
+    CK(cudaMemcpyAsync(dl, ang_mom, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, B->stream));
+    pack_dyn_kernel<<<(n + 255) / 256, 256, 0, B->stream>>>(B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn, b0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(B->stream));
+    return PS_OK;
+}
+
+int ps_batch_get_contacts(void* handle, int32_t world, int32_t* n_pairs, int32_t* pair_ids, int32_t* first_contact,
+                          double* normal, double* position, double* penetration, uint32_t* feature_id, int32_t pair_capacity,
+                          int32_t contact_capacity)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    if (world < 0 || world >= B->n_worlds) return fail(PS_ERR_OUT_OF_RANGE, "world %d outside [0,%d)", world, B->n_worlds);
+    if (!B->d_rec_pairs) return fail(PS_ERR_INVALID_OPERATION, "batch was created with record_contacts = 0");
+    if (!n_pairs) return fail(PS_ERR_INVALID_ARGUMENT, "n_pairs is null");
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    int cnt[2];
+    CK(cudaMemcpy(cnt, B->d_rec_counts + 2 * world, sizeof cnt, cudaMemcpyDeviceToHost));
+    if (cnt[0] > B->rec_pair_cap || cnt[1] > B->rec_contact_cap)
+        return fail(PS_ERR_CAPACITY, "world %d: %d pairs / %d contacts exceed the recording capacity (%d / %d)", world, cnt[0], cnt[1],
+                    B->rec_pair_cap, B->rec_contact_cap);
+    *n_pairs = cnt[0];
+    if (cnt[0] > pair_capacity || cnt[1] > contact_capacity)
+        return fail(PS_ERR_CAPACITY, "need room for %d pairs and %d contacts", cnt[0], cnt[1]);
+    std::vector<RecPair> rp(cnt[0]);
+    std::vector<RecContact> rcs(cnt[1]);
+    if (cnt[0]) CK(cudaMemcpy(rp.data(), B->d_rec_pairs + (size_t)world * B->rec_pair_cap, cnt[0] * sizeof(RecPair), cudaMemcpyDeviceToHost));
+    if (cnt[1]) CK(cudaMemcpy(rcs.data(), B->d_rec_contacts + (size_t)world * B->rec_contact_cap, cnt[1] * sizeof(RecContact), cudaMemcpyDeviceToHost));
+    // Collisions is a Map keyed by the id set: ascending (i,j) (CollisionResolver.fs:33-34)
+    std::sort(rp.begin(), rp.end(), [](const RecPair& x, const RecPair& y) { return x.i != y.i ? x.i < y.i : x.j < y.j; });
+    int c = 0;
+    for (int k = 0; k < cnt[0]; k++) {
+        if (pair_ids) { pair_ids[2 * k] = rp[k].i; pair_ids[2 * k + 1] = rp[k].j; }
+        if (first_contact) first_contact[k] = c;
+        for (int q = 0; q < rp[k].count; q++, c++) {
+            const RecContact& r = rcs[rp[k].first + q];
+            if (normal) for (int t = 0; t < 3; t++) normal[3 * c + t] = r.n[t];
+            if (position) for (int t = 0; t < 3; t++) position[3 * c + t] = r.p[t];
+            if (penetration) penetration[c] = r.pen;
+            if (feature_id) feature_id[c] = r.feat;
+        }
+    }
+    if (first_contact) first_contact[cnt[0]] = c;
+    return PS_OK;
+}
+
+int ps_batch_get_candidates(void* handle, int32_t world, int32_t* n_pairs, int32_t* pair_ids, int32_t pair_capacity)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    if (world < 0 || world >= B->n_worlds) return fail(PS_ERR_OUT_OF_RANGE, "world %d outside [0,%d)", world, B->n_worlds);
+    // Dummy order (BroadPhase.fs:33-39) filtered by canIntersect (CollisionResolver.fs:58-60): a function of
+    // the body set only, so it is produced here from the static flags.
+    int o = B->cur.off[world], N = B->cur.off[world + 1] - o;
+    int n = 0;
+    for (int i = 0; i < N; i++)
+        for (int j = i + 1; j < N; j++) {
+            if (std::isinf(B->cur.mass[o + i]) && std::isinf(B->cur.mass[o + j])) continue;
+            if (pair_ids && n < pair_capacity) { pair_ids[2 * n] = i; pair_ids[2 * n + 1] = j; }
+            n++;
+        }
+    if (n_pairs) *n_pairs = n;
+    if (pair_ids && n > pair_capacity) return fail(PS_ERR_CAPACITY, "need room for %d pairs", n);
+    return PS_OK;
+}
+
+int ps_batch_apply_impulse(void* handle, int32_t world, int32_t body, const double impulse[3], const double offset[3])
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    if (world < 0 || world >= B->n_worlds) return fail(PS_ERR_OUT_OF_RANGE, "world %d outside [0,%d)", world, B->n_worlds);
+    int N = B->cur.off[world + 1] - B->cur.off[world];
+    if (body < 0 || body >= N) return fail(PS_ERR_OUT_OF_RANGE, "body %d outside [0,%d)", body, N);  // KeyNotFoundException
+    if (!impulse || !offset) return fail(PS_ERR_INVALID_ARGUMENT, "impulse/offset is null");
+    CK(cudaSetDevice(B->device));
+    apply_impulse_kernel<<<1, 1, 0, B->stream>>>(B->d_dyn, B->d_par, B->d_off, world, body, impulse[0], impulse[1], impulse[2],
+                                                 offset[0], offset[1], offset[2]);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(B->stream));
+    return PS_OK;
+}
+
+int ps_batch_add_body(void* handle, int32_t world, const ps_bodies_view* one)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    if (world < 0 || world >= B->n_worlds) return fail(PS_ERR_OUT_OF_RANGE, "world %d outside [0,%d)", world, B->n_worlds);
+    int rc = check_view(one);
+    if (rc) return rc;
+    if (one->n_worlds != 1 || one->world_offset[1] != 1) return fail(PS_ERR_INVALID_ARGUMENT, "add_body takes exactly one body");
+    HostBodies nb;
+    copy_view(nb, one);
+    rc = validate_bodies(nb);
+    if (rc) return rc;
+    // pull the live state, splice the body in as id = max id + 1 of that world (SimulatorState.fs:90-92), re-upload
+    HostBodies& h = B->cur;
+    rc = ps_batch_get_state(B, 0, B->n_worlds, h.pos.data(), h.vel.data(), h.rot.data(), h.L.data());
+    if (rc) return rc;
+    int at = h.off[world + 1];
+    auto ins = [&](std::vector<double>& dst, const std::vector<double>& src, int per) { dst.insert(dst.begin() + (size_t)per * at, src.begin(), src.end()); };
+    h.shape.insert(h.shape.begin() + at, nb.shape[0]);
+    ins(h.dims, nb.dims, 3); ins(h.mass, nb.mass, 1); ins(h.iinv, nb.iinv, 3); ins(h.pos, nb.pos, 3); ins(h.vel, nb.vel, 3);
+    ins(h.rot, nb.rot, 9); ins(h.L, nb.L, 3); ins(h.force, nb.force, 3); ins(h.torque, nb.torque, 3); ins(h.e, nb.e, 1);
+    ins(h.muk, nb.muk, 1); ins(h.mus, nb.mus, 1);
+    for (int w = world + 1; w <= B->n_worlds; w++) h.off[w]++;
+    std::vector<WorldStats> keep(B->n_worlds);
+    CK(cudaMemcpy(keep.data(), B->d_stats, keep.size() * sizeof(WorldStats), cudaMemcpyDeviceToHost));
+    rc = upload(B, true);
+    if (rc) return rc;
+    CK(cudaMemcpy(B->d_stats, keep.data(), keep.size() * sizeof(WorldStats), cudaMemcpyHostToDevice));
+    return PS_OK;
+}
+
+int ps_batch_reset(void* handle)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    B->cur = B->init;  // bodies added later are dropped (Simulator.fs:36-40,113-121)
+    return upload(B, true);
+}
+
+int ps_batch_stats(void* handle, ps_stats* out)
+{
+    if (!handle || !out) return fail(PS_ERR_INVALID_ARGUMENT, "handle/out is null");
+    Batch* B = (Batch*)handle;
+    CK(cudaSetDevice(B->device));
+    CK(cudaMemsetAsync(B->d_stats_sum, 0, sizeof(ps_stats), B->stream));
+    if (B->n_worlds > 0) {
+        int blocks = std::min(64, (B->n_worlds + 127) / 128);
+        stats_reduce_kernel<<<blocks, 128, 0, B->stream>>>(B->d_stats, B->d_off, B->d_par, B->n_worlds, B->d_stats_sum);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(out, B->d_stats_sum, sizeof(ps_stats), cudaMemcpyDeviceToHost, B->stream));
+    CK(cudaStreamSynchronize(B->stream));
+    return PS_OK;
+}
+
+int ps_batch_num_bodies(void* handle, int32_t* n_bodies_total, int32_t* n_dynamic_total)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    if (n_bodies_total) *n_bodies_total = B->n_bodies;
+    if (n_dynamic_total) *n_dynamic_total = B->n_dynamic;
+    return PS_OK;
+}
+
+}  // extern "C"

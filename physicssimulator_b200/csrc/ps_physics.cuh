@@ -1,0 +1,617 @@
+// ps_physics.cuh — per-body and per-pair device routines of the step:
+// integration, narrow phase (sphere/sphere, sphere/box, box/box SAT + clipping), and the
+// per-pair sequential-impulse solve with friction.  One thread runs one body or one pair.
+//
+// These follow the reference's discrete decisions and floating-point operation order exactly
+// (first-wins arg-min/arg-max, reverse contact order, MathNet scalar special cases ...), so that
+// candidate sets, contact features and states match the CPU restatement bit for bit.
+//
+// Citations are relative to /root/reference/PhysicsSimulatorCore/.
+#pragma once
+#include "../../include/ps_b200.h"
+#include "ps_math.cuh"
+
+namespace psp {
+using namespace psm;
+
+// step parameters in kernel-argument form
+struct StepParams {
+    double eps, baumgarte, slop, max_corr, dt;
+    int iterations, friction, integrator;
+};
+
+// dynamic state of one body: 18 doubles (Entities/RigidBody.fs:6-8, Entities/Particle.fs:8-10)
+struct Dyn {
+    d3 x, v;
+    m33 R;
+    d3 L;
+};
+// constant parameters of one body (16 doubles in HBM)
+struct Par {
+    double inv_mass;  // 1.0 / mass (0 for +inf): what `v / mass` multiplies by (Vector3D.fs:34)
+    double iinv[3];
+    d3 F, T;
+    double e, mu;
+    double dims[3];
+    int shape;  // 0 sphere, 1 box
+    bool is_static;
+};
+
+struct Contact {
+    d3 n, p;
+    double pen;
+    uint32_t feat;
+};
+
+// Box.fs:23-49 tables.  Vertex k = (sx, sy, sz) signs; kept as bit masks: bit2 = +x, bit1 = +y, bit0 = +z.
+// V = (---)(-+-)(++-)(+--)(--+)(-++)(+++)(+-+)
+PS_TABLE unsigned char kVertSign[8] = {0, 2, 6, 4, 1, 3, 7, 5};
+PS_TABLE unsigned char kFaceVert[6][4] = {{0, 1, 2, 3}, {7, 6, 5, 4}, {5, 6, 2, 1},
+                                                               {0, 3, 7, 4}, {6, 7, 3, 2}, {4, 5, 1, 0}};
+// distinct-vertex order of OrientedBox.Vertices (OrientedBox.fs:25): faces 0 and 1 already cover all 8
+PS_TABLE unsigned char kDistinctVert[8] = {0, 1, 2, 3, 7, 6, 5, 4};
+// face normal k = sign * e_axis
+PS_TABLE signed char kFaceAxis[6] = {2, 2, 1, 1, 0, 0};
+PS_TABLE signed char kFaceSign[6] = {-1, 1, 1, -1, 1, -1};
+
+// ----------------------------------------------------------------------------------------
+// Integration (RigidBody.fs:202-220 -> Particle.fs:25-30 + RigidBody.fs:142-190)
+// ----------------------------------------------------------------------------------------
+PSD void integrate(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o)
+{
+    const double dt = sp.dt;
+    d3 acc = scale(p.inv_mass, p.F);       // RigidBody.fs:210  totalForce / mass
+    d3 nv = b.v + scale(dt, acc);          // Particle.fs:27
+    o.x = b.x + scale(dt, nv);             // Particle.fs:29
+    o.v = nv;
+    m33 Iw = inertia_inv_world(b.R, p.iinv);  // RigidBody.fs:216 (old orientation)
+    d3 dL = scale(dt, p.T);
+    d3 axis;
+    if (sp.integrator == 0) {              // firstOrder :142-160
+        d3 nL = b.L + dL;
+        axis = scale(dt, mulMV(Iw, nL));
+        o.L = nL;
+    } else {                               // augmentedSecondOrder :162-190
+        d3 w = mulMV(Iw, b.L);
+        d3 vv = cross(w, b.L);             // L |> crossProduct w  = w x L
+        d3 deriv = mulMV(Iw, p.T - vv);
+        d3 comp1 = cross(deriv, w);        // w |> crossProduct deriv = deriv x w
+        d3 avg = (w + scale(dt * 0.5, deriv)) + scale(dt * dt / 12.0, comp1);
+        axis = scale(dt, avg);
+        o.L = b.L + dL;
+    }
+    double angle = norm(axis);
+    m33 rot = from_axis_angle(normalize(axis), angle);
+    o.R = orthonormalize(mulMM(rot, b.R));
+}
+
+// ----------------------------------------------------------------------------------------
+// Oriented box in world space (OrientedBox.fs:10-27 over Box.fs:100-111)
+// ----------------------------------------------------------------------------------------
+struct OBox {
+    d3 v[8];  // world vertices, Box.fs:23-32 index
+    d3 n[6];  // world face normals
+};
+PSD void make_obox(const Dyn& b, const Par& p, OBox& ob)
+{
+    double hx = p.dims[0] / 2.0, hy = p.dims[1] / 2.0, hz = p.dims[2] / 2.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned s = kVertSign[k];
+        // PointwiseMultiply of (+-1,+-1,+-1) by the half sizes: exact
+        d3 local = mk((s & 4) ? hx : -hx, (s & 2) ? hy : -hy, (s & 1) ? hz : -hz);
+        ob.v[k] = mulMV(b.R, local) + b.x;  // toWorldCoordinates (GraphicsUtils.fs:109-110)
+    }
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+        int ax = kFaceAxis[f];
+        double sg = (double)kFaceSign[f];
+        d3 local = mk(ax == 0 ? sg : 0.0, ax == 1 ? sg : 0.0, ax == 2 ? sg : 0.0);
+        ob.n[f] = mulMV(b.R, local) + mk(0.0, 0.0, 0.0);
+    }
+}
+PSD d3 face_vertex(const OBox& ob, int f, int k) { return ob.v[kFaceVert[f][k]]; }
+
+// min/max of the 8 vertex projections in OrientedBox.Vertices order (ties keep the first, values only)
+PSD void project_box(const OBox& ob, d3 axis, double& mn, double& mx)
+{
+    double p0 = dot(axis, ob.v[0]);
+    mn = p0;
+    mx = p0;
+#pragma unroll
+    for (int k = 1; k < 8; k++) {
+        double p = dot(axis, ob.v[kDistinctVert[k]]);
+        if (p < mn) mn = p;
+        if (p > mx) mx = p;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// GraphicsUtils (Utilities/GraphicsUtils.fs)
+// ----------------------------------------------------------------------------------------
+PSD d3 closest_on_edge(d3 a, d3 b, d3 pos)  // :9-24
+{
+    d3 ap = pos - a, ab = b - a;
+    double t = dot(ab, ap) / dot(ab, ab);
+    t = fmax_net(0.0, fmin_net(1.0, t));
+    return a + scale(t, ab);
+}
+PSD d3 closest_on_quad(d3 pos, const d3 q[4])  // :26-37, edges (last,first),(0,1),(1,2),(2,3); first min
+{
+    d3 best = closest_on_edge(q[3], q[0], pos);
+    d3 d = pos - best;
+    double bd = dot(d, d);
+#pragma unroll
+    for (int k = 1; k < 4; k++) {
+        d3 c = closest_on_edge(q[k - 1], q[k], pos);
+        d3 e = pos - c;
+        double dd = dot(e, e);
+        if (dd < bd) {
+            bd = dd;
+            best = c;
+        }
+    }
+    return best;
+}
+PSD bool plane_edge_hit(double eps, d3 pn, double pd, d3 s, d3 e, d3& out)  // :41-63
+{
+    d3 ab = e - s;
+    double ab_p = dot(pn, ab);
+    if (fabs(ab_p) > eps) {
+        d3 p_co = scale(pd, pn);
+        double fac = -(dot(pn, s - p_co)) / ab_p;
+        fac = fmin_net(fmax_net(fac, 0.0), 1.0);
+        out = s + scale(fac, ab);
+        return true;
+    }
+    return false;
+}
+PSD bool in_plane(d3 pn, double pd, d3 p) { return (dot(pn, p) - pd) >= 0.0; }  // :65-66
+PSD void tangents(d3 n, d3& t1, d3& t2)  // :112-123
+{
+    double v = sqrt(1.0 / 3.0);
+    d3 t = (fabs(n.x) >= v) ? mk(n.y, n.x, 0.0) : mk(0.0, n.z, -n.y);
+    t1 = normalize(t);
+    t2 = cross(n, t1);
+}
+
+// ----------------------------------------------------------------------------------------
+// Narrow phase
+// ----------------------------------------------------------------------------------------
+// detectSphereSphereCollision (CollisionDetection.fs:186-205)
+PSD int detect_ss(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, Contact* out)
+{
+    d3 d = b1.x - b2.x;
+    double dist = norm(d);
+    double r1 = p1.dims[0], r2 = p2.dims[0];
+    if (dist > r1 + r2) return 0;
+    d3 n = normalize(d);
+    d3 cp1 = b1.x + scale(r1, -n);
+    d3 cp2 = b2.x + scale(r2, n);
+    d3 cp = cp1 + scale(1.0 / 2.0, cp2 - cp1);
+    out[0].n = n;
+    out[0].p = cp;
+    out[0].pen = norm(cp1 - cp2);
+    out[0].feat = 0u;
+    return 1;
+}
+
+// SAT.SphereBox.tryFindSeparatingAxis (SAT.fs:108-151) + detectedSphereBoxCollision
+// (CollisionDetection.fs:166-184). Normal returned "from box". err set where the reference throws.
+PSD int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Par& bp, double eps, Contact* out,
+                          int& face, int& err)
+{
+    OBox ob;
+    make_obox(bb, bp, ob);
+    double r = sp_.dims[0];
+    double best_pen = 0.0;
+    int best = -1;
+    for (int f = 0; f < 6; f++) {
+        d3 axis = ob.n[f];
+        double a, b;
+        project_box(ob, axis, a, b);
+        double c = dot(axis, sb.x);
+        double cp = c + r, cm = c - r;
+        double c1 = (cm < cp) ? cm : cp;  // List.min [c+r; c-r]
+        double c2 = (cm > cp) ? cm : cp;  // List.max
+        double pen;
+        if (c1 >= a && c1 <= b)
+            pen = b - c1;
+        else if (c1 <= a && c2 >= a)
+            pen = c2 - a;
+        else
+            return 0;
+        if (best < 0 || pen < best_pen) {
+            best = f;
+            best_pen = pen;
+        }
+    }
+    d3 nb = ob.n[best];
+    d3 endP = sb.x - scale(r, nb);
+    double pd = dot(nb, face_vertex(ob, best, 0));  // Face.toPlane (Entities/Base.fs:27-29)
+    d3 pos;
+    if (!plane_edge_hit(eps, nb, pd, sb.x, endP, pos)) {
+        err = 1;  // Option.get of None
+        return 0;
+    }
+    out[0].n = nb;
+    out[0].p = pos;
+    out[0].pen = best_pen;
+    face = best;
+    return 1;
+}
+
+// SAT.tryGetCollisionDataForAxis (SAT.fs:155-183) on precomputed projection ranges
+PSD bool sat_ranges(double a, double b, double c, double d, double& pen, bool& flip)
+{
+    if (a <= c && b >= c) {
+        pen = b - c;
+        flip = false;
+        return true;
+    }
+    if (c <= a && d >= a) {
+        pen = d - a;
+        flip = true;
+        return true;
+    }
+    return false;
+}
+
+struct PolyV {
+    d3 p;
+    unsigned tag;
+};
+
+// detectBoxBoxCollision (CollisionDetection.fs:29-164) over SAT.tryFindSeparatingAxis (SAT.fs:206-240)
+// returns #contacts (0 = none); overflow set when the manifold would exceed PS_MAX_CONTACTS
+PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+                  int& overflow)
+{
+    OBox o1, o2;
+    make_obox(b1, p1, o1);
+    make_obox(b2, p2, o2);
+
+    int best_origin = -1, best_i = 0, best_j = 0;
+    double best_pen = 0.0;
+    d3 best_n = mk(0, 0, 0);
+
+    // Face1: axes = normals of box 1, target = box 1 (SAT.fs:230-231)
+    for (int f = 0; f < 6; f++) {
+        d3 axis = o1.n[f];
+        double a, b, c, d, pen;
+        bool flip;
+        project_box(o1, axis, a, b);
+        project_box(o2, axis, c, d);
+        if (!sat_ranges(a, b, c, d, pen, flip)) return 0;
+        if (best_origin < 0 || pen < best_pen) {
+            best_origin = 0;
+            best_pen = pen;
+            best_n = flip ? -axis : axis;
+        }
+    }
+    // Face2: axes = normals of box 2, target = box 2 (boxes flipped, :233-234)
+    for (int f = 0; f < 6; f++) {
+        d3 axis = o2.n[f];
+        double a, b, c, d, pen;
+        bool flip;
+        project_box(o2, axis, a, b);
+        project_box(o1, axis, c, d);
+        if (!sat_ranges(a, b, c, d, pen, flip)) return 0;
+        if (pen < best_pen) {
+            best_origin = 1;
+            best_pen = pen;
+            best_n = flip ? -axis : axis;
+        }
+    }
+    // Edge axes (:218-226): RigidBody.Axes = normalize(R e_k + 0) (RigidBody.fs:34-41)
+    d3 ax1[3], ax2[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        ax1[k] = normalize(mk(b1.R.a[k], b1.R.a[3 + k], b1.R.a[6 + k]) + mk(0.0, 0.0, 0.0));
+        ax2[k] = normalize(mk(b2.R.a[k], b2.R.a[3 + k], b2.R.a[6 + k]) + mk(0.0, 0.0, 0.0));
+    }
+    d3 fromFirst = b2.x - b1.x;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            d3 e = normalize(cross(ax2[j], ax1[i]));  // firstAxis |> crossProduct secondAxis = second x first
+            if (near_eq(0.01, 0.0, norm(e))) continue;  // isZero 0.01
+            if (dot(e, fromFirst) < 0.0) e = -e;
+            double a, b, c, d, pen;
+            bool flip;
+            project_box(o1, e, a, b);
+            project_box(o2, e, c, d);
+            if (!sat_ranges(a, b, c, d, pen, flip)) return 0;
+            if (pen < best_pen) {
+                best_origin = 2;
+                best_pen = pen;
+                best_n = flip ? -e : e;
+                best_i = i;
+                best_j = j;
+            }
+        }
+
+    if (best_origin < 2) {
+        // generateFaceContactPoints (CollisionDetection.fs:30-73)
+        const OBox& ref = (best_origin == 0) ? o1 : o2;
+        const OBox& oth = (best_origin == 0) ? o2 : o1;
+        d3 normal = best_n;
+        int rf = -1;
+        for (int f = 0; f < 6; f++)
+            if (veq(ref.n[f], normal)) {  // Box.findFaceByNormal (Box.fs:113-114)
+                rf = f;
+                break;
+            }
+        if (rf < 0) {
+            err = 1;
+            return 0;
+        }
+        d3 rn = ref.n[rf];
+        int inc = 0;
+        double incv = dot(rn, oth.n[0]);
+        for (int f = 1; f < 6; f++) {  // findIncidentFace: first min (:35-37)
+            double d = dot(rn, oth.n[f]);
+            if (d < incv) {
+                incv = d;
+                inc = f;
+            }
+        }
+        // clip the incident quad by the inverted planes of the adjacent faces (Box.fs:116-124, :56-61)
+        PolyV bufA[PS_MAX_CONTACTS + 4], bufB[PS_MAX_CONTACTS + 4];
+        PolyV* cur = bufA;
+        PolyV* nxt = bufB;
+        int n = 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            cur[k].p = face_vertex(oth, inc, k);
+            cur[k].tag = (unsigned)k;
+        }
+        int pi = 0;
+        for (int f = 0; f < 6; f++) {
+            double ad = fabs(dot(rn, ref.n[f]));
+            if (near_eq(eps, 1.0, ad)) continue;  // not adjacent
+            if (n == 0) break;  // "clipping error": the reference prints and returns the empty list
+            d3 pn = -ref.n[f];                                   // Plane.inverted
+            double pd = -dot(ref.n[f], face_vertex(ref, f, 0));  // Face.toPlane then inverted
+            int m = 0;
+            for (int k = 0; k < n; k++) {
+                const PolyV& s = (k == 0) ? cur[n - 1] : cur[k - 1];
+                const PolyV& e = cur[k];
+                bool sin_ = in_plane(pn, pd, s.p), ein = in_plane(pn, pd, e.p);
+                unsigned xtag = 0x80u | ((unsigned)(pi & 3) << 4) | (unsigned)(k & 15);
+                d3 x;
+                if (sin_ && ein) {
+                    if (m < PS_MAX_CONTACTS + 4) nxt[m++] = e; else overflow = 1;
+                } else if (sin_ && !ein) {
+                    if (plane_edge_hit(eps, pn, pd, s.p, e.p, x)) {
+                        if (m < PS_MAX_CONTACTS + 4) { nxt[m].p = x; nxt[m].tag = xtag; m++; } else overflow = 1;
+                    }
+                } else if (!sin_ && ein) {
+                    if (m < PS_MAX_CONTACTS + 4) nxt[m++] = e; else overflow = 1;
+                    if (plane_edge_hit(eps, pn, pd, s.p, e.p, x)) {
+                        if (m < PS_MAX_CONTACTS + 4) { nxt[m].p = x; nxt[m].tag = xtag; m++; } else overflow = 1;
+                    }
+                }
+            }
+            PolyV* t = cur; cur = nxt; nxt = t;
+            n = m;
+            pi++;
+        }
+        // List.distinct, then keep points on/below the reference plane (:52-54), then contacts (:63-67)
+        d3 refq[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) refq[k] = face_vertex(ref, rf, k);
+        d3 rpn = -rn;
+        double rpd = -dot(rn, refq[0]);
+        int nc = 0;
+        for (int k = 0; k < n; k++) {
+            bool dup = false;
+            for (int q = 0; q < k; q++)
+                if (veq(cur[q].p, cur[k].p)) {
+                    dup = true;
+                    break;
+                }
+            if (dup) continue;
+            if (!in_plane(rpn, rpd, cur[k].p)) continue;
+            if (nc >= PS_MAX_CONTACTS) {
+                overflow = 1;
+                break;
+            }
+            d3 cl = closest_on_quad(cur[k].p, refq);
+            out[nc].pen = dot(normal, cur[k].p - cl);
+            out[nc].n = (best_origin == 1) ? -normal : normal;  // WithInvertedNormals (:157)
+            out[nc].p = cur[k].p;
+            out[nc].feat = 3u | ((unsigned)best_origin << 2) | ((unsigned)rf << 4) | ((unsigned)inc << 7) |
+                           ((unsigned)(nc & 31) << 10) | (cur[k].tag << 15);
+            nc++;
+        }
+        return nc;
+    }
+
+    // generateEdgeContactPoints (CollisionDetection.fs:75-132)
+    d3 normal = best_n;
+    d3 ea[2], eb[2];
+    int eidx[2];
+    for (int side = 0; side < 2; side++) {
+        const OBox& ob = side == 0 ? o1 : o2;
+        d3 axis = side == 0 ? ax1[best_i] : ax2[best_j];
+        d3 nrm = side == 0 ? normal : -normal;
+        bool have = false;
+        double bestv = 0.0;
+        int idx = 0;
+        // OrientedBox.getEdges: faces 0..5, per face (v3,v0),(v0,v1),(v1,v2),(v2,v3); List.distinct on
+        // ordered pairs — every directed edge of a non-degenerate box appears once, so index = 4*f+k.
+        for (int f = 0; f < 6; f++)
+            for (int k = 0; k < 4; k++) {
+                d3 a = face_vertex(ob, f, (k + 3) & 3), b = face_vertex(ob, f, k);
+                d3 dd = b - a;
+                if (!near_eq(eps, 0.0, norm(cross(dd, axis)))) continue;  // areParallel: axis |> crossProduct d = d x axis
+                double pa = dot(nrm, a), pb = dot(nrm, b);
+                double key = (pb > pa) ? pb : pa;
+                if (!have || key > bestv) {
+                    have = true;
+                    bestv = key;
+                    idx = 4 * f + k;
+                    ea[side] = a;
+                    eb[side] = b;
+                }
+            }
+        if (!have) {
+            err = 1;  // List.maxBy on an empty list
+            return 0;
+        }
+        eidx[side] = idx;
+    }
+    d3 DA = eb[0] - ea[0], DB = eb[1] - ea[1];
+    d3 r = ea[0] - ea[1];
+    double a = dot(DA, DA), e = dot(DB, DB), f = dot(DB, r), c = dot(DA, r), b = dot(DA, DB);
+    double denom = a * e - b * b;
+    double TA = (b * f - c * e) / denom;
+    double TB = (b * TA + f) / e;
+    d3 CA = ea[0] + scale(TA, DA);
+    d3 CB = ea[1] + scale(TB, DB);
+    out[0].n = normal;
+    out[0].p = scale(0.5, CA) + scale(0.5, CB);
+    out[0].pen = -best_pen;
+    out[0].feat = 3u | (2u << 2) | ((unsigned)best_i << 4) | ((unsigned)best_j << 7) | ((unsigned)eidx[0] << 10) |
+                  ((unsigned)eidx[1] << 15);
+    return 1;
+}
+
+// CollisionDetection.areColliding (CollisionDetection.fs:208-220)
+PSD int detect(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+               int& overflow)
+{
+    if (p1.shape == 0 && p2.shape == 0) return detect_ss(b1, p1, b2, p2, out);
+    if (p1.shape == 1 && p2.shape == 1) return detect_bb(b1, p1, b2, p2, eps, out, err, overflow);
+    int face = 0;
+    if (p1.shape == 0) {
+        int n = detect_sphere_box(b1, p1, b2, p2, eps, out, face, err);
+        if (n) {
+            out[0].n = -out[0].n;  // WithInvertedNormals (:217-219)
+            out[0].feat = 1u | ((unsigned)face << 4);
+        }
+        return n;
+    }
+    int n = detect_sphere_box(b2, p2, b1, p1, eps, out, face, err);
+    if (n) out[0].feat = 2u | ((unsigned)face << 4);
+    return n;
+}
+
+// ----------------------------------------------------------------------------------------
+// Per-pair solve (CollisionResponse.fs:73-146, ContactPointImpulseData.fs:23-66, Friction.fs:39-68)
+// ----------------------------------------------------------------------------------------
+struct CPData {
+    d3 r1, r2;
+    double bias, mN, mT0, mT1, accN, accT0, accT1;
+};
+
+// hat(r)^T * Iw * hat(r), products evaluated as dense 3x3 (RigidBody.fs:225-229)
+PSD m33 hat(d3 v)
+{
+    m33 o;
+    o.a[0] = 0.0;  o.a[1] = -v.z; o.a[2] = v.y;
+    o.a[3] = v.z;  o.a[4] = 0.0;  o.a[5] = -v.x;
+    o.a[6] = -v.y; o.a[7] = v.x;  o.a[8] = 0.0;
+    return o;
+}
+PSD m33 transpose(const m33& m)
+{
+    m33 o;
+    o.a[0] = m.a[0]; o.a[1] = m.a[3]; o.a[2] = m.a[6];
+    o.a[3] = m.a[1]; o.a[4] = m.a[4]; o.a[5] = m.a[7];
+    o.a[6] = m.a[2]; o.a[7] = m.a[5]; o.a[8] = m.a[8];
+    return o;
+}
+PSD void add_K(m33& s, const Par& p, const m33& Iw, d3 r)
+{
+    if (p.is_static) {  // Mass.Infinite -> Matrix3.zero: s + 0
+#pragma unroll
+        for (int k = 0; k < 9; k++) s.a[k] = s.a[k] + 0.0;
+        return;
+    }
+    m33 h = hat(r);
+    m33 t = mulMM(mulMM(transpose(h), Iw), h);
+    t.a[0] = t.a[0] + p.inv_mass;
+    t.a[4] = t.a[4] + p.inv_mass;
+    t.a[8] = t.a[8] + p.inv_mass;
+#pragma unroll
+    for (int k = 0; k < 9; k++) s.a[k] = s.a[k] + t.a[k];
+}
+// RigidBodyMotion.applyImpulse (RigidBody.fs:194-197)
+PSD void apply_impulse(Dyn& b, const Par& p, d3 off, d3 P)
+{
+    b.v = b.v + scale(p.inv_mass, P);
+    b.L = b.L + cross(off, P);
+}
+PSD d3 velocity_at(const Dyn& b, const m33& Iw, d3 off) { return b.v + cross(mulMV(Iw, b.L), off); }
+
+// resolves one pair in place; b1/b2 are the predicted bodies
+PSD void resolve(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* cs, int nc, CPData* cp,
+                 const StepParams& sp)
+{
+    // orientation is constant during the solve, so R Ip^-1 R^T is evaluated once per body (exact)
+    m33 Iw1 = inertia_inv_world(b1.R, p1.iinv);
+    m33 Iw2 = inertia_inv_world(b2.R, p2.iinv);
+    d3 t0, t1;
+    tangents(cs[0].n, t0, t1);  // CollisionResponse.fs:80-81
+    for (int k = 0; k < nc; k++) {
+        CPData d;
+        d.bias = fmin_net(sp.max_corr, -sp.baumgarte / sp.dt * fmin_net(0.0, cs[k].pen + sp.slop));  // :35-41
+        d.r1 = cs[k].p - b1.x;
+        d.r2 = cs[k].p - b2.x;
+        m33 K;
+#pragma unroll
+        for (int q = 0; q < 9; q++) K.a[q] = 0.0;
+        add_K(K, p1, Iw1, d.r1);
+        add_K(K, p2, Iw2, d.r2);
+        d.mN = dot(cs[k].n, mulMV(K, cs[k].n));
+        d.mT0 = dot(t0, mulMV(K, t0));
+        d.mT1 = dot(t1, mulMV(K, t1));
+        d.accN = 0.0;
+        d.accT0 = 0.0;
+        d.accT1 = 0.0;
+        cp[k] = d;
+    }
+    const double e = fmin_net(p1.e, p2.e);
+    const double mu = fmax_net(p2.mu, p1.mu);
+    const double inf = from_bits(0x7ff0000000000000LL);
+    for (int it = 0; it < sp.iterations; it++) {
+        for (int k = nc - 1; k >= 0; k--) {  // List.foldBack: reverse order
+            CPData d = cp[k];
+            d3 n = cs[k].n;
+            d3 P;
+            if (d.mN == 0.0) {
+                P = mk(0.0, 0.0, 0.0);
+            } else {
+                d3 vrel = velocity_at(b2, Iw2, d.r2) - velocity_at(b1, Iw1, d.r1);
+                double vn = dot(vrel, n);
+                double j = (-(e + 1.0) * vn + d.bias) / d.mN;
+                double old = d.accN;
+                d.accN = clamp_net(0.0, inf, old + j);
+                P = scale(-(d.accN - old), n);
+            }
+            apply_impulse(b1, p1, d.r1, P);
+            apply_impulse(b2, p2, d.r2, -P);
+            if (sp.friction) {
+                d3 vrel = velocity_at(b2, Iw2, d.r2) - velocity_at(b1, Iw1, d.r1);
+                double maxF = mu * d.accN;
+                double j0 = dot(t0, vrel) / d.mT0;
+                double j1 = dot(t1, vrel) / d.mT1;
+                double o0 = d.accT0, o1 = d.accT1;
+                d.accT0 = clamp_net(-maxF, maxF, o0 + j0);
+                d.accT1 = clamp_net(-maxF, maxF, o1 + j1);
+                d3 P0 = scale(d.accT0 - o0, t0);
+                d3 P1 = scale(d.accT1 - o1, t1);
+                apply_impulse(b1, p1, d.r1, P0);
+                apply_impulse(b1, p1, d.r1, P1);
+                apply_impulse(b2, p2, d.r2, -P0);
+                apply_impulse(b2, p2, d.r2, -P1);
+            }
+            cp[k].accN = d.accN;
+            cp[k].accT0 = d.accT0;
+            cp[k].accT1 = d.accT1;
+        }
+    }
+}
+
+}  // namespace psp

@@ -1,0 +1,594 @@
+// ps_step_kernel.cuh — the fused per-world step kernel (block per world).
+//
+// One CTA owns one world for n_steps steps; the world's state lives in shared memory for the
+// whole launch (HBM is touched once per step to publish the state, which doubles as the
+// restart point of the exact fallback).
+//
+// Per step (reference order: Simulator.fs:52-56 = resolveAll (CollisionResolver.fs:49-69) then
+// SimulatorState.update (SimulatorState.fs:169-173)):
+//   A  per body : cull sphere (bounding radius + motion margin) from the step-start pose
+//   B  per row  : conservative cull of the Dummy-order pair list (BroadPhase.fs:33-39) -> ordered
+//                 near list in shared memory (block scan keeps lexicographic order)
+//   C  thread 0 : wavefront level of every near pair (a pair waits for the previous near pair of
+//                 either of its dynamic bodies); the other warps integrate every body once
+//                 (the "predicted" copy, CollisionResolver.fs:42-43) meanwhile
+//   D  per level: one thread per pair: (re-integrate a body an earlier pair changed) -> narrow
+//                 phase -> N-iteration solve -> write back (CollisionResolver.fs:13-38)
+//   E  per static body: fold the angular-momentum sums of its pairs in pair order
+//   J  joints (off by default, Simulator.fs:55)
+//   F  per body : final integration (a body no pair changed reuses its predicted copy — same value)
+//
+// Exactness: pairs in one level touch disjoint dynamic bodies, so the fold over the ordered pair
+// list (CollisionResolver.fs:66-68) commutes inside a level; a culled pair can never collide as
+// long as every position used for detection stays within the margin of its step-start position,
+// which is checked on every integration; a violated margin or a full list restarts the step from
+// the published state with an 8x margin and then with the exact serial walk over ALL pairs.
+// Static bodies do not serialise their pairs when their pose is a fixed point of integrate()
+// (checked every step); their angular momentum (Q2) is then summed per pair and folded in pair
+// order — equal to the reference up to floating-point association; the serial
+// walk reproduces it bit for bit.
+#pragma once
+#include "ps_physics.cuh"
+
+namespace psk {
+using namespace psp;
+
+constexpr int kThreads = 128;
+constexpr int kDynF = 18;  // doubles of dynamic state per body
+constexpr int kParF = 16;  // doubles of parameters per body
+
+struct WorldStats {  // per world, accumulated over steps
+    unsigned long long steps, tested, hits, contacts, fallback, overflow, ref_exc;
+    double max_pen;
+    int nan_flag, pad;
+};
+
+struct RecPair {  // one entry of the last step's Collisions map
+    int i, j, first, count;
+};
+struct RecContact {
+    double n[3], p[3], pen;
+    unsigned feat, pad;
+};
+
+struct KArgs {
+    double* dyn;          // [total_bodies*18], per world planar: dyn[off*18 + f*N + b]
+    const double* par;    // [total_bodies*16], per world planar
+    const int* off;       // n_worlds+1
+    WorldStats* stats;    // n_worlds
+    int n_worlds, n_steps;
+    StepParams sp;
+    int exact_all_pairs;
+    int restore_joints;
+    // joints, grouped per world
+    const int* joff;      // n_worlds+1 (nullptr when no joints)
+    const int* ja;
+    const int* jb;
+    const double* jla;    // 3/joint
+    const double* jlb;
+    const unsigned char* jlast;  // bit0: last writer of a, bit1: last writer of b
+    // recording of the last step's contacts (nullptr when off)
+    RecPair* rec_pairs;       // n_worlds * rec_pair_cap
+    RecContact* rec_contacts; // n_worlds * rec_contact_cap
+    int* rec_counts;          // n_worlds * 2 : pairs, contacts
+    int rec_pair_cap, rec_contact_cap;
+    int max_n;                // largest world (sizes the shared-memory carve-up)
+    int k_cap;                // near-list capacity
+    int ks_cap;               // static-pair slot capacity
+};
+
+// ---- shared-memory carve-up ------------------------------------------------------------------
+struct Smem {
+    double* dyn;     // 18*N  current bodies
+    double* pred;    // 18*N  predicted bodies
+    double* par;     // 16*N
+    double* sx;      // 3*N step-start positions
+    double* rad_s;   // N   cull radius against a sphere (margin included)
+    double* rad_b;   // N   cull radius against a box
+    double* marg2;   // N   squared margin
+    double* S;       // 3*ks_cap angular-momentum sums of static-body pairs
+    unsigned* near;  // k_cap  i | j<<16
+    int* lvl_start;  // k_cap+2
+    int* row;        // N+1
+    int* srow;       // N+1
+    unsigned short* level;  // k_cap
+    unsigned short* order;  // k_cap
+    unsigned short* sslot;  // k_cap
+    unsigned short* last;   // N
+    unsigned char* pvalid;  // N
+    unsigned char* isstat;  // N
+    unsigned char* hit;     // k_cap
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline size_t smem_bytes(int N, int k_cap, int ks_cap)
+{
+    size_t b = 0;
+    b += sizeof(double) * (size_t)(kDynF * N) * 2;
+    b += sizeof(double) * (size_t)(kParF * N);
+    b += sizeof(double) * (size_t)(3 * N + 3 * N);
+    b += sizeof(double) * (size_t)(3 * ks_cap);
+    b += sizeof(unsigned) * (size_t)k_cap;
+    b += sizeof(int) * (size_t)(k_cap + 2);
+    b += sizeof(int) * (size_t)(2 * (N + 1));
+    b += sizeof(unsigned short) * (size_t)(3 * k_cap + N);
+    b += (size_t)(2 * N + k_cap);
+    return align_up(b, 16) + 64;
+}
+
+__device__ inline void carve(unsigned char* base, int N, int k_cap, int ks_cap, Smem& s)
+{
+    double* d = reinterpret_cast<double*>(base);
+    s.dyn = d;    d += kDynF * N;
+    s.pred = d;   d += kDynF * N;
+    s.par = d;    d += kParF * N;
+    s.sx = d;     d += 3 * N;
+    s.rad_s = d;  d += N;
+    s.rad_b = d;  d += N;
+    s.marg2 = d;  d += N;
+    s.S = d;      d += 3 * ks_cap;
+    unsigned* u = reinterpret_cast<unsigned*>(d);
+    s.near = u;   u += k_cap;
+    int* ip = reinterpret_cast<int*>(u);
+    s.lvl_start = ip; ip += k_cap + 2;
+    s.row = ip;   ip += N + 1;
+    s.srow = ip;  ip += N + 1;
+    unsigned short* h = reinterpret_cast<unsigned short*>(ip);
+    s.level = h;  h += k_cap;
+    s.order = h;  h += k_cap;
+    s.sslot = h;  h += k_cap;
+    s.last = h;   h += N;
+    unsigned char* c = reinterpret_cast<unsigned char*>(h);
+    s.pvalid = c; c += N;
+    s.isstat = c; c += N;
+    s.hit = c;
+}
+
+// ---- planar accessors ------------------------------------------------------------------------
+PSD void ld_dyn(const double* a, int N, int b, Dyn& d)
+{
+    d.x = mk(a[b], a[N + b], a[2 * N + b]);
+    d.v = mk(a[3 * N + b], a[4 * N + b], a[5 * N + b]);
+#pragma unroll
+    for (int k = 0; k < 9; k++) d.R.a[k] = a[(6 + k) * N + b];
+    d.L = mk(a[15 * N + b], a[16 * N + b], a[17 * N + b]);
+}
+PSD void st_dyn(double* a, int N, int b, const Dyn& d)
+{
+    a[b] = d.x.x; a[N + b] = d.x.y; a[2 * N + b] = d.x.z;
+    a[3 * N + b] = d.v.x; a[4 * N + b] = d.v.y; a[5 * N + b] = d.v.z;
+#pragma unroll
+    for (int k = 0; k < 9; k++) a[(6 + k) * N + b] = d.R.a[k];
+    a[15 * N + b] = d.L.x; a[16 * N + b] = d.L.y; a[17 * N + b] = d.L.z;
+}
+// parameter planes: 0 1/mass (host-evaluated 1.0/mass, what Vector3D `/` multiplies by), 1-3 iinv, 4-6 F, 7-9 T, 10 e, 11 mu_k, 12-14 dims, 15 shape
+PSD void ld_par(const double* a, int N, int b, Par& p)
+{
+    p.inv_mass = a[b];
+    p.is_static = (p.inv_mass == 0.0);  // 1/mass == 0 <=> mass is +-inf (Mass.Infinite)
+    p.iinv[0] = a[N + b]; p.iinv[1] = a[2 * N + b]; p.iinv[2] = a[3 * N + b];
+    p.F = mk(a[4 * N + b], a[5 * N + b], a[6 * N + b]);
+    p.T = mk(a[7 * N + b], a[8 * N + b], a[9 * N + b]);
+    p.e = a[10 * N + b];
+    p.mu = a[11 * N + b];
+    p.dims[0] = a[12 * N + b]; p.dims[1] = a[13 * N + b]; p.dims[2] = a[14 * N + b];
+    p.shape = (int)a[15 * N + b];
+}
+
+PSD bool same_bits(double a, double b) { return bits_of(a) == bits_of(b); }
+PSD bool pose_fixed(const Dyn& a, const Dyn& b)
+{
+    bool ok = same_bits(a.x.x, b.x.x) && same_bits(a.x.y, b.x.y) && same_bits(a.x.z, b.x.z) &&
+              same_bits(a.v.x, b.v.x) && same_bits(a.v.y, b.v.y) && same_bits(a.v.z, b.v.z);
+#pragma unroll
+    for (int k = 0; k < 9; k++) ok = ok && same_bits(a.R.a[k], b.R.a[k]);
+    return ok;
+}
+PSD bool finite3(d3 v) { return isfinite(v.x) && isfinite(v.y) && isfinite(v.z); }
+
+struct Ctx {
+    Smem s;
+    int N, w, tid;
+    const KArgs* a;
+    // per-thread counters of the current attempt
+    unsigned tested, hits, contacts, overflow, ref_exc;
+    double max_pen;
+};
+
+// block-wide flags / counters in static shared memory
+struct BlockShared {
+    int violate;       // margin violated or capacity exceeded -> restart
+    int need_serial;   // a static pose is not a fixed point
+    int K, KS, maxl;
+    unsigned tested, hits, contacts, overflow, ref_exc;
+    unsigned long long max_pen_bits;
+};
+
+// record one colliding pair for ps_batch_get_contacts
+PSD void record_pair(const Ctx& c, int i, int j, const Contact* cs, int nc)
+{
+    const KArgs& a = *c.a;
+    if (!a.rec_pairs) return;
+    int* cnt = a.rec_counts + 2 * c.w;
+    int slot = atomicAdd(&cnt[0], 1);
+    int first = atomicAdd(&cnt[1], nc);
+    if (slot >= a.rec_pair_cap || first + nc > a.rec_contact_cap) return;  // counted; host reports capacity
+    RecPair rp; rp.i = i; rp.j = j; rp.first = first; rp.count = nc;
+    a.rec_pairs[(size_t)c.w * a.rec_pair_cap + slot] = rp;
+    RecContact* out = a.rec_contacts + (size_t)c.w * a.rec_contact_cap + first;
+    for (int k = 0; k < nc; k++) {
+        RecContact r;
+        r.n[0] = cs[k].n.x; r.n[1] = cs[k].n.y; r.n[2] = cs[k].n.z;
+        r.p[0] = cs[k].p.x; r.p[1] = cs[k].p.y; r.p[2] = cs[k].p.z;
+        r.pen = cs[k].pen; r.feat = cs[k].feat; r.pad = 0;
+        out[k] = r;
+    }
+}
+
+// predicted copy of body b, integrating it first if an earlier pair changed it (lazy refresh).
+// check_margin: the position is about to be used for detection under a culled pair list.
+PSD void get_pred(Ctx& c, int b, const Par& p, Dyn& out, bool check_margin, BlockShared& bs)
+{
+    if (c.s.pvalid[b]) {
+        ld_dyn(c.s.pred, c.N, b, out);
+        return;
+    }
+    Dyn cur;
+    ld_dyn(c.s.dyn, c.N, b, cur);
+    integrate(cur, p, c.a->sp, out);
+    st_dyn(c.s.pred, c.N, b, out);
+    c.s.pvalid[b] = 1;
+    if (check_margin) {
+        d3 d = out.x - mk(c.s.sx[b], c.s.sx[c.N + b], c.s.sx[2 * c.N + b]);
+        double dd = d.x * d.x + d.y * d.y + d.z * d.z;
+        if (!(dd <= c.s.marg2[b])) bs.violate = 1;
+    }
+}
+
+// one candidate pair of the ordered fold (CollisionResolver.fs:40-46, 13-38).
+// fast != 0: static bodies are shared (pose fixed): their L is summed into slot `sslot`.
+PSD void process_pair(Ctx& c, int i, int j, int near_k, bool fast, BlockShared& bs)
+{
+    Par pi, pj;
+    ld_par(c.s.par, c.N, i, pi);
+    ld_par(c.s.par, c.N, j, pj);
+    Dyn di, dj;
+    get_pred(c, i, pi, di, fast, bs);
+    get_pred(c, j, pj, dj, fast, bs);
+    Contact cs[PS_MAX_CONTACTS];
+    int err = 0, ovf = 0;
+    c.tested++;
+    int nc = detect(di, pi, dj, pj, c.a->sp.eps, cs, err, ovf);
+    if (err) c.ref_exc++;
+    if (ovf) c.overflow++;
+    if (nc <= 0) return;
+    c.hits++;
+    c.contacts += nc;
+    for (int k = 0; k < nc; k++) c.max_pen = fmax(c.max_pen, fabs(cs[k].pen));
+    record_pair(c, i, j, cs, nc);
+    bool si = fast && pi.is_static, sj = fast && pj.is_static;
+    if (si) di.L = mk(0.0, 0.0, 0.0);
+    if (sj) dj.L = mk(0.0, 0.0, 0.0);
+    CPData cp[PS_MAX_CONTACTS];
+    resolve(di, pi, dj, pj, cs, nc, cp, c.a->sp);
+    if (fast) c.s.hit[near_k] = 1;
+    if (si || sj) {
+        int slot = c.s.sslot[near_k];
+        d3 sum = si ? di.L : dj.L;  // a static-static pair never reaches here (canIntersect)
+        c.s.S[3 * slot] = sum.x; c.s.S[3 * slot + 1] = sum.y; c.s.S[3 * slot + 2] = sum.z;
+    }
+    if (!si) { st_dyn(c.s.dyn, c.N, i, di); c.s.pvalid[i] = 0; }  // write back (CollisionResolver.fs:27-31)
+    if (!sj) { st_dyn(c.s.dyn, c.N, j, dj); c.s.pvalid[j] = 0; }
+}
+
+// conservative "may these two ever collide during this step" test on step-start positions
+PSD bool near_test(const Smem& s, int N, int i, int j)
+{
+    if (s.isstat[i] && s.isstat[j]) return false;  // canIntersect (CollisionResolver.fs:58-60)
+    double dx = s.sx[i] - s.sx[j], dy = s.sx[N + i] - s.sx[N + j], dz = s.sx[2 * N + i] - s.sx[2 * N + j];
+    double dd = dx * dx + dy * dy + dz * dz;
+    // radius of i depends on what j is (a sphere against a box can report a hit up to sqrt(3) r from a corner)
+    double ri = (s.par[15 * N + j] != 0.0) ? s.rad_b[i] : s.rad_s[i];
+    double rj = (s.par[15 * N + i] != 0.0) ? s.rad_b[j] : s.rad_s[j];
+    double r = ri + rj;
+    return !(dd > r * r);  // NaN -> near
+}
+
+__global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ BlockShared bs;
+
+    const int w = blockIdx.x;
+    if (w >= a.n_worlds) return;
+    const int tid = threadIdx.x;
+    const int off = a.off[w];
+    const int N = a.off[w + 1] - off;
+    Ctx c;
+    c.N = N; c.w = w; c.tid = tid; c.a = &a;
+    carve(smem_raw, N, a.k_cap, a.ks_cap, c.s);
+    Smem& s = c.s;
+    double* gdyn = a.dyn + (size_t)off * kDynF;
+    const double* gpar = a.par + (size_t)off * kParF;
+    const StepParams sp = a.sp;
+
+    // world -> shared memory (coalesced, contiguous per world)
+    for (int k = tid; k < kDynF * N; k += kThreads) s.dyn[k] = gdyn[k];
+    for (int k = tid; k < kParF * N; k += kThreads) s.par[k] = gpar[k];
+    __syncthreads();
+    for (int b = tid; b < N; b += kThreads) s.isstat[b] = (s.par[b] == 0.0) ? 1 : 0;
+
+    unsigned long long t_steps = 0, t_tested = 0, t_hits = 0, t_contacts = 0, t_fallback = 0, t_overflow = 0, t_exc = 0;
+    double t_maxpen = 0.0;
+
+    for (int step = 0; step < a.n_steps; step++) {
+        // attempts: 0 = margin x1, 1 = margin x8, 2 = exact serial walk over all pairs
+        int attempt = a.exact_all_pairs ? 2 : 0;
+        for (;; attempt++) {
+            if (tid == 0) {
+                bs.violate = 0; bs.need_serial = 0; bs.K = 0; bs.KS = 0; bs.maxl = 0;
+                bs.tested = bs.hits = bs.contacts = bs.overflow = bs.ref_exc = 0;
+                bs.max_pen_bits = 0ull;
+                if (a.rec_counts) { a.rec_counts[2 * w] = 0; a.rec_counts[2 * w + 1] = 0; }
+            }
+            c.tested = c.hits = c.contacts = c.overflow = c.ref_exc = 0;
+            c.max_pen = 0.0;
+            for (int b = tid; b < N; b += kThreads) s.pvalid[b] = 0;
+            __syncthreads();
+
+            if (attempt < 2) {
+                // ---- A: cull spheres -----------------------------------------------------------
+                const double mscale = attempt == 0 ? 1.0 : 8.0;
+                for (int b = tid; b < N; b += kThreads) {
+                    double x = s.dyn[b], y = s.dyn[N + b], z = s.dyn[2 * N + b];
+                    s.sx[b] = x; s.sx[N + b] = y; s.sx[2 * N + b] = z;
+                    double vx = s.dyn[3 * N + b], vy = s.dyn[4 * N + b], vz = s.dyn[5 * N + b];
+                    double speed = sqrt(vx * vx + vy * vy + vz * vz);
+                    double m = s.isstat[b] ? 0.0 : mscale * (0.03 + 6.0 * speed * sp.dt);
+                    double rs, rb;
+                    if (s.par[15 * N + b] == 0.0) {  // sphere
+                        double r = s.par[12 * N + b];
+                        rs = r; rb = 1.7320508075688774 * r;
+                    } else {
+                        double hx = 0.5 * s.par[12 * N + b], hy = 0.5 * s.par[13 * N + b], hz = 0.5 * s.par[14 * N + b];
+                        rs = rb = sqrt(hx * hx + hy * hy + hz * hz);
+                    }
+                    const double slack = 1.0 + 1e-6;
+                    s.rad_s[b] = rs * slack + 1e-9 + m;
+                    s.rad_b[b] = rb * slack + 1e-9 + m;
+                    s.marg2[b] = m * m;
+                    s.last[b] = 0;
+                }
+                __syncthreads();
+                // ---- B: near list, lexicographic order kept by a row scan ------------------------
+                for (int i = tid; i < N; i += kThreads) {
+                    int cn = 0, cs_ = 0;
+                    for (int j = i + 1; j < N; j++)
+                        if (near_test(s, N, i, j)) {
+                            cn++;
+                            if (s.isstat[i] | s.isstat[j]) cs_++;
+                        }
+                    s.row[i] = cn; s.srow[i] = cs_;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int acc = 0, sacc = 0;
+                    for (int i = 0; i < N; i++) {
+                        int t = s.row[i]; s.row[i] = acc; acc += t;
+                        int u = s.srow[i]; s.srow[i] = sacc; sacc += u;
+                    }
+                    s.row[N] = acc; s.srow[N] = sacc;
+                    bs.K = acc; bs.KS = sacc;
+                    if (acc > a.k_cap || sacc > a.ks_cap) bs.violate = 1;
+                }
+                __syncthreads();
+                const int K = bs.K;
+                if (!bs.violate) {
+                    for (int i = tid; i < N; i += kThreads) {
+                        int o = s.row[i], so = s.srow[i];
+                        for (int j = i + 1; j < N; j++)
+                            if (near_test(s, N, i, j)) {
+                                s.near[o] = (unsigned)i | ((unsigned)j << 16);
+                                s.hit[o] = 0;
+                                if (s.isstat[i] | s.isstat[j]) s.sslot[o] = (unsigned short)so++;
+                                else s.sslot[o] = 0xffff;
+                                o++;
+                            }
+                    }
+                }
+                __syncthreads();
+                // ---- C: levels (thread 0) || predicted copies (warps 1..) -------------------------
+                if (!bs.violate) {
+                    if (tid == 0) {
+                        int maxl = 0;
+                        for (int k = 0; k < K; k++) {
+                            unsigned ij = s.near[k];
+                            int i = ij & 0xffff, j = ij >> 16;
+                            int li = s.isstat[i] ? 0 : s.last[i];
+                            int lj = s.isstat[j] ? 0 : s.last[j];
+                            int l = (li > lj ? li : lj) + 1;
+                            s.level[k] = (unsigned short)l;
+                            if (!s.isstat[i]) s.last[i] = (unsigned short)l;
+                            if (!s.isstat[j]) s.last[j] = (unsigned short)l;
+                            if (l > maxl) maxl = l;
+                        }
+                        bs.maxl = maxl;
+                    }
+                    if (tid >= 32) {
+                        for (int b = tid - 32; b < N; b += kThreads - 32) {
+                            Par p; ld_par(s.par, N, b, p);
+                            Dyn cur, pr;
+                            ld_dyn(s.dyn, N, b, cur);
+                            integrate(cur, p, sp, pr);
+                            st_dyn(s.pred, N, b, pr);
+                            s.pvalid[b] = 1;
+                            if (p.is_static) {
+                                if (!pose_fixed(cur, pr)) bs.need_serial = 1;
+                            } else {
+                                d3 d = pr.x - cur.x;
+                                double dd = d.x * d.x + d.y * d.y + d.z * d.z;
+                                if (!(dd <= s.marg2[b])) bs.violate = 1;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (bs.need_serial) { attempt = 1; }  // jump straight to the serial walk
+                if (bs.violate || bs.need_serial) {
+                    // restart from the published state
+                    __syncthreads();
+                    for (int k = tid; k < kDynF * N; k += kThreads) s.dyn[k] = gdyn[k];
+                    __syncthreads();
+                    continue;
+                }
+                // counting sort of the near list by level (order inside a level is free)
+                const int maxl = bs.maxl;
+                for (int l = tid; l <= maxl + 1; l += kThreads) s.lvl_start[l] = 0;
+                __syncthreads();
+                for (int k = tid; k < K; k += kThreads) atomicAdd(&s.lvl_start[s.level[k]], 1);
+                __syncthreads();
+                if (tid == 0) {
+                    int acc = 0;
+                    for (int l = 0; l <= maxl + 1; l++) { int t = s.lvl_start[l]; s.lvl_start[l] = acc; acc += t; }
+                }
+                __syncthreads();
+                // scatter; lvl_start[l] is advanced to the END of level l, i.e. the start of l+1
+                for (int k = tid; k < K; k += kThreads) {
+                    int pos = atomicAdd(&s.lvl_start[s.level[k]], 1);
+                    s.order[pos] = (unsigned short)k;
+                }
+                __syncthreads();
+                // ---- D: wavefronts ---------------------------------------------------------------
+                for (int l = 1; l <= maxl; l++) {
+                    int beg = s.lvl_start[l - 1], end = s.lvl_start[l];
+                    for (int q = beg + tid; q < end; q += kThreads) {
+                        int k = s.order[q];
+                        unsigned ij = s.near[k];
+                        process_pair(c, ij & 0xffff, ij >> 16, k, true, bs);
+                    }
+                    __syncthreads();
+                }
+                if (bs.violate) {
+                    for (int k = tid; k < kDynF * N; k += kThreads) s.dyn[k] = gdyn[k];
+                    __syncthreads();
+                    continue;
+                }
+                // ---- E: static bodies: L = fold over their colliding pairs in pair order -----------
+                for (int b = tid; b < N; b += kThreads) {
+                    if (!s.isstat[b]) continue;
+                    Par p; ld_par(s.par, N, b, p);
+                    d3 L = mk(s.dyn[15 * N + b], s.dyn[16 * N + b], s.dyn[17 * N + b]);
+                    d3 dL = scale(sp.dt, p.T);
+                    for (int k = 0; k < K; k++) {
+                        if (!s.hit[k]) continue;
+                        unsigned ij = s.near[k];
+                        if ((int)(ij & 0xffff) != b && (int)(ij >> 16) != b) continue;
+                        int slot = s.sslot[k];
+                        L = L + dL;  // the predicted copy's integration
+                        L = L + mk(s.S[3 * slot], s.S[3 * slot + 1], s.S[3 * slot + 2]);
+                    }
+                    s.dyn[15 * N + b] = L.x; s.dyn[16 * N + b] = L.y; s.dyn[17 * N + b] = L.z;
+                    // pose is a fixed point: the final sweep only has to add dt*T to L
+                    s.pred[15 * N + b] = (L + dL).x; s.pred[16 * N + b] = (L + dL).y; s.pred[17 * N + b] = (L + dL).z;
+                }
+                __syncthreads();
+            } else {
+                // ---- exact serial walk over ALL pairs in Dummy order (BroadPhase.fs:33-39) -----------
+                if (tid == 0) {
+                    for (int i = 0; i < N; i++)
+                        for (int j = i + 1; j < N; j++) {
+                            if (s.isstat[i] && s.isstat[j]) continue;
+                            process_pair(c, i, j, 0, false, bs);
+                        }
+                }
+                __syncthreads();
+            }
+            break;
+        }
+        if (attempt > 0 && !a.exact_all_pairs) t_fallback += (tid == 0) ? 1 : 0;
+
+        // ---- J: joints (JointsRestorer.fs:9-26, Joints.fs:26-94) — all read the entry state --------
+        if (a.restore_joints && a.joff) {
+            int j0 = a.joff[w], nj = a.joff[w + 1] - j0;
+            Dyn o1, o2;
+            int ba = -1, bb = -1;
+            unsigned char lastf = 0;
+            if (tid < nj) {
+                int q = j0 + tid;
+                ba = a.ja[q]; bb = a.jb[q];
+                lastf = a.jlast[q];
+                Par p1, p2;
+                ld_par(s.par, N, ba, p1);
+                ld_par(s.par, N, bb, p2);
+                Dyn e1, e2;
+                ld_dyn(s.dyn, N, ba, e1);
+                ld_dyn(s.dyn, N, bb, e2);
+                d3 la = mk(a.jla[3 * q], a.jla[3 * q + 1], a.jla[3 * q + 2]);
+                d3 lb = mk(a.jlb[3 * q], a.jlb[3 * q + 1], a.jlb[3 * q + 2]);
+                m33 Iw1 = inertia_inv_world(e1.R, p1.iinv), Iw2 = inertia_inv_world(e2.R, p2.iinv);
+                d3 aw1 = mulMV(e1.R, la), aw2 = mulMV(e2.R, lb);  // JointImpulseData.init
+                m33 K;
+#pragma unroll
+                for (int k = 0; k < 9; k++) K.a[k] = 0.0;
+                add_K(K, p1, Iw1, aw1);
+                add_K(K, p2, Iw2, aw2);
+                d3 vrel = velocity_at(e2, Iw2, lb) - velocity_at(e1, Iw1, la);  // local offsets (Q14)
+                d3 imp = mulMV(K, mk(0.0, 0.0, 0.0) - vrel);
+                o1 = e1; o2 = e2;
+                for (int it = 0; it < sp.iterations; it++) {
+                    apply_impulse(o1, p1, la, imp);
+                    apply_impulse(o2, p2, lb, -imp);
+                }
+            }
+            __syncthreads();
+            if (tid < nj) {
+                if (lastf & 1) { st_dyn(s.dyn, N, ba, o1); s.pvalid[ba] = 0; }
+                if (lastf & 2) { st_dyn(s.dyn, N, bb, o2); s.pvalid[bb] = 0; }
+            }
+            __syncthreads();
+        }
+
+        // ---- F: final integration of every body (SimulatorState.fs:169-173) ---------------------------
+        for (int b = tid; b < N; b += kThreads) {
+            Dyn out;
+            if (s.pvalid[b]) {
+                ld_dyn(s.pred, N, b, out);
+            } else {
+                Par p; ld_par(s.par, N, b, p);
+                Dyn cur; ld_dyn(s.dyn, N, b, cur);
+                integrate(cur, p, sp, out);
+            }
+            st_dyn(s.dyn, N, b, out);
+        }
+        __syncthreads();
+        // publish the step (also the restart point of the next step's fallback)
+        for (int k = tid; k < kDynF * N; k += kThreads) gdyn[k] = s.dyn[k];
+
+        // fold per-thread counters
+        atomicAdd(&bs.tested, c.tested); atomicAdd(&bs.hits, c.hits); atomicAdd(&bs.contacts, c.contacts);
+        atomicAdd(&bs.overflow, c.overflow); atomicAdd(&bs.ref_exc, c.ref_exc);
+        atomicMax(&bs.max_pen_bits, (unsigned long long)__double_as_longlong(c.max_pen));
+        __syncthreads();
+        if (tid == 0) {
+            t_steps++; t_tested += bs.tested; t_hits += bs.hits; t_contacts += bs.contacts;
+            t_overflow += bs.overflow; t_exc += bs.ref_exc;
+            t_maxpen = fmax(t_maxpen, __longlong_as_double((long long)bs.max_pen_bits));
+        }
+        __syncthreads();
+    }
+
+    // NaN/Inf scan + stats write-out
+    int bad = 0;
+    for (int k = tid; k < kDynF * N; k += kThreads) bad |= !isfinite(s.dyn[k]);
+    bad = __syncthreads_or(bad);
+    if (tid == 0) {
+        WorldStats& st = a.stats[w];
+        st.steps += t_steps; st.tested += t_tested; st.hits += t_hits; st.contacts += t_contacts;
+        st.fallback += t_fallback; st.overflow += t_overflow; st.ref_exc += t_exc;
+        st.max_pen = fmax(st.max_pen, t_maxpen);
+        st.nan_flag = bad ? 1 : 0;
+    }
+}
+
+}  // namespace psk

@@ -1,0 +1,110 @@
+"""Shared helpers of the test-suite (not product code)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from physicssimulator_b200 import prototypes as P  # noqa: E402
+from physicssimulator_b200 import scenes  # noqa: E402
+from physicssimulator_b200.configuration import Configuration, StepConfiguration, to_native_config  # noqa: E402
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def same_bits(a, b):
+    """bit-exact equality, NaN == NaN when the payload bits agree; +0 and -0 differ"""
+    return np.array_equal(bits(a), bits(b))
+
+
+def assert_state_bits(a: dict, b: dict, what=""):
+    for k in ("pos", "vel", "rot", "ang_mom"):
+        if not same_bits(a[k], b[k]):
+            bad = np.argwhere(bits(a[k]) != bits(b[k]))
+            i = tuple(bad[0])
+            raise AssertionError(f"{what}: field {k} differs at {i}: {a[k][i]!r} vs {b[k][i]!r} ({len(bad)} entries)")
+
+
+def to_planar(bodies: dict):
+    """per-world planar layout of ps_step_kernel.cuh: (par[16*N], dyn[18*N])"""
+    n = len(bodies["mass"])
+    par = np.zeros((16, n))
+    with np.errstate(divide="ignore"):
+        par[0] = 1.0 / bodies["mass"]
+    par[1:4] = bodies["inertia_inv"].T
+    par[4:7] = bodies["force"].T
+    par[7:10] = bodies["torque"].T
+    par[10] = bodies["elasticity"]
+    par[11] = bodies["mu_kinetic"]
+    par[12:15] = bodies["dims"].T
+    par[15] = bodies["shape"]
+    dyn = np.zeros((18, n))
+    dyn[0:3] = bodies["pos"].T
+    dyn[3:6] = bodies["vel"].T
+    dyn[6:15] = bodies["rot"].T
+    dyn[15:18] = bodies["ang_mom"].T
+    return np.ascontiguousarray(par), np.ascontiguousarray(dyn)
+
+
+def from_planar_dyn(dyn):
+    return {"pos": np.ascontiguousarray(dyn[0:3].T), "vel": np.ascontiguousarray(dyn[3:6].T),
+            "rot": np.ascontiguousarray(dyn[6:15].T), "ang_mom": np.ascontiguousarray(dyn[15:18].T)}
+
+
+_HH = None
+
+
+def host_harness():
+    """g++ build of the device physics headers (tests/host_harness) — CPU check of the per-pair routines."""
+    global _HH
+    if _HH is None:
+        d = os.path.join(ROOT, "tests", "host_harness")
+        so = os.path.join(d, "libps_host_harness.so")
+        src = os.path.join(d, "physics_host.cpp")
+        deps = [src] + [os.path.join(ROOT, "physicssimulator_b200", "csrc", f) for f in ("ps_physics.cuh", "ps_math.cuh", "ps_sincos.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-x", "c++", src, "-o", so])
+        _HH = ctypes.CDLL(so)
+        _HH.hh_world_step.restype = None
+    return _HH
+
+
+def harness_step(bodies: dict, cfg_native, nsteps: int, cap_pairs=4096, cap_contacts=32768):
+    hh = host_harness()
+    par, dyn = to_planar(bodies)
+    n = len(bodies["mass"])
+    counters = np.zeros(5, dtype=np.int64)
+    pairs = np.zeros((cap_pairs, 3), dtype=np.int32)
+    feats = np.zeros(cap_contacts, dtype=np.uint32)
+    cont = np.zeros((cap_contacts, 7))
+    counts = np.zeros(2, dtype=np.int32)
+    P_ = ctypes.POINTER
+    hh.hh_world_step(ctypes.c_int(n), par.ctypes.data_as(P_(ctypes.c_double)), dyn.ctypes.data_as(P_(ctypes.c_double)),
+                     ctypes.byref(cfg_native), ctypes.c_int(nsteps), counters.ctypes.data_as(P_(ctypes.c_int64)),
+                     pairs.ctypes.data_as(P_(ctypes.c_int32)), feats.ctypes.data_as(P_(ctypes.c_uint32)),
+                     cont.ctypes.data_as(P_(ctypes.c_double)), counts.ctypes.data_as(P_(ctypes.c_int32)),
+                     ctypes.c_int(cap_pairs), ctypes.c_int(cap_contacts))
+    st = from_planar_dyn(dyn)
+    npairs, nc = int(counts[0]), int(counts[1])
+    first = np.concatenate([[0], np.cumsum(pairs[:npairs, 2])]).astype(np.int32)
+    rec = {"pairs": pairs[:npairs, :2].copy(), "first": first, "normal": cont[:nc, 0:3].copy(), "position": cont[:nc, 3:6].copy(),
+           "penetration": cont[:nc, 6].copy(), "feature": feats[:nc].copy()}
+    return st, rec, {"pairs_tested": int(counters[0]), "pairs_colliding": int(counters[1]), "contacts": int(counters[2]),
+                     "errors": int(counters[3]), "overflow": int(counters[4])}
+
+
+def assert_contacts_equal(a: dict, b: dict, what=""):
+    assert np.array_equal(a["pairs"], b["pairs"]), f"{what}: colliding pair sets differ\n{a['pairs']}\n{b['pairs']}"
+    assert np.array_equal(a["first"], b["first"]), f"{what}: contact counts differ"
+    assert np.array_equal(a["feature"], b["feature"]), f"{what}: feature ids differ"
+    for k in ("normal", "position", "penetration"):
+        assert same_bits(a[k], b[k]), f"{what}: contact {k} differs"

@@ -1,0 +1,103 @@
+// tests/host_harness/physics_host.cpp — TEST-ONLY build of the device physics headers with g++.
+//
+// Compiles physicssimulator_b200/csrc/ps_physics.cuh (integration, narrow phase, per-pair solve) for
+// the host so that `-m "not gpu"` tests can compare those routines with the oracle bit for bit in a
+// container without a GPU.  It walks ALL pairs serially like the kernel's exact path.  It is not part
+// of libps_b200.so and nothing in the product links or loads it.
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "../../physicssimulator_b200/csrc/ps_physics.cuh"
+
+using namespace psp;
+
+namespace {
+void ld_dyn(const double* a, int N, int b, Dyn& d)
+{
+    d.x = mk(a[b], a[N + b], a[2 * N + b]);
+    d.v = mk(a[3 * N + b], a[4 * N + b], a[5 * N + b]);
+    for (int k = 0; k < 9; k++) d.R.a[k] = a[(6 + k) * N + b];
+    d.L = mk(a[15 * N + b], a[16 * N + b], a[17 * N + b]);
+}
+void st_dyn(double* a, int N, int b, const Dyn& d)
+{
+    a[b] = d.x.x; a[N + b] = d.x.y; a[2 * N + b] = d.x.z;
+    a[3 * N + b] = d.v.x; a[4 * N + b] = d.v.y; a[5 * N + b] = d.v.z;
+    for (int k = 0; k < 9; k++) a[(6 + k) * N + b] = d.R.a[k];
+    a[15 * N + b] = d.L.x; a[16 * N + b] = d.L.y; a[17 * N + b] = d.L.z;
+}
+void ld_par(const double* a, int N, int b, Par& p)
+{
+    p.inv_mass = a[b];
+    p.is_static = (p.inv_mass == 0.0);
+    p.iinv[0] = a[N + b]; p.iinv[1] = a[2 * N + b]; p.iinv[2] = a[3 * N + b];
+    p.F = mk(a[4 * N + b], a[5 * N + b], a[6 * N + b]);
+    p.T = mk(a[7 * N + b], a[8 * N + b], a[9 * N + b]);
+    p.e = a[10 * N + b];
+    p.mu = a[11 * N + b];
+    p.dims[0] = a[12 * N + b]; p.dims[1] = a[13 * N + b]; p.dims[2] = a[14 * N + b];
+    p.shape = (int)a[15 * N + b];
+}
+}  // namespace
+
+extern "C" {
+
+// planar layouts as in ps_step_kernel.cuh: dyn[f*N+b] (18 planes), par[f*N+b] (16 planes, plane 0 = 1/mass)
+void hh_world_step(int N, const double* par, double* dyn, const ps_step_config* cfg, int nsteps, int64_t* counters /*tested,hits,contacts,exc,overflow*/,
+                   int32_t* last_pairs, uint32_t* last_feats, double* last_contacts /*7 per contact*/, int32_t* last_counts /*pairs,contacts*/, int cap_pairs, int cap_contacts)
+{
+    StepParams sp;
+    sp.eps = cfg->epsilon; sp.baumgarte = cfg->baumgarte; sp.slop = cfg->allowed_penetration; sp.max_corr = cfg->max_correction_velocity;
+    sp.dt = cfg->dt; sp.iterations = cfg->solver_iterations; sp.friction = cfg->enable_friction; sp.integrator = cfg->integrator_kind;
+    std::vector<double> pred(18 * (size_t)N);
+    std::vector<char> pvalid(N);
+    for (int s = 0; s < nsteps; s++) {
+        std::fill(pvalid.begin(), pvalid.end(), 0);
+        int np = 0, ncs = 0;
+        auto get_pred = [&](int b, const Par& p, Dyn& out) {
+            if (pvalid[b]) { ld_dyn(pred.data(), N, b, out); return; }
+            Dyn cur; ld_dyn(dyn, N, b, cur);
+            integrate(cur, p, sp, out);
+            st_dyn(pred.data(), N, b, out);
+            pvalid[b] = 1;
+        };
+        for (int i = 0; i < N; i++)
+            for (int j = i + 1; j < N; j++) {
+                Par pi, pj; ld_par(par, N, i, pi); ld_par(par, N, j, pj);
+                if (pi.is_static && pj.is_static) continue;
+                Dyn di, dj; get_pred(i, pi, di); get_pred(j, pj, dj);
+                Contact cs[PS_MAX_CONTACTS];
+                int err = 0, ovf = 0;
+                counters[0]++;
+                int nc = detect(di, pi, dj, pj, sp.eps, cs, err, ovf);
+                counters[3] += err; counters[4] += ovf;
+                if (nc <= 0) continue;
+                counters[1]++; counters[2] += nc;
+                if (s == nsteps - 1 && last_pairs) {
+                    if (np < cap_pairs) { last_pairs[3 * np] = i; last_pairs[3 * np + 1] = j; last_pairs[3 * np + 2] = nc; }
+                    np++;
+                    for (int k = 0; k < nc; k++) {
+                        if (ncs < cap_contacts) {
+                            double* o = last_contacts + 7 * (size_t)ncs;
+                            o[0] = cs[k].n.x; o[1] = cs[k].n.y; o[2] = cs[k].n.z; o[3] = cs[k].p.x; o[4] = cs[k].p.y; o[5] = cs[k].p.z; o[6] = cs[k].pen;
+                            last_feats[ncs] = cs[k].feat;
+                        }
+                        ncs++;
+                    }
+                }
+                CPData cp[PS_MAX_CONTACTS];
+                resolve(di, pi, dj, pj, cs, nc, cp, sp);
+                st_dyn(dyn, N, i, di); pvalid[i] = 0;
+                st_dyn(dyn, N, j, dj); pvalid[j] = 0;
+            }
+        for (int b = 0; b < N; b++) {
+            Dyn out;
+            if (pvalid[b]) ld_dyn(pred.data(), N, b, out);
+            else { Par p; ld_par(par, N, b, p); Dyn cur; ld_dyn(dyn, N, b, cur); integrate(cur, p, sp, out); }
+            st_dyn(dyn, N, b, out);
+        }
+        if (last_counts) { last_counts[0] = np; last_counts[1] = ncs; }
+    }
+}
+}
