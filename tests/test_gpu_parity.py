@@ -173,7 +173,9 @@ def test_t8_joints_chain():
         p, cfg, j = scenes.c4_chain32(w, n_links=8)
         worlds.append(p)
         joints.append(j)
-    _run(worlds, cfg, [1, 5, 30], "C4 chains", joints=joints)
+    # the "restore" as written is energetic (Q14): the chains blow up to NaN within ~35 steps in the oracle too;
+    # parity is checked before and through the blow-up (NaN == NaN)
+    _run(worlds, cfg, [1, 5, 14, 30], "C4 chains", joints=joints)
 
 
 def test_mutations_apply_impulse_add_object_reset():
