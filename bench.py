@@ -170,7 +170,12 @@ def main():
     sim = BatchSimulator(None, cfg, joints=joints, device=local, _prebuilt=built)
     n_bodies, n_dynamic = sim.batch.num_bodies()
     assert n_dynamic == n_dyn * per_gpu
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default stream of our own: the kernels are launched on it through ps_batch_step_async and the CUDA
+    # events below are recorded on it (torch.cuda.Event sees only torch's current stream)
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     # setup (untimed): settle, then W warm-up steps
     sim.batch.step(args.settle)

@@ -146,7 +146,7 @@ int ps_batch_get_state(void* handle, int32_t w0, int32_t w1, double* pos, double
                        double* ang_mom);
 int ps_batch_set_state(void* handle, int32_t w0, int32_t w1, const double* pos, const double* vel,
                        const double* rot, const double* ang_mom);
-/* same pair with DEVICE pointers (torch tensors' data_ptr): no host round trip */
+/* same read-back into caller-owned DEVICE buffers (plain device pointers): no host round trip */
 int ps_batch_get_state_device(void* handle, int32_t w0, int32_t w1, double* d_pos, double* d_vel,
                               double* d_rot, double* d_ang_mom, void* cuda_stream);
 

@@ -150,6 +150,8 @@ class Batch:
 
     def get_state(self, w0=0, w1=None, out=None):
         w1 = self.n_worlds if w1 is None else w1
+        if not (0 <= w0 <= w1 <= self.n_worlds):  # let the native range check speak (KeyNotFoundException)
+            check(lib().ps_batch_get_state(self.h, c_int32(w0), c_int32(w1), None, None, None, None))
         n = int(self.world_offset[w1] - self.world_offset[w0])
         if out is None:
             out = {"pos": np.empty((n, 3)), "vel": np.empty((n, 3)), "rot": np.empty((n, 9)), "ang_mom": np.empty((n, 3))}

@@ -338,20 +338,28 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
             __syncthreads();
 
             if (attempt < 2) {
-                // ---- A: cull spheres -----------------------------------------------------------
+                // ---- A: predicted copy of every body (CollisionResolver.fs:42-43) + cull spheres ------------
+                // The sphere is centred on the PREDICTED position: a body no pair has changed is tested
+                // exactly there (deviation 0); after a write-back the position is unchanged and the next
+                // prediction moves it by v'*dt only, which the margin has to cover.
                 const double mscale = attempt == 0 ? 1.0 : 8.0;
                 for (int b = tid; b < N; b += kThreads) {
-                    double x = s.dyn[b], y = s.dyn[N + b], z = s.dyn[2 * N + b];
-                    s.sx[b] = x; s.sx[N + b] = y; s.sx[2 * N + b] = z;
-                    double vx = s.dyn[3 * N + b], vy = s.dyn[4 * N + b], vz = s.dyn[5 * N + b];
-                    double speed = sqrt(vx * vx + vy * vy + vz * vz);
-                    double m = s.isstat[b] ? 0.0 : mscale * (0.03 + 6.0 * speed * sp.dt);
+                    Par p; ld_par(s.par, N, b, p);
+                    Dyn cur, pr;
+                    ld_dyn(s.dyn, N, b, cur);
+                    integrate(cur, p, sp, pr);
+                    st_dyn(s.pred, N, b, pr);
+                    s.pvalid[b] = 1;
+                    if (p.is_static && !pose_fixed(cur, pr)) bs.need_serial = 1;
+                    s.sx[b] = pr.x.x; s.sx[N + b] = pr.x.y; s.sx[2 * N + b] = pr.x.z;
+                    double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
+                    double m = p.is_static ? 0.0 : mscale * (0.02 + 3.0 * speed * sp.dt);
+                    if (!(m == m)) m = 0.0;  // NaN state: the world is flagged anyway
                     double rs, rb;
-                    if (s.par[15 * N + b] == 0.0) {  // sphere
-                        double r = s.par[12 * N + b];
-                        rs = r; rb = 1.7320508075688774 * r;
+                    if (p.shape == 0) {
+                        rs = p.dims[0]; rb = 1.7320508075688774 * p.dims[0];
                     } else {
-                        double hx = 0.5 * s.par[12 * N + b], hy = 0.5 * s.par[13 * N + b], hz = 0.5 * s.par[14 * N + b];
+                        double hx = 0.5 * p.dims[0], hy = 0.5 * p.dims[1], hz = 0.5 * p.dims[2];
                         rs = rb = sqrt(hx * hx + hy * hy + hz * hz);
                     }
                     const double slack = 1.0 + 1e-6;
@@ -361,6 +369,11 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
                     s.last[b] = 0;
                 }
                 __syncthreads();
+                if (bs.need_serial) {  // a static pose still moves under integrate(): exact serial walk this step
+                    __syncthreads();   // every thread has read the flag before thread 0 clears it at the loop top
+                    attempt = 1;
+                    continue;          // state untouched so far: no reload needed
+                }
                 // ---- B: near list, lexicographic order kept by a row scan ------------------------
                 for (int i = tid; i < N; i += kThreads) {
                     int cn = 0, cs_ = 0;
@@ -380,11 +393,16 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
                     }
                     s.row[N] = acc; s.srow[N] = sacc;
                     bs.K = acc; bs.KS = sacc;
-                    if (acc > a.k_cap || sacc > a.ks_cap) bs.violate = 1;
+                    if (acc > a.k_cap || sacc > a.ks_cap) bs.need_serial = 1;  // list full: a wider margin cannot help
                 }
                 __syncthreads();
                 const int K = bs.K;
-                if (!bs.violate) {
+                if (bs.need_serial) {
+                    __syncthreads();
+                    attempt = 1;
+                    continue;
+                }
+                {
                     for (int i = tid; i < N; i += kThreads) {
                         int o = s.row[i], so = s.srow[i];
                         for (int j = i + 1; j < N; j++)
@@ -398,50 +416,23 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
                     }
                 }
                 __syncthreads();
-                // ---- C: levels (thread 0) || predicted copies (warps 1..) -------------------------
-                if (!bs.violate) {
-                    if (tid == 0) {
-                        int maxl = 0;
-                        for (int k = 0; k < K; k++) {
-                            unsigned ij = s.near[k];
-                            int i = ij & 0xffff, j = ij >> 16;
-                            int li = s.isstat[i] ? 0 : s.last[i];
-                            int lj = s.isstat[j] ? 0 : s.last[j];
-                            int l = (li > lj ? li : lj) + 1;
-                            s.level[k] = (unsigned short)l;
-                            if (!s.isstat[i]) s.last[i] = (unsigned short)l;
-                            if (!s.isstat[j]) s.last[j] = (unsigned short)l;
-                            if (l > maxl) maxl = l;
-                        }
-                        bs.maxl = maxl;
+                // ---- C: wavefront levels (serial scan of the ordered list by one thread) -------------------
+                if (tid == 0) {
+                    int maxl = 0;
+                    for (int k = 0; k < K; k++) {
+                        unsigned ij = s.near[k];
+                        int i = ij & 0xffff, j = ij >> 16;
+                        int li = s.isstat[i] ? 0 : s.last[i];
+                        int lj = s.isstat[j] ? 0 : s.last[j];
+                        int l = (li > lj ? li : lj) + 1;
+                        s.level[k] = (unsigned short)l;
+                        if (!s.isstat[i]) s.last[i] = (unsigned short)l;
+                        if (!s.isstat[j]) s.last[j] = (unsigned short)l;
+                        if (l > maxl) maxl = l;
                     }
-                    if (tid >= 32) {
-                        for (int b = tid - 32; b < N; b += kThreads - 32) {
-                            Par p; ld_par(s.par, N, b, p);
-                            Dyn cur, pr;
-                            ld_dyn(s.dyn, N, b, cur);
-                            integrate(cur, p, sp, pr);
-                            st_dyn(s.pred, N, b, pr);
-                            s.pvalid[b] = 1;
-                            if (p.is_static) {
-                                if (!pose_fixed(cur, pr)) bs.need_serial = 1;
-                            } else {
-                                d3 d = pr.x - cur.x;
-                                double dd = d.x * d.x + d.y * d.y + d.z * d.z;
-                                if (!(dd <= s.marg2[b])) bs.violate = 1;
-                            }
-                        }
-                    }
+                    bs.maxl = maxl;
                 }
                 __syncthreads();
-                if (bs.need_serial) { attempt = 1; }  // jump straight to the serial walk
-                if (bs.violate || bs.need_serial) {
-                    // restart from the published state
-                    __syncthreads();
-                    for (int k = tid; k < kDynF * N; k += kThreads) s.dyn[k] = gdyn[k];
-                    __syncthreads();
-                    continue;
-                }
                 // counting sort of the near list by level (order inside a level is free)
                 const int maxl = bs.maxl;
                 for (int l = tid; l <= maxl + 1; l += kThreads) s.lvl_start[l] = 0;

@@ -1,0 +1,67 @@
+"""CPU check of the DEVICE physics routines: physicssimulator_b200/csrc/ps_physics.cuh compiled with g++
+(tests/host_harness) must reproduce the oracle bit for bit — states, colliding sets, contacts and feature ids.
+This runs without a GPU; the same comparison through the real kernels is tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from common import (P, scenes, Configuration, StepConfiguration, to_native_config, assert_state_bits, assert_contacts_equal,
+                    harness_step)
+from oracle.oracle import OracleWorld
+
+
+def _run(protos, cfg, chunks, what):
+    b = P.build_world(protos, cfg.StepConfig.GravitationalAccelerationMagnitude, cfg.StepConfig.GravityDirection)
+    nc = to_native_config(cfg)
+    o = OracleWorld(b, nc)
+    cur = {k: v.copy() for k, v in b.items()}
+    done = 0
+    for n in chunks:
+        o.step(n)
+        st, rec, cnt = harness_step(cur, nc, n)
+        done += n
+        assert_state_bits(o.get_state(), st, f"{what} @ {done}")
+        assert_contacts_equal(o.contacts(), rec, f"{what} @ {done}")
+        assert cnt["overflow"] == 0
+        cur.update(st)
+
+
+def test_stack_scene():
+    _run(*scenes.stack_scene(), [1, 9, 90, 200], "stack")
+
+
+def test_domino_scene():
+    _run(*scenes.domino_scene(), [1, 9, 60], "domino")
+
+
+def test_c1_stack20():
+    _run(*scenes.c1_stack20(), [1, 24, 100], "c1")
+
+
+def test_c2_world():
+    p, c = scenes.c2_spheres64(3)
+    _run(p, c, [1, 49, 150], "c2")
+
+
+def test_c3_world():
+    p, c = scenes.c3_mixed128(1, n_boxes=32, n_spheres=31)
+    _run(p, c, [1, 29, 90], "c3")
+
+
+@pytest.mark.parametrize("integrator", [0, 1])
+def test_free_flight(integrator):
+    rng = scenes.SplitMix64(5 + integrator)
+    protos = []
+    for k in range(12):
+        p = P.createDefaultBox(rng.uniform(.2, 1), rng.uniform(.2, 1), rng.uniform(.2, 1)) if k % 2 else P.createDefaultSphere(rng.uniform(.2, .5))
+        protos.append(p.With(Position=(10.0 * k, 0, 0), Velocity=(rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-1, 1)),
+                             Yaw=rng.uniform(-3, 3), Pitch=rng.uniform(-3, 3), Roll=rng.uniform(-3, 3)))
+    cfg = Configuration(StepConfig=StepConfiguration(RigidBodyIntegratorKind=integrator))
+    b = P.build_world(protos)
+    b["ang_mom"][:] = np.array([[rng.uniform(-1, 1) for _ in range(3)] for _ in range(12)])
+    b["ang_mom"][5] = 0.0
+    b["torque"][3] = (0.1, -0.2, 0.05)
+    nc = to_native_config(cfg)
+    o = OracleWorld(b, nc)
+    o.step(500)
+    st, _, _ = harness_step(b, nc, 500)
+    assert_state_bits(o.get_state(), st, "free flight")
