@@ -102,12 +102,16 @@ typedef struct {
     int64_t pairs_tested;     /* candidate pairs that reached the narrow phase */
     int64_t pairs_colliding;  /* |HIT| summed */
     int64_t contacts;         /* contact points summed */
-    int64_t fallback_steps;   /* world-steps that took the exact serial walk (margin/capacity) */
+    int64_t fallback_steps;   /* world-steps that restarted (wider margin) or took the exact serial walk */
     int64_t nan_worlds;       /* worlds whose state holds a NaN/Inf now */
     int64_t contact_overflow; /* manifolds truncated at PS_MAX_CONTACTS (must stay 0) */
     int64_t reference_exceptions; /* pair tests on which the reference would have thrown (Option.get of None,
                                      Seq.find / List.maxBy on nothing); treated as "no collision" here */
     double max_penetration;   /* max |penetration| seen */
+    /* why a world-step left the wavefront path (sum = fallback_steps) */
+    int64_t fallback_margin_steps;   /* a motion margin was violated: retried with an 8x margin */
+    int64_t fallback_capacity_steps; /* near list or level table full: exact serial walk */
+    int64_t fallback_static_steps;   /* a static body's pose still moved under integrate(): exact serial walk */
 } ps_stats;
 
 #define PS_MAX_CONTACTS 20 /* worst case of the reference clipper is 19 */

@@ -56,7 +56,7 @@ struct Batch {
     HostBodies init, cur;  // `cur` holds parameters (+ possibly added bodies); dynamic state lives on the device
     HostJoints joints;
     int n_worlds = 0, n_bodies = 0, n_dynamic = 0, max_n = 0;
-    int k_cap = 0, ks_cap = 0;
+    int k_cap = 0, threads = 128;
     size_t smem = 0;
     // device
     double* d_dyn = nullptr;
@@ -64,6 +64,7 @@ struct Batch {
     double* d_stage = nullptr;  // 18 doubles/body staging in ABI layout: pos | vel | rot | L
     int* d_off = nullptr;
     WorldStats* d_stats = nullptr;
+    unsigned char* d_hitcnt = nullptr;
     int *d_joff = nullptr, *d_ja = nullptr, *d_jb = nullptr;
     double *d_jla = nullptr, *d_jlb = nullptr;
     unsigned char* d_jlast = nullptr;
@@ -141,11 +142,13 @@ __global__ void apply_impulse_kernel(double* dyn, const double* par, const int* 
 __global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const double* par, int n_worlds, ps_stats* out)
 {
     unsigned long long steps = 0, tested = 0, hits = 0, contacts = 0, fallback = 0, overflow = 0, exc = 0, nanw = 0, bsteps = 0;
+    unsigned long long fbm = 0, fbc = 0, fbs = 0;
     double mp = 0.0;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_worlds; w += gridDim.x * blockDim.x) {
         const WorldStats& s = ws[w];
         steps += s.steps; tested += s.tested; hits += s.hits; contacts += s.contacts;
         fallback += s.fallback; overflow += s.overflow; exc += s.ref_exc; nanw += s.nan_flag ? 1 : 0;
+        fbm += s.fb_margin; fbc += s.fb_capacity; fbs += s.fb_static;
         mp = fmax(mp, s.max_pen);
         int o = off[w], N = off[w + 1] - o, dynb = 0;
         const double* p = par + (size_t)o * kParF;
@@ -161,6 +164,9 @@ __global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const 
     atomicAdd((unsigned long long*)&out->nan_worlds, nanw);
     atomicAdd((unsigned long long*)&out->contact_overflow, overflow);
     atomicAdd((unsigned long long*)&out->reference_exceptions, exc);
+    atomicAdd((unsigned long long*)&out->fallback_margin_steps, fbm);
+    atomicAdd((unsigned long long*)&out->fallback_capacity_steps, fbc);
+    atomicAdd((unsigned long long*)&out->fallback_static_steps, fbs);
     atomicMax((unsigned long long*)&out->max_penetration, (unsigned long long)__double_as_longlong(mp));
 }
 
@@ -173,7 +179,7 @@ void dfree(T*& p)
 }
 void free_device(Batch* B)
 {
-    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats);
+    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt);
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
 }
@@ -208,14 +214,18 @@ int upload(Batch* B, bool with_state)
     B->n_dynamic = 0;
     for (int w = 0; w < B->n_worlds; w++) B->max_n = std::max(B->max_n, h.off[w + 1] - h.off[w]);
     for (int i = 0; i < B->n_bodies; i++) B->n_dynamic += std::isinf(h.mass[i]) ? 0 : 1;
-    B->k_cap = std::min(60000, std::max(64, 10 * B->max_n));
-    B->ks_cap = std::min(B->k_cap, std::max(16, 3 * B->max_n));
-    B->smem = smem_bytes(B->max_n, B->k_cap, B->ks_cap);
+    // near-list capacity: all pairs for small worlds, 16 per body otherwise (a fuller list takes the serial walk)
+    B->k_cap = std::max(32, std::min(B->max_n * (B->max_n - 1) / 2, 16 * B->max_n));
+    // CTA width: a wavefront level rarely holds more pairs than bodies/4; narrow CTAs let more worlds share an SM
+    B->threads = B->max_n <= 80 ? 32 : (B->max_n <= 200 ? 64 : 128);
+    B->smem = smem_bytes(B->max_n, B->k_cap);
     int dev_max = 0;
     CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, B->device));
     if ((long long)B->smem > dev_max)
         return fail(PS_ERR_INVALID_ARGUMENT, "largest world (%d bodies) needs %zu B of shared memory; device allows %d", B->max_n, B->smem, dev_max);
-    CK(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem));
+    CK(cudaFuncSetAttribute(step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem));
+    CK(cudaFuncSetAttribute(step_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem));
+    CK(cudaFuncSetAttribute(step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem));
 
     size_t nb = (size_t)std::max(1, B->n_bodies);
     CK(cudaMalloc(&B->d_dyn, nb * kDynF * sizeof(double)));
@@ -224,6 +234,8 @@ int upload(Batch* B, bool with_state)
     CK(cudaMalloc(&B->d_off, (size_t)(B->n_worlds + 1) * sizeof(int)));
     CK(cudaMalloc(&B->d_stats, (size_t)std::max(1, B->n_worlds) * sizeof(WorldStats)));
     CK(cudaMalloc(&B->d_stats_sum, sizeof(ps_stats)));
+    CK(cudaMalloc(&B->d_hitcnt, nb));
+    CK(cudaMemsetAsync(B->d_hitcnt, 0, nb, B->stream));
     CK(cudaMemsetAsync(B->d_stats, 0, (size_t)std::max(1, B->n_worlds) * sizeof(WorldStats), B->stream));
     CK(cudaMemcpyAsync(B->d_off, h.off.data(), (size_t)(B->n_worlds + 1) * sizeof(int), cudaMemcpyHostToDevice, B->stream));
 
@@ -261,7 +273,7 @@ int upload(Batch* B, bool with_state)
         std::vector<unsigned char> last(nj, 0);
         for (int q = 0; q < nj; q++) joff[J.world[order[q]] + 1]++;
         for (int w = 0; w < B->n_worlds; w++) {
-            if (joff[w + 1] > kThreads) return fail(PS_ERR_INVALID_ARGUMENT, "world %d has %d joints; at most %d per world", w, joff[w + 1], kThreads);
+            if (joff[w + 1] > B->threads) return fail(PS_ERR_INVALID_ARGUMENT, "world %d has %d joints; at most %d per world of this size", w, joff[w + 1], B->threads);
             joff[w + 1] += joff[w];
         }
         for (int q = 0; q < nj; q++) {
@@ -436,8 +448,11 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
     a.joff = B->d_joff; a.ja = B->d_ja; a.jb = B->d_jb; a.jla = B->d_jla; a.jlb = B->d_jlb; a.jlast = B->d_jlast;
     a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
-    a.max_n = B->max_n; a.k_cap = B->k_cap; a.ks_cap = B->ks_cap;
-    step_kernel<<<B->n_worlds, kThreads, B->smem, st>>>(a);
+    a.max_n = B->max_n; a.k_cap = B->k_cap;
+    a.hitcnt = B->d_hitcnt;
+    if (B->threads == 32) step_kernel<32><<<B->n_worlds, 32, B->smem, st>>>(a);
+    else if (B->threads == 64) step_kernel<64><<<B->n_worlds, 64, B->smem, st>>>(a);
+    else step_kernel<128><<<B->n_worlds, 128, B->smem, st>>>(a);
     CK(cudaGetLastError());
     B->launches++;
     return PS_OK;

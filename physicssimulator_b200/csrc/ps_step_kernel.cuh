@@ -1,17 +1,19 @@
-// ps_step_kernel.cuh — the fused per-world step kernel (block per world).
+// ps_step_kernel.cuh — the fused per-world step kernel (one CTA per world).
 //
 // One CTA owns one world for n_steps steps; the world's state lives in shared memory for the
 // whole launch (HBM is touched once per step to publish the state, which doubles as the
-// restart point of the exact fallback).
+// restart point of the exact fallback).  The CTA width T is 32, 64 or 128 threads, chosen by the
+// host from the world size: a level of the wavefront rarely holds more pairs than that, and narrow
+// CTAs let many worlds share one SM.
 //
 // Per step (reference order: Simulator.fs:52-56 = resolveAll (CollisionResolver.fs:49-69) then
 // SimulatorState.update (SimulatorState.fs:169-173)):
-//   A  per body : cull sphere (bounding radius + motion margin) from the step-start pose
+//   A  per body : predicted copy = integrate(body) (CollisionResolver.fs:42-43); cull sphere =
+//                 bounding radius + motion margin around the PREDICTED position
 //   B  per row  : conservative cull of the Dummy-order pair list (BroadPhase.fs:33-39) -> ordered
-//                 near list in shared memory (block scan keeps lexicographic order)
+//                 near list in shared memory (row scan keeps the lexicographic order)
 //   C  thread 0 : wavefront level of every near pair (a pair waits for the previous near pair of
-//                 either of its dynamic bodies); the other warps integrate every body once
-//                 (the "predicted" copy, CollisionResolver.fs:42-43) meanwhile
+//                 either of its dynamic bodies), then a counting sort by level
 //   D  per level: one thread per pair: (re-integrate a body an earlier pair changed) -> narrow
 //                 phase -> N-iteration solve -> write back (CollisionResolver.fs:13-38)
 //   E  per static body: fold the angular-momentum sums of its pairs in pair order
@@ -19,10 +21,11 @@
 //   F  per body : final integration (a body no pair changed reuses its predicted copy — same value)
 //
 // Exactness: pairs in one level touch disjoint dynamic bodies, so the fold over the ordered pair
-// list (CollisionResolver.fs:66-68) commutes inside a level; a culled pair can never collide as
-// long as every position used for detection stays within the margin of its step-start position,
-// which is checked on every integration; a violated margin or a full list restarts the step from
-// the published state with an 8x margin and then with the exact serial walk over ALL pairs.
+// list (CollisionResolver.fs:66-68) commutes inside a level.  A culled pair can never collide as
+// long as every position used for detection stays within the margin of the sphere centre; that is
+// checked on every re-integration.  A violated margin restarts the step from the published state
+// with an 8x margin; a full list, too many levels or a static body whose pose is not a fixed point
+// of integrate() sends the step to the exact serial walk over ALL pairs.
 // Static bodies do not serialise their pairs when their pose is a fixed point of integrate()
 // (checked every step); their angular momentum (Q2) is then summed per pair and folded in pair
 // order — equal to the reference up to floating-point association; the serial
@@ -33,12 +36,15 @@
 namespace psk {
 using namespace psp;
 
-constexpr int kThreads = 128;
-constexpr int kDynF = 18;  // doubles of dynamic state per body
-constexpr int kParF = 16;  // doubles of parameters per body
+constexpr int kDynF = 18;       // doubles of dynamic state per body
+constexpr int kParF = 16;       // doubles of parameters per body
+constexpr int kMaxLevels = 1022;
+constexpr int kMaxStatics = 4;  // static bodies per world whose pairs run in parallel (more -> serial walk)
+constexpr int kMaxThreads = 128;
 
 struct WorldStats {  // per world, accumulated over steps
     unsigned long long steps, tested, hits, contacts, fallback, overflow, ref_exc;
+    unsigned long long fb_margin, fb_capacity, fb_static;
     double max_pen;
     int nan_flag, pad;
 };
@@ -56,6 +62,7 @@ struct KArgs {
     const double* par;    // [total_bodies*16], per world planar
     const int* off;       // n_worlds+1
     WorldStats* stats;    // n_worlds
+    unsigned char* hitcnt;  // [total_bodies] colliding pairs each body was in during its last step (margin model)
     int n_worlds, n_steps;
     StepParams sp;
     int exact_all_pairs;
@@ -74,7 +81,6 @@ struct KArgs {
     int rec_pair_cap, rec_contact_cap;
     int max_n;                // largest world (sizes the shared-memory carve-up)
     int k_cap;                // near-list capacity
-    int ks_cap;               // static-pair slot capacity
 };
 
 // ---- shared-memory carve-up ------------------------------------------------------------------
@@ -82,42 +88,42 @@ struct Smem {
     double* dyn;     // 18*N  current bodies
     double* pred;    // 18*N  predicted bodies
     double* par;     // 16*N
-    double* sx;      // 3*N step-start positions
+    double* sx;      // 3*N cull-sphere centres (predicted positions)
     double* rad_s;   // N   cull radius against a sphere (margin included)
     double* rad_b;   // N   cull radius against a box
     double* marg2;   // N   squared margin
-    double* S;       // 3*ks_cap angular-momentum sums of static-body pairs
+    double* S;       // 3*kMaxStatics*N angular-momentum sums of static-body pairs, [static ordinal][partner]
     unsigned* near;  // k_cap  i | j<<16
-    int* lvl_start;  // k_cap+2
+    int* lvl_start;  // kMaxLevels+2
     int* row;        // N+1
-    int* srow;       // N+1
     unsigned short* level;  // k_cap
     unsigned short* order;  // k_cap
-    unsigned short* sslot;  // k_cap
     unsigned short* last;   // N
     unsigned char* pvalid;  // N
-    unsigned char* isstat;  // N
+    unsigned char* isstat;  // N   0 dynamic, 1+ordinal static
     unsigned char* hit;     // k_cap
+    unsigned char* nhit;    // N   colliding pairs of the body this step (saturating)
+    unsigned char* nprev;   // N   ... during the previous step
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline size_t smem_bytes(int N, int k_cap, int ks_cap)
+__host__ __device__ inline size_t smem_bytes(int N, int k_cap)
 {
     size_t b = 0;
     b += sizeof(double) * (size_t)(kDynF * N) * 2;
     b += sizeof(double) * (size_t)(kParF * N);
-    b += sizeof(double) * (size_t)(3 * N + 3 * N);
-    b += sizeof(double) * (size_t)(3 * ks_cap);
+    b += sizeof(double) * (size_t)(6 * N);
+    b += sizeof(double) * (size_t)(3 * kMaxStatics * N);
     b += sizeof(unsigned) * (size_t)k_cap;
-    b += sizeof(int) * (size_t)(k_cap + 2);
-    b += sizeof(int) * (size_t)(2 * (N + 1));
-    b += sizeof(unsigned short) * (size_t)(3 * k_cap + N);
-    b += (size_t)(2 * N + k_cap);
+    b += sizeof(int) * (size_t)(kMaxLevels + 2);
+    b += sizeof(int) * (size_t)(N + 1);
+    b += sizeof(unsigned short) * (size_t)(2 * k_cap + N);
+    b += (size_t)(4 * N + k_cap);
     return align_up(b, 16) + 64;
 }
 
-__device__ inline void carve(unsigned char* base, int N, int k_cap, int ks_cap, Smem& s)
+__device__ inline void carve(unsigned char* base, int N, int k_cap, Smem& s)
 {
     double* d = reinterpret_cast<double*>(base);
     s.dyn = d;    d += kDynF * N;
@@ -127,21 +133,21 @@ __device__ inline void carve(unsigned char* base, int N, int k_cap, int ks_cap, 
     s.rad_s = d;  d += N;
     s.rad_b = d;  d += N;
     s.marg2 = d;  d += N;
-    s.S = d;      d += 3 * ks_cap;
+    s.S = d;      d += 3 * kMaxStatics * N;
     unsigned* u = reinterpret_cast<unsigned*>(d);
     s.near = u;   u += k_cap;
     int* ip = reinterpret_cast<int*>(u);
-    s.lvl_start = ip; ip += k_cap + 2;
+    s.lvl_start = ip; ip += kMaxLevels + 2;
     s.row = ip;   ip += N + 1;
-    s.srow = ip;  ip += N + 1;
     unsigned short* h = reinterpret_cast<unsigned short*>(ip);
     s.level = h;  h += k_cap;
     s.order = h;  h += k_cap;
-    s.sslot = h;  h += k_cap;
     s.last = h;   h += N;
     unsigned char* c = reinterpret_cast<unsigned char*>(h);
     s.pvalid = c; c += N;
     s.isstat = c; c += N;
+    s.nhit = c;   c += N;
+    s.nprev = c;  c += N;
     s.hit = c;
 }
 
@@ -162,7 +168,8 @@ PSD void st_dyn(double* a, int N, int b, const Dyn& d)
     for (int k = 0; k < 9; k++) a[(6 + k) * N + b] = d.R.a[k];
     a[15 * N + b] = d.L.x; a[16 * N + b] = d.L.y; a[17 * N + b] = d.L.z;
 }
-// parameter planes: 0 1/mass (host-evaluated 1.0/mass, what Vector3D `/` multiplies by), 1-3 iinv, 4-6 F, 7-9 T, 10 e, 11 mu_k, 12-14 dims, 15 shape
+// parameter planes: 0 1/mass (host-evaluated 1.0/mass, what Vector3D `/` multiplies by), 1-3 iinv,
+// 4-6 F, 7-9 T, 10 e, 11 mu_k, 12-14 dims, 15 shape
 PSD void ld_par(const double* a, int N, int b, Par& p)
 {
     p.inv_mass = a[b];
@@ -185,24 +192,24 @@ PSD bool pose_fixed(const Dyn& a, const Dyn& b)
     for (int k = 0; k < 9; k++) ok = ok && same_bits(a.R.a[k], b.R.a[k]);
     return ok;
 }
-PSD bool finite3(d3 v) { return isfinite(v.x) && isfinite(v.y) && isfinite(v.z); }
-
-struct Ctx {
-    Smem s;
-    int N, w, tid;
-    const KArgs* a;
-    // per-thread counters of the current attempt
-    unsigned tested, hits, contacts, overflow, ref_exc;
-    double max_pen;
-};
 
 // block-wide flags / counters in static shared memory
 struct BlockShared {
-    int violate;       // margin violated or capacity exceeded -> restart
-    int need_serial;   // a static pose is not a fixed point
-    int K, KS, maxl;
+    int violate;      // a margin was violated -> restart with a wider one
+    int need_serial;  // a static pose moves / list full / too many levels -> exact serial walk
+    int K, maxl, nstat;
     unsigned tested, hits, contacts, overflow, ref_exc;
     unsigned long long max_pen_bits;
+};
+
+struct Ctx {
+    Smem s;
+    int N, w;
+    const KArgs* a;
+    BlockShared* bs;
+    // per-thread counters of the current attempt
+    unsigned tested, hits, contacts, overflow, ref_exc;
+    double max_pen;
 };
 
 // record one colliding pair for ps_batch_get_contacts
@@ -228,7 +235,7 @@ PSD void record_pair(const Ctx& c, int i, int j, const Contact* cs, int nc)
 
 // predicted copy of body b, integrating it first if an earlier pair changed it (lazy refresh).
 // check_margin: the position is about to be used for detection under a culled pair list.
-PSD void get_pred(Ctx& c, int b, const Par& p, Dyn& out, bool check_margin, BlockShared& bs)
+PSD void get_pred(Ctx& c, int b, const Par& p, Dyn& out, bool check_margin)
 {
     if (c.s.pvalid[b]) {
         ld_dyn(c.s.pred, c.N, b, out);
@@ -242,20 +249,26 @@ PSD void get_pred(Ctx& c, int b, const Par& p, Dyn& out, bool check_margin, Bloc
     if (check_margin) {
         d3 d = out.x - mk(c.s.sx[b], c.s.sx[c.N + b], c.s.sx[2 * c.N + b]);
         double dd = d.x * d.x + d.y * d.y + d.z * d.z;
-        if (!(dd <= c.s.marg2[b])) bs.violate = 1;
+        if (!(dd <= c.s.marg2[b])) c.bs->violate = 1;
     }
 }
 
+PSD void bump(unsigned char* p)  // saturating per-body hit counter (the body is owned by this thread at this level)
+{
+    unsigned v = *p;
+    if (v < 255u) *p = (unsigned char)(v + 1u);
+}
+
 // one candidate pair of the ordered fold (CollisionResolver.fs:40-46, 13-38).
-// fast != 0: static bodies are shared (pose fixed): their L is summed into slot `sslot`.
-PSD void process_pair(Ctx& c, int i, int j, int near_k, bool fast, BlockShared& bs)
+// fast: static bodies are shared (pose fixed): their angular-momentum sum goes to S[ordinal][partner].
+PSD void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
 {
     Par pi, pj;
     ld_par(c.s.par, c.N, i, pi);
     ld_par(c.s.par, c.N, j, pj);
     Dyn di, dj;
-    get_pred(c, i, pi, di, fast, bs);
-    get_pred(c, j, pj, dj, fast, bs);
+    get_pred(c, i, pi, di, fast);
+    get_pred(c, j, pj, dj, fast);
     Contact cs[PS_MAX_CONTACTS];
     int err = 0, ovf = 0;
     c.tested++;
@@ -273,16 +286,25 @@ PSD void process_pair(Ctx& c, int i, int j, int near_k, bool fast, BlockShared& 
     CPData cp[PS_MAX_CONTACTS];
     resolve(di, pi, dj, pj, cs, nc, cp, c.a->sp);
     if (fast) c.s.hit[near_k] = 1;
-    if (si || sj) {
-        int slot = c.s.sslot[near_k];
-        d3 sum = si ? di.L : dj.L;  // a static-static pair never reaches here (canIntersect)
-        c.s.S[3 * slot] = sum.x; c.s.S[3 * slot + 1] = sum.y; c.s.S[3 * slot + 2] = sum.z;
+    if (si) {  // a static-static pair never reaches here (canIntersect)
+        double* S = c.s.S + 3 * ((c.s.isstat[i] - 1) * c.N + j);
+        S[0] = di.L.x; S[1] = di.L.y; S[2] = di.L.z;
+    } else {
+        st_dyn(c.s.dyn, c.N, i, di);  // write back (CollisionResolver.fs:27-31)
+        c.s.pvalid[i] = 0;
+        bump(&c.s.nhit[i]);
     }
-    if (!si) { st_dyn(c.s.dyn, c.N, i, di); c.s.pvalid[i] = 0; }  // write back (CollisionResolver.fs:27-31)
-    if (!sj) { st_dyn(c.s.dyn, c.N, j, dj); c.s.pvalid[j] = 0; }
+    if (sj) {
+        double* S = c.s.S + 3 * ((c.s.isstat[j] - 1) * c.N + i);
+        S[0] = dj.L.x; S[1] = dj.L.y; S[2] = dj.L.z;
+    } else {
+        st_dyn(c.s.dyn, c.N, j, dj);
+        c.s.pvalid[j] = 0;
+        bump(&c.s.nhit[j]);
+    }
 }
 
-// conservative "may these two ever collide during this step" test on step-start positions
+// conservative "may these two ever collide during this step" test on the cull spheres
 PSD bool near_test(const Smem& s, int N, int i, int j)
 {
     if (s.isstat[i] && s.isstat[j]) return false;  // canIntersect (CollisionResolver.fs:58-60)
@@ -295,7 +317,8 @@ PSD bool near_test(const Smem& s, int N, int i, int j)
     return !(dd > r * r);  // NaN -> near
 }
 
-__global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
+template <int T>
+__global__ void __launch_bounds__(T) step_kernel(KArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BlockShared bs;
@@ -306,44 +329,56 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
     const int off = a.off[w];
     const int N = a.off[w + 1] - off;
     Ctx c;
-    c.N = N; c.w = w; c.tid = tid; c.a = &a;
-    carve(smem_raw, N, a.k_cap, a.ks_cap, c.s);
+    c.N = N; c.w = w; c.a = &a; c.bs = &bs;
+    carve(smem_raw, N, a.k_cap, c.s);
     Smem& s = c.s;
     double* gdyn = a.dyn + (size_t)off * kDynF;
     const double* gpar = a.par + (size_t)off * kParF;
     const StepParams sp = a.sp;
 
     // world -> shared memory (coalesced, contiguous per world)
-    for (int k = tid; k < kDynF * N; k += kThreads) s.dyn[k] = gdyn[k];
-    for (int k = tid; k < kParF * N; k += kThreads) s.par[k] = gpar[k];
+    for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
+    for (int k = tid; k < kParF * N; k += T) s.par[k] = gpar[k];
+    for (int b = tid; b < N; b += T) s.nprev[b] = a.hitcnt[off + b];
     __syncthreads();
-    for (int b = tid; b < N; b += kThreads) s.isstat[b] = (s.par[b] == 0.0) ? 1 : 0;
+    if (tid == 0) {  // static ordinals (1-based); more than kMaxStatics -> always the serial walk
+        int ns = 0;
+        for (int b = 0; b < N; b++) {
+            if (s.par[b] == 0.0) { ns++; s.isstat[b] = (unsigned char)(ns <= kMaxStatics ? ns : kMaxStatics); }
+            else s.isstat[b] = 0;
+        }
+        bs.nstat = ns;
+    }
+    __syncthreads();
 
     unsigned long long t_steps = 0, t_tested = 0, t_hits = 0, t_contacts = 0, t_fallback = 0, t_overflow = 0, t_exc = 0;
+    unsigned long long t_fbm = 0, t_fbc = 0, t_fbs = 0;
     double t_maxpen = 0.0;
 
     for (int step = 0; step < a.n_steps; step++) {
         // attempts: 0 = margin x1, 1 = margin x8, 2 = exact serial walk over all pairs
-        int attempt = a.exact_all_pairs ? 2 : 0;
+        int attempt = (a.exact_all_pairs || bs.nstat > kMaxStatics) ? 2 : 0;
+        int fb_reason = 0;  // 1 margin, 2 capacity/levels, 3 static pose
         for (;; attempt++) {
             if (tid == 0) {
-                bs.violate = 0; bs.need_serial = 0; bs.K = 0; bs.KS = 0; bs.maxl = 0;
+                bs.violate = 0; bs.need_serial = 0; bs.K = 0; bs.maxl = 0;
                 bs.tested = bs.hits = bs.contacts = bs.overflow = bs.ref_exc = 0;
                 bs.max_pen_bits = 0ull;
                 if (a.rec_counts) { a.rec_counts[2 * w] = 0; a.rec_counts[2 * w + 1] = 0; }
             }
             c.tested = c.hits = c.contacts = c.overflow = c.ref_exc = 0;
             c.max_pen = 0.0;
-            for (int b = tid; b < N; b += kThreads) s.pvalid[b] = 0;
+            for (int b = tid; b < N; b += T) { s.pvalid[b] = 0; s.nhit[b] = 0; }
             __syncthreads();
 
             if (attempt < 2) {
-                // ---- A: predicted copy of every body (CollisionResolver.fs:42-43) + cull spheres ------------
+                // ---- A: predicted copy of every body + cull spheres -----------------------------------
                 // The sphere is centred on the PREDICTED position: a body no pair has changed is tested
-                // exactly there (deviation 0); after a write-back the position is unchanged and the next
-                // prediction moves it by v'*dt only, which the margin has to cover.
+                // exactly there (deviation 0).  A write-back keeps the position, and each further
+                // prediction moves it by dt * (its new velocity): the margin covers n such moves, n
+                // estimated from the number of colliding pairs the body was in during the previous step.
                 const double mscale = attempt == 0 ? 1.0 : 8.0;
-                for (int b = tid; b < N; b += kThreads) {
+                for (int b = tid; b < N; b += T) {
                     Par p; ld_par(s.par, N, b, p);
                     Dyn cur, pr;
                     ld_dyn(s.dyn, N, b, cur);
@@ -353,7 +388,9 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
                     if (p.is_static && !pose_fixed(cur, pr)) bs.need_serial = 1;
                     s.sx[b] = pr.x.x; s.sx[N + b] = pr.x.y; s.sx[2 * N + b] = pr.x.z;
                     double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
-                    double m = p.is_static ? 0.0 : mscale * (0.02 + 3.0 * speed * sp.dt);
+                    double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
+                    double n = (double)s.nprev[b] + 2.0;
+                    double m = p.is_static ? 0.0 : mscale * (0.01 + n * sp.dt * (speed + n * acc * sp.dt + 0.5));
                     if (!(m == m)) m = 0.0;  // NaN state: the world is flagged anyway
                     double rs, rb;
                     if (p.shape == 0) {
@@ -371,52 +408,41 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
                 __syncthreads();
                 if (bs.need_serial) {  // a static pose still moves under integrate(): exact serial walk this step
                     __syncthreads();   // every thread has read the flag before thread 0 clears it at the loop top
-                    attempt = 1;
+                    attempt = 1; fb_reason = 3;
                     continue;          // state untouched so far: no reload needed
                 }
-                // ---- B: near list, lexicographic order kept by a row scan ------------------------
-                for (int i = tid; i < N; i += kThreads) {
-                    int cn = 0, cs_ = 0;
-                    for (int j = i + 1; j < N; j++)
-                        if (near_test(s, N, i, j)) {
-                            cn++;
-                            if (s.isstat[i] | s.isstat[j]) cs_++;
-                        }
-                    s.row[i] = cn; s.srow[i] = cs_;
+                // ---- B: near list, lexicographic order kept by a row scan -------------------------------
+                for (int i = tid; i < N; i += T) {
+                    int cn = 0;
+                    for (int j = i + 1; j < N; j++) cn += near_test(s, N, i, j) ? 1 : 0;
+                    s.row[i] = cn;
                 }
                 __syncthreads();
                 if (tid == 0) {
-                    int acc = 0, sacc = 0;
-                    for (int i = 0; i < N; i++) {
-                        int t = s.row[i]; s.row[i] = acc; acc += t;
-                        int u = s.srow[i]; s.srow[i] = sacc; sacc += u;
-                    }
-                    s.row[N] = acc; s.srow[N] = sacc;
-                    bs.K = acc; bs.KS = sacc;
-                    if (acc > a.k_cap || sacc > a.ks_cap) bs.need_serial = 1;  // list full: a wider margin cannot help
+                    int acc = 0;
+                    for (int i = 0; i < N; i++) { int t = s.row[i]; s.row[i] = acc; acc += t; }
+                    s.row[N] = acc;
+                    bs.K = acc;
+                    if (acc > a.k_cap) bs.need_serial = 1;  // list full: a wider margin cannot help
                 }
                 __syncthreads();
                 const int K = bs.K;
                 if (bs.need_serial) {
                     __syncthreads();
-                    attempt = 1;
+                    attempt = 1; fb_reason = 2;
                     continue;
                 }
-                {
-                    for (int i = tid; i < N; i += kThreads) {
-                        int o = s.row[i], so = s.srow[i];
-                        for (int j = i + 1; j < N; j++)
-                            if (near_test(s, N, i, j)) {
-                                s.near[o] = (unsigned)i | ((unsigned)j << 16);
-                                s.hit[o] = 0;
-                                if (s.isstat[i] | s.isstat[j]) s.sslot[o] = (unsigned short)so++;
-                                else s.sslot[o] = 0xffff;
-                                o++;
-                            }
-                    }
+                for (int i = tid; i < N; i += T) {
+                    int o = s.row[i];
+                    for (int j = i + 1; j < N; j++)
+                        if (near_test(s, N, i, j)) {
+                            s.near[o] = (unsigned)i | ((unsigned)j << 16);
+                            s.hit[o] = 0;
+                            o++;
+                        }
                 }
                 __syncthreads();
-                // ---- C: wavefront levels (serial scan of the ordered list by one thread) -------------------
+                // ---- C: wavefront levels (serial scan of the ordered list by one thread) ------------------
                 if (tid == 0) {
                     int maxl = 0;
                     for (int k = 0; k < K; k++) {
@@ -431,13 +457,19 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
                         if (l > maxl) maxl = l;
                     }
                     bs.maxl = maxl;
+                    if (maxl > kMaxLevels) bs.need_serial = 1;
                 }
                 __syncthreads();
+                if (bs.need_serial) {
+                    __syncthreads();
+                    attempt = 1; fb_reason = 2;
+                    continue;
+                }
                 // counting sort of the near list by level (order inside a level is free)
                 const int maxl = bs.maxl;
-                for (int l = tid; l <= maxl + 1; l += kThreads) s.lvl_start[l] = 0;
+                for (int l = tid; l <= maxl + 1; l += T) s.lvl_start[l] = 0;
                 __syncthreads();
-                for (int k = tid; k < K; k += kThreads) atomicAdd(&s.lvl_start[s.level[k]], 1);
+                for (int k = tid; k < K; k += T) atomicAdd(&s.lvl_start[s.level[k]], 1);
                 __syncthreads();
                 if (tid == 0) {
                     int acc = 0;
@@ -445,67 +477,77 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
                 }
                 __syncthreads();
                 // scatter; lvl_start[l] is advanced to the END of level l, i.e. the start of l+1
-                for (int k = tid; k < K; k += kThreads) {
+                for (int k = tid; k < K; k += T) {
                     int pos = atomicAdd(&s.lvl_start[s.level[k]], 1);
                     s.order[pos] = (unsigned short)k;
                 }
                 __syncthreads();
-                // ---- D: wavefronts ---------------------------------------------------------------
+                // ---- D: wavefronts ------------------------------------------------------------------------
                 for (int l = 1; l <= maxl; l++) {
                     int beg = s.lvl_start[l - 1], end = s.lvl_start[l];
-                    for (int q = beg + tid; q < end; q += kThreads) {
+                    for (int q = beg + tid; q < end; q += T) {
                         int k = s.order[q];
                         unsigned ij = s.near[k];
-                        process_pair(c, ij & 0xffff, ij >> 16, k, true, bs);
+                        process_pair(c, ij & 0xffff, ij >> 16, k, true);
                     }
                     __syncthreads();
                 }
-                if (bs.violate) {
-                    for (int k = tid; k < kDynF * N; k += kThreads) s.dyn[k] = gdyn[k];
+                if (bs.violate) {  // restart from the published state
+                    for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
                     __syncthreads();
+                    fb_reason = 1;
                     continue;
                 }
-                // ---- E: static bodies: L = fold over their colliding pairs in pair order -----------
-                for (int b = tid; b < N; b += kThreads) {
+                // ---- E: static bodies: L = fold over their colliding pairs in pair order -------------------
+                for (int b = tid; b < N; b += T) {
                     if (!s.isstat[b]) continue;
                     Par p; ld_par(s.par, N, b, p);
                     d3 L = mk(s.dyn[15 * N + b], s.dyn[16 * N + b], s.dyn[17 * N + b]);
                     d3 dL = scale(sp.dt, p.T);
+                    const double* Sb = s.S + 3 * (s.isstat[b] - 1) * N;
                     for (int k = 0; k < K; k++) {
                         if (!s.hit[k]) continue;
                         unsigned ij = s.near[k];
-                        if ((int)(ij & 0xffff) != b && (int)(ij >> 16) != b) continue;
-                        int slot = s.sslot[k];
+                        int i = ij & 0xffff, j = ij >> 16;
+                        int other;
+                        if (i == b) other = j; else if (j == b) other = i; else continue;
                         L = L + dL;  // the predicted copy's integration
-                        L = L + mk(s.S[3 * slot], s.S[3 * slot + 1], s.S[3 * slot + 2]);
+                        L = L + mk(Sb[3 * other], Sb[3 * other + 1], Sb[3 * other + 2]);
                     }
                     s.dyn[15 * N + b] = L.x; s.dyn[16 * N + b] = L.y; s.dyn[17 * N + b] = L.z;
                     // pose is a fixed point: the final sweep only has to add dt*T to L
-                    s.pred[15 * N + b] = (L + dL).x; s.pred[16 * N + b] = (L + dL).y; s.pred[17 * N + b] = (L + dL).z;
+                    d3 Lf = L + dL;
+                    s.pred[15 * N + b] = Lf.x; s.pred[16 * N + b] = Lf.y; s.pred[17 * N + b] = Lf.z;
                 }
                 __syncthreads();
             } else {
-                // ---- exact serial walk over ALL pairs in Dummy order (BroadPhase.fs:33-39) -----------
+                // ---- exact serial walk over ALL pairs in Dummy order (BroadPhase.fs:33-39) -------------------
                 if (tid == 0) {
                     for (int i = 0; i < N; i++)
                         for (int j = i + 1; j < N; j++) {
                             if (s.isstat[i] && s.isstat[j]) continue;
-                            process_pair(c, i, j, 0, false, bs);
+                            process_pair(c, i, j, 0, false);
                         }
                 }
                 __syncthreads();
             }
             break;
         }
-        if (attempt > 0 && !a.exact_all_pairs) t_fallback += (tid == 0) ? 1 : 0;
+        if (tid == 0 && attempt > 0 && !a.exact_all_pairs) {
+            t_fallback++;
+            if (fb_reason == 1) t_fbm++; else if (fb_reason == 2) t_fbc++; else t_fbs++;
+        }
 
-        // ---- J: joints (JointsRestorer.fs:9-26, Joints.fs:26-94) — all read the entry state --------
+        // ---- J: joints (JointsRestorer.fs:9-26, Joints.fs:26-94) — all read the entry state ----------------
         if (a.restore_joints && a.joff) {
-            int j0 = a.joff[w], nj = a.joff[w + 1] - j0;
+            // every joint reads the state at entry, so a chunk computes, syncs, then writes; the host limits a
+            // world to T joints (ps_batch_create) so that there is exactly one chunk
+            const int j0 = a.joff[w], nj = a.joff[w + 1] - j0;
             Dyn o1, o2;
             int ba = -1, bb = -1;
             unsigned char lastf = 0;
-            if (tid < nj) {
+            const bool act = tid < nj;
+            if (act) {
                 int q = j0 + tid;
                 ba = a.ja[q]; bb = a.jb[q];
                 lastf = a.jlast[q];
@@ -518,7 +560,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
                 d3 la = mk(a.jla[3 * q], a.jla[3 * q + 1], a.jla[3 * q + 2]);
                 d3 lb = mk(a.jlb[3 * q], a.jlb[3 * q + 1], a.jlb[3 * q + 2]);
                 m33 Iw1 = inertia_inv_world(e1.R, p1.iinv), Iw2 = inertia_inv_world(e2.R, p2.iinv);
-                d3 aw1 = mulMV(e1.R, la), aw2 = mulMV(e2.R, lb);  // JointImpulseData.init
+                d3 aw1 = mulMV(e1.R, la), aw2 = mulMV(e2.R, lb);  // JointImpulseData.init (Joints.fs:26-40)
                 m33 K;
 #pragma unroll
                 for (int k = 0; k < 9; k++) K.a[k] = 0.0;
@@ -533,15 +575,15 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
                 }
             }
             __syncthreads();
-            if (tid < nj) {
+            if (act) {
                 if (lastf & 1) { st_dyn(s.dyn, N, ba, o1); s.pvalid[ba] = 0; }
                 if (lastf & 2) { st_dyn(s.dyn, N, bb, o2); s.pvalid[bb] = 0; }
             }
             __syncthreads();
         }
 
-        // ---- F: final integration of every body (SimulatorState.fs:169-173) ---------------------------
-        for (int b = tid; b < N; b += kThreads) {
+        // ---- F: final integration of every body (SimulatorState.fs:169-173) -----------------------------------
+        for (int b = tid; b < N; b += T) {
             Dyn out;
             if (s.pvalid[b]) {
                 ld_dyn(s.pred, N, b, out);
@@ -551,10 +593,11 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
                 integrate(cur, p, sp, out);
             }
             st_dyn(s.dyn, N, b, out);
+            s.nprev[b] = s.nhit[b];
         }
         __syncthreads();
         // publish the step (also the restart point of the next step's fallback)
-        for (int k = tid; k < kDynF * N; k += kThreads) gdyn[k] = s.dyn[k];
+        for (int k = tid; k < kDynF * N; k += T) gdyn[k] = s.dyn[k];
 
         // fold per-thread counters
         atomicAdd(&bs.tested, c.tested); atomicAdd(&bs.hits, c.hits); atomicAdd(&bs.contacts, c.contacts);
@@ -571,12 +614,14 @@ __global__ void __launch_bounds__(kThreads) step_kernel(KArgs a)
 
     // NaN/Inf scan + stats write-out
     int bad = 0;
-    for (int k = tid; k < kDynF * N; k += kThreads) bad |= !isfinite(s.dyn[k]);
+    for (int k = tid; k < kDynF * N; k += T) bad |= !isfinite(s.dyn[k]);
     bad = __syncthreads_or(bad);
+    for (int b = tid; b < N; b += T) a.hitcnt[off + b] = s.nprev[b];
     if (tid == 0) {
         WorldStats& st = a.stats[w];
         st.steps += t_steps; st.tested += t_tested; st.hits += t_hits; st.contacts += t_contacts;
         st.fallback += t_fallback; st.overflow += t_overflow; st.ref_exc += t_exc;
+        st.fb_margin += t_fbm; st.fb_capacity += t_fbc; st.fb_static += t_fbs;
         st.max_pen = fmax(st.max_pen, t_maxpen);
         st.nan_flag = bad ? 1 : 0;
     }
