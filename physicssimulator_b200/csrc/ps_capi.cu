@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -65,6 +66,7 @@ struct Batch {
     int* d_off = nullptr;
     WorldStats* d_stats = nullptr;
     unsigned char* d_hitcnt = nullptr;
+    double *d_cur = nullptr, *d_pred = nullptr, *d_S = nullptr;  // per-world scratch of the step kernel
     int *d_joff = nullptr, *d_ja = nullptr, *d_jb = nullptr;
     double *d_jla = nullptr, *d_jlb = nullptr;
     unsigned char* d_jlast = nullptr;
@@ -92,15 +94,15 @@ __global__ void pack_dyn_kernel(const int* __restrict__ off, int w0, int w1, con
         int mid = (lo + hi) >> 1;
         if (off[mid] <= g) lo = mid; else hi = mid;
     }
-    int o = off[lo], N = off[lo + 1] - o, b = g - o;
-    double* d = dyn + (size_t)o * kDynF;
+    (void)lo;
+    double* d = dyn + (size_t)g * kDynF;  // body-major record
     int s = g - body0;  // index into the caller arrays (which start at world w0)
     for (int k = 0; k < 3; k++) {
-        d[k * N + b] = pos[3 * s + k];
-        d[(3 + k) * N + b] = vel[3 * s + k];
-        d[(15 + k) * N + b] = L[3 * s + k];
+        d[k] = pos[3 * s + k];
+        d[3 + k] = vel[3 * s + k];
+        d[15 + k] = L[3 * s + k];
     }
-    for (int k = 0; k < 9; k++) d[(6 + k) * N + b] = rot[9 * s + k];
+    for (int k = 0; k < 9; k++) d[6 + k] = rot[9 * s + k];
 }
 __global__ void unpack_dyn_kernel(const int* __restrict__ off, int w0, int w1, double* __restrict__ pos,
                                   double* __restrict__ vel, double* __restrict__ rot, double* __restrict__ L,
@@ -113,16 +115,16 @@ __global__ void unpack_dyn_kernel(const int* __restrict__ off, int w0, int w1, d
         int mid = (lo + hi) >> 1;
         if (off[mid] <= g) lo = mid; else hi = mid;
     }
-    int o = off[lo], N = off[lo + 1] - o, b = g - o;
-    const double* d = dyn + (size_t)o * kDynF;
+    (void)lo;
+    const double* d = dyn + (size_t)g * kDynF;
     int s = g - body0;
     for (int k = 0; k < 3; k++) {
-        if (pos) pos[3 * s + k] = d[k * N + b];
-        if (vel) vel[3 * s + k] = d[(3 + k) * N + b];
-        if (L) L[3 * s + k] = d[(15 + k) * N + b];
+        if (pos) pos[3 * s + k] = d[k];
+        if (vel) vel[3 * s + k] = d[3 + k];
+        if (L) L[3 * s + k] = d[15 + k];
     }
     if (rot)
-        for (int k = 0; k < 9; k++) rot[9 * s + k] = d[(6 + k) * N + b];
+        for (int k = 0; k < 9; k++) rot[9 * s + k] = d[6 + k];
 }
 
 // Simulator.ApplyImpulse -> RigidBodyMotion.applyImpulse (RigidBody.fs:194-197)
@@ -152,7 +154,7 @@ __global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const 
         mp = fmax(mp, s.max_pen);
         int o = off[w], N = off[w + 1] - o, dynb = 0;
         const double* p = par + (size_t)o * kParF;
-        for (int b = 0; b < N; b++) dynb += (p[b] != 0.0);
+        for (int b = 0; b < N; b++) dynb += (p[(size_t)b * kParF] != 0.0);
         bsteps += s.steps * (unsigned long long)dynb;
     }
     atomicAdd((unsigned long long*)&out->steps, steps);
@@ -179,7 +181,7 @@ void dfree(T*& p)
 }
 void free_device(Batch* B)
 {
-    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt);
+    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S);
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
 }
@@ -216,8 +218,9 @@ int upload(Batch* B, bool with_state)
     for (int i = 0; i < B->n_bodies; i++) B->n_dynamic += std::isinf(h.mass[i]) ? 0 : 1;
     // near-list capacity: all pairs for small worlds, 16 per body otherwise (a fuller list takes the serial walk)
     B->k_cap = std::max(32, std::min(B->max_n * (B->max_n - 1) / 2, 16 * B->max_n));
-    // CTA width: a wavefront level rarely holds more pairs than bodies/4; narrow CTAs let more worlds share an SM
-    B->threads = B->max_n <= 80 ? 32 : (B->max_n <= 200 ? 64 : 128);
+    // CTA width: a wavefront level holds ~10 pairs for a 128-body pile; one warp per world lets many worlds share an SM
+    B->threads = B->max_n <= 256 ? 32 : (B->max_n <= 512 ? 64 : 128);
+    if (const char* e = getenv("PS_B200_CTA")) { int t = atoi(e); if (t == 32 || t == 64 || t == 128) B->threads = t; }  // tuning knob
     B->smem = smem_bytes(B->max_n, B->k_cap);
     int dev_max = 0;
     CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, B->device));
@@ -234,29 +237,28 @@ int upload(Batch* B, bool with_state)
     CK(cudaMalloc(&B->d_off, (size_t)(B->n_worlds + 1) * sizeof(int)));
     CK(cudaMalloc(&B->d_stats, (size_t)std::max(1, B->n_worlds) * sizeof(WorldStats)));
     CK(cudaMalloc(&B->d_stats_sum, sizeof(ps_stats)));
+    CK(cudaMalloc(&B->d_cur, nb * kDynF * sizeof(double)));
+    CK(cudaMalloc(&B->d_pred, nb * kDynF * sizeof(double)));
+    CK(cudaMalloc(&B->d_S, nb * 3 * kMaxStatics * sizeof(double)));
     CK(cudaMalloc(&B->d_hitcnt, nb));
     CK(cudaMemsetAsync(B->d_hitcnt, 0, nb, B->stream));
     CK(cudaMemsetAsync(B->d_stats, 0, (size_t)std::max(1, B->n_worlds) * sizeof(WorldStats), B->stream));
     CK(cudaMemcpyAsync(B->d_off, h.off.data(), (size_t)(B->n_worlds + 1) * sizeof(int), cudaMemcpyHostToDevice, B->stream));
 
-    // parameters -> per-world planar (plane 0 = 1.0/mass, IEEE division as on the reference's `v / mass`)
+    // parameters -> body-major records (slot 0 = 1.0/mass, IEEE division as on the reference's `v / mass`)
     std::vector<double> par(nb * kParF, 0.0);
-    for (int w = 0; w < B->n_worlds; w++) {
-        int o = h.off[w], N = h.off[w + 1] - o;
-        double* p = par.data() + (size_t)o * kParF;
-        for (int b = 0; b < N; b++) {
-            int g = o + b;
-            p[b] = 1.0 / h.mass[g];
-            for (int k = 0; k < 3; k++) {
-                p[(1 + k) * N + b] = h.iinv[3 * g + k];
-                p[(4 + k) * N + b] = h.force[3 * g + k];
-                p[(7 + k) * N + b] = h.torque[3 * g + k];
-                p[(12 + k) * N + b] = h.dims[3 * g + k];
-            }
-            p[10 * N + b] = h.e[g];
-            p[11 * N + b] = h.muk[g];
-            p[15 * N + b] = (double)h.shape[g];
+    for (int g = 0; g < B->n_bodies; g++) {
+        double* p = par.data() + (size_t)g * kParF;
+        p[0] = 1.0 / h.mass[g];
+        for (int k = 0; k < 3; k++) {
+            p[1 + k] = h.iinv[3 * g + k];
+            p[4 + k] = h.force[3 * g + k];
+            p[7 + k] = h.torque[3 * g + k];
+            p[12 + k] = h.dims[3 * g + k];
         }
+        p[10] = h.e[g];
+        p[11] = h.muk[g];
+        p[15] = (double)h.shape[g];
     }
     CK(cudaMemcpyAsync(B->d_par, par.data(), nb * kParF * sizeof(double), cudaMemcpyHostToDevice, B->stream));
     CK(cudaStreamSynchronize(B->stream));  // `par` is a local
@@ -449,7 +451,7 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
     a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
     a.max_n = B->max_n; a.k_cap = B->k_cap;
-    a.hitcnt = B->d_hitcnt;
+    a.hitcnt = B->d_hitcnt; a.cur = B->d_cur; a.pred = B->d_pred; a.S = B->d_S;
     if (B->threads == 32) step_kernel<32><<<B->n_worlds, 32, B->smem, st>>>(a);
     else if (B->threads == 64) step_kernel<64><<<B->n_worlds, 64, B->smem, st>>>(a);
     else step_kernel<128><<<B->n_worlds, 128, B->smem, st>>>(a);

@@ -1,10 +1,12 @@
 // ps_step_kernel.cuh — the fused per-world step kernel (one CTA per world).
 //
-// One CTA owns one world for n_steps steps; the world's state lives in shared memory for the
-// whole launch (HBM is touched once per step to publish the state, which doubles as the
-// restart point of the exact fallback).  The CTA width T is 32, 64 or 128 threads, chosen by the
-// host from the world size: a level of the wavefront rarely holds more pairs than that, and narrow
-// CTAs let many worlds share one SM.
+// One CTA owns one world for n_steps steps.  The bodies live in a per-world scratch record in global
+// memory (body-major, 144 B of state + 128 B of parameters per body, read with 16-byte loads; the
+// working set of the resident CTAs sits in L2/L1); shared memory only holds the per-step scheduling
+// data (cull spheres, near list, levels), ~10-17 KB per world, so that many worlds share one SM: the
+// step is a chain of dependent FP64 operations per pair and needs warps, not bandwidth.  The state is
+// published to the batch buffer once per step, which doubles as the restart point of the fallback.
+// The CTA width T is one warp (32) unless the host asks for more.
 //
 // Per step (reference order: Simulator.fs:52-56 = resolveAll (CollisionResolver.fs:49-69) then
 // SimulatorState.update (SimulatorState.fs:169-173)):
@@ -58,11 +60,14 @@ struct RecContact {
 };
 
 struct KArgs {
-    double* dyn;          // [total_bodies*18], per world planar: dyn[off*18 + f*N + b]
-    const double* par;    // [total_bodies*16], per world planar
+    double* dyn;          // [total_bodies*18], body-major: dyn[(off+b)*18 + f]  f: x 0-2, v 3-5, R 6-14, L 15-17
+    const double* par;    // [total_bodies*16], body-major
     const int* off;       // n_worlds+1
     WorldStats* stats;    // n_worlds
     unsigned char* hitcnt;  // [total_bodies] colliding pairs each body was in during its last step (margin model)
+    double* cur;          // [total_bodies*18] working copy of the state during a step
+    double* pred;         // [total_bodies*18] predicted copies
+    double* S;            // [total_bodies*3*kMaxStatics] angular-momentum sums of static-body pairs
     int n_worlds, n_steps;
     StepParams sp;
     int exact_all_pairs;
@@ -83,16 +88,16 @@ struct KArgs {
     int k_cap;                // near-list capacity
 };
 
-// ---- shared-memory carve-up ------------------------------------------------------------------
+// ---- shared-memory carve-up (scheduling data only) ----------------------------------------------
 struct Smem {
-    double* dyn;     // 18*N  current bodies
-    double* pred;    // 18*N  predicted bodies
-    double* par;     // 16*N
+    double* dyn;     // GLOBAL scratch: 18*N current bodies (body-major)
+    double* pred;    // GLOBAL scratch: 18*N predicted bodies
+    const double* par;  // GLOBAL: 16*N parameters
+    double* S;       // GLOBAL scratch: 3*kMaxStatics*N, [static ordinal][partner]
     double* sx;      // 3*N cull-sphere centres (predicted positions)
     double* rad_s;   // N   cull radius against a sphere (margin included)
     double* rad_b;   // N   cull radius against a box
     double* marg2;   // N   squared margin
-    double* S;       // 3*kMaxStatics*N angular-momentum sums of static-body pairs, [static ordinal][partner]
     unsigned* near;  // k_cap  i | j<<16
     int* lvl_start;  // kMaxLevels+2
     int* row;        // N+1
@@ -101,6 +106,7 @@ struct Smem {
     unsigned short* last;   // N
     unsigned char* pvalid;  // N
     unsigned char* isstat;  // N   0 dynamic, 1+ordinal static
+    unsigned char* isbox;   // N
     unsigned char* hit;     // k_cap
     unsigned char* nhit;    // N   colliding pairs of the body this step (saturating)
     unsigned char* nprev;   // N   ... during the previous step
@@ -111,29 +117,22 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 __host__ __device__ inline size_t smem_bytes(int N, int k_cap)
 {
     size_t b = 0;
-    b += sizeof(double) * (size_t)(kDynF * N) * 2;
-    b += sizeof(double) * (size_t)(kParF * N);
     b += sizeof(double) * (size_t)(6 * N);
-    b += sizeof(double) * (size_t)(3 * kMaxStatics * N);
     b += sizeof(unsigned) * (size_t)k_cap;
     b += sizeof(int) * (size_t)(kMaxLevels + 2);
     b += sizeof(int) * (size_t)(N + 1);
     b += sizeof(unsigned short) * (size_t)(2 * k_cap + N);
-    b += (size_t)(4 * N + k_cap);
+    b += (size_t)(5 * N + k_cap);
     return align_up(b, 16) + 64;
 }
 
 __device__ inline void carve(unsigned char* base, int N, int k_cap, Smem& s)
 {
     double* d = reinterpret_cast<double*>(base);
-    s.dyn = d;    d += kDynF * N;
-    s.pred = d;   d += kDynF * N;
-    s.par = d;    d += kParF * N;
     s.sx = d;     d += 3 * N;
     s.rad_s = d;  d += N;
     s.rad_b = d;  d += N;
     s.marg2 = d;  d += N;
-    s.S = d;      d += 3 * kMaxStatics * N;
     unsigned* u = reinterpret_cast<unsigned*>(d);
     s.near = u;   u += k_cap;
     int* ip = reinterpret_cast<int*>(u);
@@ -146,41 +145,49 @@ __device__ inline void carve(unsigned char* base, int N, int k_cap, Smem& s)
     unsigned char* c = reinterpret_cast<unsigned char*>(h);
     s.pvalid = c; c += N;
     s.isstat = c; c += N;
+    s.isbox = c;  c += N;
     s.nhit = c;   c += N;
     s.nprev = c;  c += N;
     s.hit = c;
 }
 
-// ---- planar accessors ------------------------------------------------------------------------
+// ---- body-major accessors (records are 16-byte aligned: 144 B and 128 B per body) ------------------
 PSD void ld_dyn(const double* a, int N, int b, Dyn& d)
 {
-    d.x = mk(a[b], a[N + b], a[2 * N + b]);
-    d.v = mk(a[3 * N + b], a[4 * N + b], a[5 * N + b]);
-#pragma unroll
-    for (int k = 0; k < 9; k++) d.R.a[k] = a[(6 + k) * N + b];
-    d.L = mk(a[15 * N + b], a[16 * N + b], a[17 * N + b]);
+    (void)N;
+    const double2* q = reinterpret_cast<const double2*>(a + (size_t)b * kDynF);
+    double2 t0 = q[0], t1 = q[1], t2 = q[2], t3 = q[3], t4 = q[4], t5 = q[5], t6 = q[6], t7 = q[7], t8 = q[8];
+    d.x = mk(t0.x, t0.y, t1.x);
+    d.v = mk(t1.y, t2.x, t2.y);
+    d.R.a[0] = t3.x; d.R.a[1] = t3.y; d.R.a[2] = t4.x; d.R.a[3] = t4.y; d.R.a[4] = t5.x; d.R.a[5] = t5.y;
+    d.R.a[6] = t6.x; d.R.a[7] = t6.y; d.R.a[8] = t7.x;
+    d.L = mk(t7.y, t8.x, t8.y);
 }
 PSD void st_dyn(double* a, int N, int b, const Dyn& d)
 {
-    a[b] = d.x.x; a[N + b] = d.x.y; a[2 * N + b] = d.x.z;
-    a[3 * N + b] = d.v.x; a[4 * N + b] = d.v.y; a[5 * N + b] = d.v.z;
-#pragma unroll
-    for (int k = 0; k < 9; k++) a[(6 + k) * N + b] = d.R.a[k];
-    a[15 * N + b] = d.L.x; a[16 * N + b] = d.L.y; a[17 * N + b] = d.L.z;
+    (void)N;
+    double2* q = reinterpret_cast<double2*>(a + (size_t)b * kDynF);
+    q[0] = make_double2(d.x.x, d.x.y); q[1] = make_double2(d.x.z, d.v.x); q[2] = make_double2(d.v.y, d.v.z);
+    q[3] = make_double2(d.R.a[0], d.R.a[1]); q[4] = make_double2(d.R.a[2], d.R.a[3]); q[5] = make_double2(d.R.a[4], d.R.a[5]);
+    q[6] = make_double2(d.R.a[6], d.R.a[7]); q[7] = make_double2(d.R.a[8], d.L.x); q[8] = make_double2(d.L.y, d.L.z);
 }
-// parameter planes: 0 1/mass (host-evaluated 1.0/mass, what Vector3D `/` multiplies by), 1-3 iinv,
+// parameter record: 0 1/mass (host-evaluated 1.0/mass, what Vector3D `/` multiplies by), 1-3 iinv,
 // 4-6 F, 7-9 T, 10 e, 11 mu_k, 12-14 dims, 15 shape
 PSD void ld_par(const double* a, int N, int b, Par& p)
 {
-    p.inv_mass = a[b];
+    (void)N;
+    const double2* q = reinterpret_cast<const double2*>(a + (size_t)b * kParF);
+    double2 t0 = __ldg(q), t1 = __ldg(q + 1), t2 = __ldg(q + 2), t3 = __ldg(q + 3), t4 = __ldg(q + 4), t5 = __ldg(q + 5),
+            t6 = __ldg(q + 6), t7 = __ldg(q + 7);
+    p.inv_mass = t0.x;
     p.is_static = (p.inv_mass == 0.0);  // 1/mass == 0 <=> mass is +-inf (Mass.Infinite)
-    p.iinv[0] = a[N + b]; p.iinv[1] = a[2 * N + b]; p.iinv[2] = a[3 * N + b];
-    p.F = mk(a[4 * N + b], a[5 * N + b], a[6 * N + b]);
-    p.T = mk(a[7 * N + b], a[8 * N + b], a[9 * N + b]);
-    p.e = a[10 * N + b];
-    p.mu = a[11 * N + b];
-    p.dims[0] = a[12 * N + b]; p.dims[1] = a[13 * N + b]; p.dims[2] = a[14 * N + b];
-    p.shape = (int)a[15 * N + b];
+    p.iinv[0] = t0.y; p.iinv[1] = t1.x; p.iinv[2] = t1.y;
+    p.F = mk(t2.x, t2.y, t3.x);
+    p.T = mk(t3.y, t4.x, t4.y);
+    p.e = t5.x;
+    p.mu = t5.y;
+    p.dims[0] = t6.x; p.dims[1] = t6.y; p.dims[2] = t7.x;
+    p.shape = (int)t7.y;
 }
 
 PSD bool same_bits(double a, double b) { return bits_of(a) == bits_of(b); }
@@ -311,8 +318,8 @@ PSD bool near_test(const Smem& s, int N, int i, int j)
     double dx = s.sx[i] - s.sx[j], dy = s.sx[N + i] - s.sx[N + j], dz = s.sx[2 * N + i] - s.sx[2 * N + j];
     double dd = dx * dx + dy * dy + dz * dz;
     // radius of i depends on what j is (a sphere against a box can report a hit up to sqrt(3) r from a corner)
-    double ri = (s.par[15 * N + j] != 0.0) ? s.rad_b[i] : s.rad_s[i];
-    double rj = (s.par[15 * N + i] != 0.0) ? s.rad_b[j] : s.rad_s[j];
+    double ri = s.isbox[j] ? s.rad_b[i] : s.rad_s[i];
+    double rj = s.isbox[i] ? s.rad_b[j] : s.rad_s[j];
     double r = ri + rj;
     return !(dd > r * r);  // NaN -> near
 }
@@ -333,20 +340,24 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
     carve(smem_raw, N, a.k_cap, c.s);
     Smem& s = c.s;
     double* gdyn = a.dyn + (size_t)off * kDynF;
-    const double* gpar = a.par + (size_t)off * kParF;
+    s.dyn = a.cur + (size_t)off * kDynF;
+    s.pred = a.pred + (size_t)off * kDynF;
+    s.par = a.par + (size_t)off * kParF;
+    s.S = a.S + (size_t)off * 3 * kMaxStatics;
     const StepParams sp = a.sp;
 
-    // world -> shared memory (coalesced, contiguous per world)
+    // working copy of the world (coalesced, contiguous per world)
     for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
-    for (int k = tid; k < kParF * N; k += T) s.par[k] = gpar[k];
-    for (int b = tid; b < N; b += T) s.nprev[b] = a.hitcnt[off + b];
+    for (int b = tid; b < N; b += T) {
+        s.nprev[b] = a.hitcnt[off + b];
+        s.isbox[b] = (__ldg(s.par + (size_t)b * kParF + 15) != 0.0) ? 1 : 0;
+        s.isstat[b] = (__ldg(s.par + (size_t)b * kParF) == 0.0) ? 1 : 0;
+    }
     __syncthreads();
     if (tid == 0) {  // static ordinals (1-based); more than kMaxStatics -> always the serial walk
         int ns = 0;
-        for (int b = 0; b < N; b++) {
-            if (s.par[b] == 0.0) { ns++; s.isstat[b] = (unsigned char)(ns <= kMaxStatics ? ns : kMaxStatics); }
-            else s.isstat[b] = 0;
-        }
+        for (int b = 0; b < N; b++)
+            if (s.isstat[b]) { ns++; s.isstat[b] = (unsigned char)(ns <= kMaxStatics ? ns : kMaxStatics); }
         bs.nstat = ns;
     }
     __syncthreads();
@@ -502,7 +513,9 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                 for (int b = tid; b < N; b += T) {
                     if (!s.isstat[b]) continue;
                     Par p; ld_par(s.par, N, b, p);
-                    d3 L = mk(s.dyn[15 * N + b], s.dyn[16 * N + b], s.dyn[17 * N + b]);
+                    double* cb = s.dyn + (size_t)b * kDynF;
+                    double* pb = s.pred + (size_t)b * kDynF;
+                    d3 L = mk(cb[15], cb[16], cb[17]);
                     d3 dL = scale(sp.dt, p.T);
                     const double* Sb = s.S + 3 * (s.isstat[b] - 1) * N;
                     for (int k = 0; k < K; k++) {
@@ -514,10 +527,10 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                         L = L + dL;  // the predicted copy's integration
                         L = L + mk(Sb[3 * other], Sb[3 * other + 1], Sb[3 * other + 2]);
                     }
-                    s.dyn[15 * N + b] = L.x; s.dyn[16 * N + b] = L.y; s.dyn[17 * N + b] = L.z;
+                    cb[15] = L.x; cb[16] = L.y; cb[17] = L.z;
                     // pose is a fixed point: the final sweep only has to add dt*T to L
                     d3 Lf = L + dL;
-                    s.pred[15 * N + b] = Lf.x; s.pred[16 * N + b] = Lf.y; s.pred[17 * N + b] = Lf.z;
+                    pb[15] = Lf.x; pb[16] = Lf.y; pb[17] = Lf.z;
                 }
                 __syncthreads();
             } else {
