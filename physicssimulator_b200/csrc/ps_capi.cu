@@ -67,6 +67,8 @@ struct Batch {
     WorldStats* d_stats = nullptr;
     unsigned char* d_hitcnt = nullptr;
     double *d_cur = nullptr, *d_pred = nullptr, *d_S = nullptr;  // per-world scratch of the step kernel
+    unsigned char* d_ovf = nullptr;   // overflow near lists (worlds whose list exceeds the shared-memory capacity)
+    long long* d_ovf_off = nullptr;
     int *d_joff = nullptr, *d_ja = nullptr, *d_jb = nullptr;
     double *d_jla = nullptr, *d_jlb = nullptr;
     unsigned char* d_jlast = nullptr;
@@ -181,7 +183,7 @@ void dfree(T*& p)
 }
 void free_device(Batch* B)
 {
-    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S);
+    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_ovf); dfree(B->d_ovf_off);
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
 }
@@ -217,7 +219,7 @@ int upload(Batch* B, bool with_state)
     for (int w = 0; w < B->n_worlds; w++) B->max_n = std::max(B->max_n, h.off[w + 1] - h.off[w]);
     for (int i = 0; i < B->n_bodies; i++) B->n_dynamic += std::isinf(h.mass[i]) ? 0 : 1;
     // near-list capacity: all pairs for small worlds, 16 per body otherwise (a fuller list takes the serial walk)
-    B->k_cap = std::max(32, std::min(B->max_n * (B->max_n - 1) / 2, 16 * B->max_n));
+    B->k_cap = std::max(32, std::min(B->max_n * (B->max_n - 1) / 2, 8 * B->max_n));
     // CTA width: a wavefront level holds ~10 pairs for a 128-body pile; one warp per world lets many worlds share an SM
     B->threads = B->max_n <= 256 ? 32 : (B->max_n <= 512 ? 64 : 128);
     if (const char* e = getenv("PS_B200_CTA")) { int t = atoi(e); if (t == 32 || t == 64 || t == 128) B->threads = t; }  // tuning knob
@@ -240,6 +242,20 @@ int upload(Batch* B, bool with_state)
     CK(cudaMalloc(&B->d_cur, nb * kDynF * sizeof(double)));
     CK(cudaMalloc(&B->d_pred, nb * kDynF * sizeof(double)));
     CK(cudaMalloc(&B->d_S, nb * 3 * kMaxStatics * sizeof(double)));
+    {   // overflow lists: 9 bytes per pair of the world, only when a world can exceed the shared-memory list
+        std::vector<long long> ooff(B->n_worlds + 1, 0);
+        bool need = false;
+        for (int w = 0; w < B->n_worlds; w++) {
+            long long N = h.off[w + 1] - h.off[w], np = N * (N - 1) / 2;
+            if (np > B->k_cap) need = true;
+            ooff[w + 1] = ooff[w] + ((np * 9 + 15) / 16) * 16;
+        }
+        if (need && ooff[B->n_worlds] <= (8ll << 30)) {
+            CK(cudaMalloc(&B->d_ovf, (size_t)ooff[B->n_worlds]));
+            CK(cudaMalloc(&B->d_ovf_off, ooff.size() * sizeof(long long)));
+            CK(cudaMemcpy(B->d_ovf_off, ooff.data(), ooff.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        }
+    }
     CK(cudaMalloc(&B->d_hitcnt, nb));
     CK(cudaMemsetAsync(B->d_hitcnt, 0, nb, B->stream));
     CK(cudaMemsetAsync(B->d_stats, 0, (size_t)std::max(1, B->n_worlds) * sizeof(WorldStats), B->stream));
@@ -452,6 +468,7 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
     a.max_n = B->max_n; a.k_cap = B->k_cap;
     a.hitcnt = B->d_hitcnt; a.cur = B->d_cur; a.pred = B->d_pred; a.S = B->d_S;
+    a.ovf = B->d_ovf; a.ovf_off = B->d_ovf_off;
     if (B->threads == 32) step_kernel<32><<<B->n_worlds, 32, B->smem, st>>>(a);
     else if (B->threads == 64) step_kernel<64><<<B->n_worlds, 64, B->smem, st>>>(a);
     else step_kernel<128><<<B->n_worlds, 128, B->smem, st>>>(a);

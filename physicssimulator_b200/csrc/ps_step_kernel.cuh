@@ -85,7 +85,10 @@ struct KArgs {
     int* rec_counts;          // n_worlds * 2 : pairs, contacts
     int rec_pair_cap, rec_contact_cap;
     int max_n;                // largest world (sizes the shared-memory carve-up)
-    int k_cap;                // near-list capacity
+    int k_cap;                // near-list capacity in shared memory
+    // overflow lists in global memory for worlds whose near list does not fit (nullptr: serial walk instead)
+    unsigned char* ovf;       // per world: n_pairs * 9 bytes (near u32 | level u16 | order u16 | hit u8)
+    const long long* ovf_off; // n_worlds+1 byte offsets (16-byte aligned)
 };
 
 // ---- shared-memory carve-up (scheduling data only) ----------------------------------------------
@@ -345,6 +348,10 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
     s.par = a.par + (size_t)off * kParF;
     s.S = a.S + (size_t)off * 3 * kMaxStatics;
     const StepParams sp = a.sp;
+    unsigned* const sm_near = s.near;
+    unsigned short* const sm_level = s.level;
+    unsigned short* const sm_order = s.order;
+    unsigned char* const sm_hit = s.hit;
 
     // working copy of the world (coalesced, contiguous per world)
     for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                     s.sx[b] = pr.x.x; s.sx[N + b] = pr.x.y; s.sx[2 * N + b] = pr.x.z;
                     double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
                     double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
-                    double n = (double)s.nprev[b] + 2.0;
+                    double n = (double)(s.nprev[b] < 6 ? s.nprev[b] : 6) + 2.0;
                     double m = p.is_static ? 0.0 : mscale * (0.01 + n * sp.dt * (speed + n * acc * sp.dt + 0.5));
                     if (!(m == m)) m = 0.0;  // NaN state: the world is flagged anyway
                     double rs, rb;
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                     for (int i = 0; i < N; i++) { int t = s.row[i]; s.row[i] = acc; acc += t; }
                     s.row[N] = acc;
                     bs.K = acc;
-                    if (acc > a.k_cap) bs.need_serial = 1;  // list full: a wider margin cannot help
+                    if (acc > a.k_cap && !a.ovf) bs.need_serial = 1;  // list full and no overflow area
                 }
                 __syncthreads();
                 const int K = bs.K;
@@ -442,6 +449,16 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                     __syncthreads();
                     attempt = 1; fb_reason = 2;
                     continue;
+                }
+                if (K > a.k_cap) {  // the lists of this step live in the world's overflow area (global memory)
+                    unsigned char* o = a.ovf + a.ovf_off[w];
+                    const size_t np = (size_t)N * (size_t)(N - 1) / 2;
+                    s.near = reinterpret_cast<unsigned*>(o);
+                    s.level = reinterpret_cast<unsigned short*>(o + 4 * np);
+                    s.order = reinterpret_cast<unsigned short*>(o + 6 * np);
+                    s.hit = o + 8 * np;
+                } else {
+                    s.near = sm_near; s.level = sm_level; s.order = sm_order; s.hit = sm_hit;
                 }
                 for (int i = tid; i < N; i += T) {
                     int o = s.row[i];
