@@ -175,6 +175,9 @@ int ps_batch_reset(void* handle);
 
 int ps_batch_stats(void* handle, ps_stats* out);
 int ps_batch_num_bodies(void* handle, int32_t* n_bodies_total, int32_t* n_dynamic_total);
+/* profiling aid: per world 8 x uint64 = SM cycles of the step phases (predict+cull spheres, near list, levels+sort,
+ * wavefronts, rest), the slowest single step, sum of near-list lengths, sum of level counts */
+int ps_batch_debug_cycles(void* handle, unsigned long long* out);
 
 /* Broad phase on one large world (BASELINE config 5): sorted list of pairs (i<j) with >= 1 dynamic
  * body whose AABBs overlap strictly on all axes — SpatialTree.areIntersecting (SpatialTree.fs:39-41)

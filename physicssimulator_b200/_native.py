@@ -26,6 +26,7 @@ EXPORTS = (
     "ps_batch_step_async", "ps_batch_synchronize", "ps_batch_get_state", "ps_batch_set_state",
     "ps_batch_get_state_device", "ps_batch_get_contacts", "ps_batch_get_candidates", "ps_batch_apply_impulse",
     "ps_batch_add_body", "ps_batch_reset", "ps_batch_stats", "ps_batch_num_bodies", "ps_broadphase_pairs",
+    "ps_batch_debug_cycles",
 )
 
 
@@ -208,6 +209,11 @@ class Batch:
         s = ps_stats()
         check(lib().ps_batch_stats(self.h, ctypes.byref(s)))
         return {k: getattr(s, k) for k, _ in ps_stats._fields_}
+
+    def debug_cycles(self):
+        out = np.zeros((self.n_worlds, 8), dtype=np.uint64)
+        check(lib().ps_batch_debug_cycles(self.h, out.ctypes.data_as(POINTER(ctypes.c_uint64))))
+        return out
 
     def num_bodies(self):
         a, b = c_int32(0), c_int32(0)

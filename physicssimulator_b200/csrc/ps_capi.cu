@@ -702,6 +702,22 @@ int ps_batch_stats(void* handle, ps_stats* out)
     return PS_OK;
 }
 
+// debug/profiling: per-world phase cycles (8 x u64 per world: cyc[0..4], slowest step, sum K, sum levels)
+int ps_batch_debug_cycles(void* handle, unsigned long long* out)
+{
+    if (!handle || !out) return fail(PS_ERR_INVALID_ARGUMENT, "handle/out is null");
+    Batch* B = (Batch*)handle;
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    std::vector<WorldStats> ws(B->n_worlds);
+    CK(cudaMemcpy(ws.data(), B->d_stats, ws.size() * sizeof(WorldStats), cudaMemcpyDeviceToHost));
+    for (int w = 0; w < B->n_worlds; w++) {
+        for (int k = 0; k < 5; k++) out[8 * w + k] = ws[w].cyc[k];
+        out[8 * w + 5] = ws[w].cyc_max_step; out[8 * w + 6] = ws[w].sum_K; out[8 * w + 7] = ws[w].sum_levels;
+    }
+    return PS_OK;
+}
+
 int ps_batch_num_bodies(void* handle, int32_t* n_bodies_total, int32_t* n_dynamic_total)
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");

@@ -57,7 +57,7 @@ PS_TABLE signed char kFaceSign[6] = {-1, 1, 1, -1, 1, -1};
 // ----------------------------------------------------------------------------------------
 // Integration (RigidBody.fs:202-220 -> Particle.fs:25-30 + RigidBody.fs:142-190)
 // ----------------------------------------------------------------------------------------
-PSD void integrate(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o)
+PSN void integrate(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o)
 {
     const double dt = sp.dt;
     d3 acc = scale(p.inv_mass, p.F);       // RigidBody.fs:210  totalForce / mass
@@ -92,7 +92,7 @@ struct OBox {
     d3 v[8];  // world vertices, Box.fs:23-32 index
     d3 n[6];  // world face normals
 };
-PSD void make_obox(const Dyn& b, const Par& p, OBox& ob)
+PSN void make_obox(const Dyn& b, const Par& p, OBox& ob)
 {
     double hx = p.dims[0] / 2.0, hy = p.dims[1] / 2.0, hz = p.dims[2] / 2.0;
 #pragma unroll
@@ -113,7 +113,7 @@ PSD void make_obox(const Dyn& b, const Par& p, OBox& ob)
 PSD d3 face_vertex(const OBox& ob, int f, int k) { return ob.v[kFaceVert[f][k]]; }
 
 // min/max of the 8 vertex projections in OrientedBox.Vertices order (ties keep the first, values only)
-PSD void project_box(const OBox& ob, d3 axis, double& mn, double& mx)
+PSN void project_box(const OBox& ob, d3 axis, double& mn, double& mx)
 {
     double p0 = dot(axis, ob.v[0]);
     mn = p0;
@@ -136,7 +136,7 @@ PSD d3 closest_on_edge(d3 a, d3 b, d3 pos)  // :9-24
     t = fmax_net(0.0, fmin_net(1.0, t));
     return a + scale(t, ab);
 }
-PSD d3 closest_on_quad(d3 pos, const d3 q[4])  // :26-37, edges (last,first),(0,1),(1,2),(2,3); first min
+PSN d3 closest_on_quad(d3 pos, const d3 q[4])  // :26-37, edges (last,first),(0,1),(1,2),(2,3); first min
 {
     d3 best = closest_on_edge(q[3], q[0], pos);
     d3 d = pos - best;
@@ -153,7 +153,7 @@ PSD d3 closest_on_quad(d3 pos, const d3 q[4])  // :26-37, edges (last,first),(0,
     }
     return best;
 }
-PSD bool plane_edge_hit(double eps, d3 pn, double pd, d3 s, d3 e, d3& out)  // :41-63
+PSN bool plane_edge_hit(double eps, d3 pn, double pd, d3 s, d3 e, d3& out)  // :41-63
 {
     d3 ab = e - s;
     double ab_p = dot(pn, ab);
@@ -179,7 +179,7 @@ PSD void tangents(d3 n, d3& t1, d3& t2)  // :112-123
 // Narrow phase
 // ----------------------------------------------------------------------------------------
 // detectSphereSphereCollision (CollisionDetection.fs:186-205)
-PSD int detect_ss(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, Contact* out)
+PSN int detect_ss(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, Contact* out)
 {
     d3 d = b1.x - b2.x;
     double dist = norm(d);
@@ -198,7 +198,7 @@ PSD int detect_ss(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, Co
 
 // SAT.SphereBox.tryFindSeparatingAxis (SAT.fs:108-151) + detectedSphereBoxCollision
 // (CollisionDetection.fs:166-184). Normal returned "from box". err set where the reference throws.
-PSD int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Par& bp, double eps, Contact* out,
+PSN int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Par& bp, double eps, Contact* out,
                           int& face, int& err)
 {
     OBox ob;
@@ -206,6 +206,7 @@ PSD int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Pa
     double r = sp_.dims[0];
     double best_pen = 0.0;
     int best = -1;
+#pragma unroll 1
     for (int f = 0; f < 6; f++) {
         d3 axis = ob.n[f];
         double a, b;
@@ -264,7 +265,7 @@ struct PolyV {
 
 // detectBoxBoxCollision (CollisionDetection.fs:29-164) over SAT.tryFindSeparatingAxis (SAT.fs:206-240)
 // returns #contacts (0 = none); overflow set when the manifold would exceed PS_MAX_CONTACTS
-PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
                   int& overflow)
 {
     OBox o1, o2;
@@ -276,6 +277,7 @@ PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
     d3 best_n = mk(0, 0, 0);
 
     // Face1: axes = normals of box 1, target = box 1 (SAT.fs:230-231)
+#pragma unroll 1
     for (int f = 0; f < 6; f++) {
         d3 axis = o1.n[f];
         double a, b, c, d, pen;
@@ -290,6 +292,7 @@ PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
         }
     }
     // Face2: axes = normals of box 2, target = box 2 (boxes flipped, :233-234)
+#pragma unroll 1
     for (int f = 0; f < 6; f++) {
         d3 axis = o2.n[f];
         double a, b, c, d, pen;
@@ -305,13 +308,15 @@ PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
     }
     // Edge axes (:218-226): RigidBody.Axes = normalize(R e_k + 0) (RigidBody.fs:34-41)
     d3 ax1[3], ax2[3];
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 3; k++) {
         ax1[k] = normalize(mk(b1.R.a[k], b1.R.a[3 + k], b1.R.a[6 + k]) + mk(0.0, 0.0, 0.0));
         ax2[k] = normalize(mk(b2.R.a[k], b2.R.a[3 + k], b2.R.a[6 + k]) + mk(0.0, 0.0, 0.0));
     }
     d3 fromFirst = b2.x - b1.x;
+#pragma unroll 1
     for (int i = 0; i < 3; i++)
+#pragma unroll 1
         for (int j = 0; j < 3; j++) {
             d3 e = normalize(cross(ax2[j], ax1[i]));  // firstAxis |> crossProduct secondAxis = second x first
             if (near_eq(0.01, 0.0, norm(e))) continue;  // isZero 0.01
@@ -336,6 +341,7 @@ PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
         const OBox& oth = (best_origin == 0) ? o2 : o1;
         d3 normal = best_n;
         int rf = -1;
+#pragma unroll 1
         for (int f = 0; f < 6; f++)
             if (veq(ref.n[f], normal)) {  // Box.findFaceByNormal (Box.fs:113-114)
                 rf = f;
@@ -348,6 +354,7 @@ PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
         d3 rn = ref.n[rf];
         int inc = 0;
         double incv = dot(rn, oth.n[0]);
+#pragma unroll 1
         for (int f = 1; f < 6; f++) {  // findIncidentFace: first min (:35-37)
             double d = dot(rn, oth.n[f]);
             if (d < incv) {
@@ -360,12 +367,13 @@ PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
         PolyV* cur = bufA;
         PolyV* nxt = bufB;
         int n = 4;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 4; k++) {
             cur[k].p = face_vertex(oth, inc, k);
             cur[k].tag = (unsigned)k;
         }
         int pi = 0;
+#pragma unroll 1
         for (int f = 0; f < 6; f++) {
             double ad = fabs(dot(rn, ref.n[f]));
             if (near_eq(eps, 1.0, ad)) continue;  // not adjacent
@@ -373,6 +381,7 @@ PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
             d3 pn = -ref.n[f];                                   // Plane.inverted
             double pd = -dot(ref.n[f], face_vertex(ref, f, 0));  // Face.toPlane then inverted
             int m = 0;
+#pragma unroll 1
             for (int k = 0; k < n; k++) {
                 const PolyV& s = (k == 0) ? cur[n - 1] : cur[k - 1];
                 const PolyV& e = cur[k];
@@ -398,13 +407,15 @@ PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
         }
         // List.distinct, then keep points on/below the reference plane (:52-54), then contacts (:63-67)
         d3 refq[4];
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 4; k++) refq[k] = face_vertex(ref, rf, k);
         d3 rpn = -rn;
         double rpd = -dot(rn, refq[0]);
         int nc = 0;
+#pragma unroll 1
         for (int k = 0; k < n; k++) {
             bool dup = false;
+#pragma unroll 1
             for (int q = 0; q < k; q++)
                 if (veq(cur[q].p, cur[k].p)) {
                     dup = true;
@@ -431,6 +442,7 @@ PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
     d3 normal = best_n;
     d3 ea[2], eb[2];
     int eidx[2];
+#pragma unroll 1
     for (int side = 0; side < 2; side++) {
         const OBox& ob = side == 0 ? o1 : o2;
         d3 axis = side == 0 ? ax1[best_i] : ax2[best_j];
@@ -440,7 +452,9 @@ PSD int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
         int idx = 0;
         // OrientedBox.getEdges: faces 0..5, per face (v3,v0),(v0,v1),(v1,v2),(v2,v3); List.distinct on
         // ordered pairs — every directed edge of a non-degenerate box appears once, so index = 4*f+k.
+#pragma unroll 1
         for (int f = 0; f < 6; f++)
+#pragma unroll 1
             for (int k = 0; k < 4; k++) {
                 d3 a = face_vertex(ob, f, (k + 3) & 3), b = face_vertex(ob, f, k);
                 d3 dd = b - a;
@@ -522,7 +536,7 @@ PSD m33 transpose(const m33& m)
     o.a[6] = m.a[2]; o.a[7] = m.a[5]; o.a[8] = m.a[8];
     return o;
 }
-PSD void add_K(m33& s, const Par& p, const m33& Iw, d3 r)
+PSN void add_K(m33& s, const Par& p, const m33& Iw, d3 r)
 {
     if (p.is_static) {  // Mass.Infinite -> Matrix3.zero: s + 0
 #pragma unroll
@@ -546,7 +560,7 @@ PSD void apply_impulse(Dyn& b, const Par& p, d3 off, d3 P)
 PSD d3 velocity_at(const Dyn& b, const m33& Iw, d3 off) { return b.v + cross(mulMV(Iw, b.L), off); }
 
 // resolves one pair in place; b1/b2 are the predicted bodies
-PSD void resolve(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* cs, int nc, CPData* cp,
+PSN void resolve(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* cs, int nc, CPData* cp,
                  const StepParams& sp)
 {
     // orientation is constant during the solve, so R Ip^-1 R^T is evaluated once per body (exact)
@@ -554,6 +568,7 @@ PSD void resolve(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* 
     m33 Iw2 = inertia_inv_world(b2.R, p2.iinv);
     d3 t0, t1;
     tangents(cs[0].n, t0, t1);  // CollisionResponse.fs:80-81
+#pragma unroll 1
     for (int k = 0; k < nc; k++) {
         CPData d;
         d.bias = fmin_net(sp.max_corr, -sp.baumgarte / sp.dt * fmin_net(0.0, cs[k].pen + sp.slop));  // :35-41
@@ -575,7 +590,9 @@ PSD void resolve(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* 
     const double e = fmin_net(p1.e, p2.e);
     const double mu = fmax_net(p2.mu, p1.mu);
     const double inf = from_bits(0x7ff0000000000000LL);
+#pragma unroll 1
     for (int it = 0; it < sp.iterations; it++) {
+#pragma unroll 1
         for (int k = nc - 1; k >= 0; k--) {  // List.foldBack: reverse order
             CPData d = cp[k];
             d3 n = cs[k].n;

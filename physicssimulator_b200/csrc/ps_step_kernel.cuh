@@ -49,6 +49,10 @@ struct WorldStats {  // per world, accumulated over steps
     unsigned long long fb_margin, fb_capacity, fb_static;
     double max_pen;
     int nan_flag, pad;
+    // SM cycles of thread 0 per phase, summed over steps: predict+cull spheres, near list, levels+sort,
+    // wavefronts (or serial walk), static fold + joints + final sweep + publish; and the slowest single step
+    unsigned long long cyc[5], cyc_max_step;
+    unsigned long long sum_K, sum_levels;
 };
 
 struct RecPair {  // one entry of the last step's Collisions map
@@ -245,7 +249,7 @@ PSD void record_pair(const Ctx& c, int i, int j, const Contact* cs, int nc)
 
 // predicted copy of body b, integrating it first if an earlier pair changed it (lazy refresh).
 // check_margin: the position is about to be used for detection under a culled pair list.
-PSD void get_pred(Ctx& c, int b, const Par& p, Dyn& out, bool check_margin)
+PSN void get_pred(Ctx& c, int b, const Par& p, Dyn& out, bool check_margin)
 {
     if (c.s.pvalid[b]) {
         ld_dyn(c.s.pred, c.N, b, out);
@@ -271,7 +275,7 @@ PSD void bump(unsigned char* p)  // saturating per-body hit counter (the body is
 
 // one candidate pair of the ordered fold (CollisionResolver.fs:40-46, 13-38).
 // fast: static bodies are shared (pose fixed): their angular-momentum sum goes to S[ordinal][partner].
-PSD void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
+PSN void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
 {
     Par pi, pj;
     ld_par(c.s.par, c.N, i, pi);
@@ -373,7 +377,9 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
     unsigned long long t_fbm = 0, t_fbc = 0, t_fbs = 0;
     double t_maxpen = 0.0;
 
+    unsigned long long cyc[5] = {0, 0, 0, 0, 0}, cyc_max = 0, sumK = 0, sumL = 0;
     for (int step = 0; step < a.n_steps; step++) {
+        long long tk0 = clock64(), tk = tk0;
         // attempts: 0 = margin x1, 1 = margin x8, 2 = exact serial walk over all pairs
         int attempt = (a.exact_all_pairs || bs.nstat > kMaxStatics) ? 2 : 0;
         int fb_reason = 0;  // 1 margin, 2 capacity/levels, 3 static pose
@@ -429,6 +435,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                     attempt = 1; fb_reason = 3;
                     continue;          // state untouched so far: no reload needed
                 }
+                if (tid == 0) { long long t = clock64(); cyc[0] += t - tk; tk = t; }
                 // ---- B: near list, lexicographic order kept by a row scan -------------------------------
                 for (int i = tid; i < N; i += T) {
                     int cn = 0;
@@ -470,6 +477,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                         }
                 }
                 __syncthreads();
+                if (tid == 0) { long long t = clock64(); cyc[1] += t - tk; tk = t; }
                 // ---- C: wavefront levels (serial scan of the ordered list by one thread) ------------------
                 if (tid == 0) {
                     int maxl = 0;
@@ -510,6 +518,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                     s.order[pos] = (unsigned short)k;
                 }
                 __syncthreads();
+                if (tid == 0) { long long t = clock64(); cyc[2] += t - tk; tk = t; sumK += K; sumL += maxl; }
                 // ---- D: wavefronts ------------------------------------------------------------------------
                 for (int l = 1; l <= maxl; l++) {
                     int beg = s.lvl_start[l - 1], end = s.lvl_start[l];
@@ -520,6 +529,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                     }
                     __syncthreads();
                 }
+                if (tid == 0) { long long t = clock64(); cyc[3] += t - tk; tk = t; }
                 if (bs.violate) {  // restart from the published state
                     for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
                     __syncthreads();
@@ -558,6 +568,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                             if (s.isstat[i] && s.isstat[j]) continue;
                             process_pair(c, i, j, 0, false);
                         }
+                    long long t = clock64(); cyc[3] += t - tk; tk = t;
                 }
                 __syncthreads();
             }
@@ -629,6 +640,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
         // publish the step (also the restart point of the next step's fallback)
         for (int k = tid; k < kDynF * N; k += T) gdyn[k] = s.dyn[k];
 
+        if (tid == 0) { long long t = clock64(); cyc[4] += t - tk; if ((unsigned long long)(t - tk0) > cyc_max) cyc_max = t - tk0; }
         // fold per-thread counters
         atomicAdd(&bs.tested, c.tested); atomicAdd(&bs.hits, c.hits); atomicAdd(&bs.contacts, c.contacts);
         atomicAdd(&bs.overflow, c.overflow); atomicAdd(&bs.ref_exc, c.ref_exc);
@@ -654,6 +666,9 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
         st.fb_margin += t_fbm; st.fb_capacity += t_fbc; st.fb_static += t_fbs;
         st.max_pen = fmax(st.max_pen, t_maxpen);
         st.nan_flag = bad ? 1 : 0;
+        for (int k = 0; k < 5; k++) st.cyc[k] += cyc[k];
+        if (cyc_max > st.cyc_max_step) st.cyc_max_step = cyc_max;
+        st.sum_K += sumK; st.sum_levels += sumL;
     }
 }
 
