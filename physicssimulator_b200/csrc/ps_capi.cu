@@ -57,7 +57,7 @@ struct Batch {
     HostBodies init, cur;  // `cur` holds parameters (+ possibly added bodies); dynamic state lives on the device
     HostJoints joints;
     int n_worlds = 0, n_bodies = 0, n_dynamic = 0, max_n = 0;
-    int k_cap = 0, threads = 128;
+    int threads = 8;  // lanes per world
     size_t smem = 0;
     // device
     double* d_dyn = nullptr;
@@ -67,8 +67,10 @@ struct Batch {
     WorldStats* d_stats = nullptr;
     unsigned char* d_hitcnt = nullptr;
     double *d_cur = nullptr, *d_pred = nullptr, *d_S = nullptr;  // per-world scratch of the step kernel
-    unsigned char* d_ovf = nullptr;   // overflow near lists (worlds whose list exceeds the shared-memory capacity)
-    long long* d_ovf_off = nullptr;
+    double* d_cull = nullptr;         // cull spheres, 6 doubles per body
+    int* d_row = nullptr;             // near-list row offsets
+    unsigned char* d_lists = nullptr; // near list | level | order | hit of every world (9 B per pair of the world)
+    long long* d_lists_off = nullptr;
     int *d_joff = nullptr, *d_ja = nullptr, *d_jb = nullptr;
     double *d_jla = nullptr, *d_jlb = nullptr;
     unsigned char* d_jlast = nullptr;
@@ -183,7 +185,7 @@ void dfree(T*& p)
 }
 void free_device(Batch* B)
 {
-    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_ovf); dfree(B->d_ovf_off);
+    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off);
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
 }
@@ -218,19 +220,20 @@ int upload(Batch* B, bool with_state)
     B->n_dynamic = 0;
     for (int w = 0; w < B->n_worlds; w++) B->max_n = std::max(B->max_n, h.off[w + 1] - h.off[w]);
     for (int i = 0; i < B->n_bodies; i++) B->n_dynamic += std::isinf(h.mass[i]) ? 0 : 1;
-    // near-list capacity: all pairs for small worlds, 16 per body otherwise (a fuller list takes the serial walk)
-    B->k_cap = std::max(32, std::min(B->max_n * (B->max_n - 1) / 2, 8 * B->max_n));
-    // CTA width: a wavefront level holds ~10 pairs for a 128-body pile; one warp per world lets many worlds share an SM
-    B->threads = B->max_n <= 256 ? 32 : (B->max_n <= 512 ? 64 : 128);
-    if (const char* e = getenv("PS_B200_CTA")) { int t = atoi(e); if (t == 32 || t == 64 || t == 128) B->threads = t; }  // tuning knob
-    B->smem = smem_bytes(B->max_n, B->k_cap);
+    // lanes per world (tile): a wavefront level of a 128-body pile holds ~10 pairs, so 8 lanes per world and 4
+    // worlds per warp keep the lanes busy; with few worlds wider tiles give the SMs more warps to overlap
+    B->threads = 8;
+    if ((long long)B->n_worlds * 8 / 32 < 148 * 8) B->threads = 16;
+    if ((long long)B->n_worlds * 16 / 32 < 148 * 8) B->threads = 32;
+    if (const char* e = getenv("PS_B200_TILE")) { int t = atoi(e); if (t == 8 || t == 16 || t == 32) B->threads = t; }  // tuning knob
+    B->smem = smem_bytes(B->max_n) * (size_t)(32 / B->threads);
     int dev_max = 0;
     CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, B->device));
     if ((long long)B->smem > dev_max)
         return fail(PS_ERR_INVALID_ARGUMENT, "largest world (%d bodies) needs %zu B of shared memory; device allows %d", B->max_n, B->smem, dev_max);
-    CK(cudaFuncSetAttribute(step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem));
-    CK(cudaFuncSetAttribute(step_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem));
-    CK(cudaFuncSetAttribute(step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem));
+    CK(cudaFuncSetAttribute(step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
+    CK(cudaFuncSetAttribute(step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
+    CK(cudaFuncSetAttribute(step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
 
     size_t nb = (size_t)std::max(1, B->n_bodies);
     CK(cudaMalloc(&B->d_dyn, nb * kDynF * sizeof(double)));
@@ -242,19 +245,17 @@ int upload(Batch* B, bool with_state)
     CK(cudaMalloc(&B->d_cur, nb * kDynF * sizeof(double)));
     CK(cudaMalloc(&B->d_pred, nb * kDynF * sizeof(double)));
     CK(cudaMalloc(&B->d_S, nb * 3 * kMaxStatics * sizeof(double)));
-    {   // overflow lists: 9 bytes per pair of the world, only when a world can exceed the shared-memory list
-        std::vector<long long> ooff(B->n_worlds + 1, 0);
-        bool need = false;
+    {   // per-step lists of every world: 9 bytes per pair of the world
+        std::vector<long long> loff(B->n_worlds + 1, 0);
         for (int w = 0; w < B->n_worlds; w++) {
             long long N = h.off[w + 1] - h.off[w], np = N * (N - 1) / 2;
-            if (np > B->k_cap) need = true;
-            ooff[w + 1] = ooff[w] + ((np * 9 + 15) / 16) * 16;
+            loff[w + 1] = loff[w] + ((np * 9 + 15) / 16) * 16;
         }
-        if (need && ooff[B->n_worlds] <= (8ll << 30)) {
-            CK(cudaMalloc(&B->d_ovf, (size_t)ooff[B->n_worlds]));
-            CK(cudaMalloc(&B->d_ovf_off, ooff.size() * sizeof(long long)));
-            CK(cudaMemcpy(B->d_ovf_off, ooff.data(), ooff.size() * sizeof(long long), cudaMemcpyHostToDevice));
-        }
+        CK(cudaMalloc(&B->d_lists, (size_t)std::max<long long>(loff[B->n_worlds], 16)));
+        CK(cudaMalloc(&B->d_lists_off, loff.size() * sizeof(long long)));
+        CK(cudaMemcpy(B->d_lists_off, loff.data(), loff.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&B->d_cull, nb * 6 * sizeof(double)));
+        CK(cudaMalloc(&B->d_row, (nb + (size_t)B->n_worlds + 1) * sizeof(int)));
     }
     CK(cudaMalloc(&B->d_hitcnt, nb));
     CK(cudaMemsetAsync(B->d_hitcnt, 0, nb, B->stream));
@@ -291,7 +292,6 @@ int upload(Batch* B, bool with_state)
         std::vector<unsigned char> last(nj, 0);
         for (int q = 0; q < nj; q++) joff[J.world[order[q]] + 1]++;
         for (int w = 0; w < B->n_worlds; w++) {
-            if (joff[w + 1] > B->threads) return fail(PS_ERR_INVALID_ARGUMENT, "world %d has %d joints; at most %d per world of this size", w, joff[w + 1], B->threads);
             joff[w + 1] += joff[w];
         }
         for (int q = 0; q < nj; q++) {
@@ -466,12 +466,14 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
     a.joff = B->d_joff; a.ja = B->d_ja; a.jb = B->d_jb; a.jla = B->d_jla; a.jlb = B->d_jlb; a.jlast = B->d_jlast;
     a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
-    a.max_n = B->max_n; a.k_cap = B->k_cap;
+    a.max_n = B->max_n;
     a.hitcnt = B->d_hitcnt; a.cur = B->d_cur; a.pred = B->d_pred; a.S = B->d_S;
-    a.ovf = B->d_ovf; a.ovf_off = B->d_ovf_off;
-    if (B->threads == 32) step_kernel<32><<<B->n_worlds, 32, B->smem, st>>>(a);
-    else if (B->threads == 64) step_kernel<64><<<B->n_worlds, 64, B->smem, st>>>(a);
-    else step_kernel<128><<<B->n_worlds, 128, B->smem, st>>>(a);
+    a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off;
+    const int wpc = 32 / B->threads;  // worlds per one-warp CTA
+    const int grid = (B->n_worlds + wpc - 1) / wpc;
+    if (B->threads == 8) step_kernel<8><<<grid, 32, B->smem, st>>>(a);
+    else if (B->threads == 16) step_kernel<16><<<grid, 32, B->smem, st>>>(a);
+    else step_kernel<32><<<grid, 32, B->smem, st>>>(a);
     CK(cudaGetLastError());
     B->launches++;
     return PS_OK;

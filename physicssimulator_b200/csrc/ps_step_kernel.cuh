@@ -1,12 +1,17 @@
 // ps_step_kernel.cuh — the fused per-world step kernel (one CTA per world).
 //
-// One CTA owns one world for n_steps steps.  The bodies live in a per-world scratch record in global
-// memory (body-major, 144 B of state + 128 B of parameters per body, read with 16-byte loads; the
-// working set of the resident CTAs sits in L2/L1); shared memory only holds the per-step scheduling
-// data (cull spheres, near list, levels), ~10-17 KB per world, so that many worlds share one SM: the
-// step is a chain of dependent FP64 operations per pair and needs warps, not bandwidth.  The state is
-// published to the batch buffer once per step, which doubles as the restart point of the fallback.
-// The CTA width T is one warp (32) unless the host asks for more.
+// A TILE of TS lanes (8, 16 or 32) owns one world for n_steps steps; a one-warp CTA hosts 32/TS worlds.
+// A wavefront level of a 128-body pile holds ~10 pairs, so a whole warp per world would leave two thirds of
+// the lanes idle; with several worlds per warp the tiles walk their levels in lockstep (same loop, same
+// program counter) and the lanes of one warp instruction work on pairs of DIFFERENT worlds.  Tiles only ever
+// synchronise among themselves (__syncwarp with the tile mask).
+//
+// Memory: the bodies live in a per-world scratch record in global memory (body-major, 144 B of state +
+// 128 B of parameters per body, read with 16-byte loads; the working set of the resident tiles sits in
+// L2/L1), and so do the per-step lists (cull spheres, near list, levels, order).  Shared memory only holds
+// ~2 KB of flags and level offsets per world, so that residency is bounded by registers, not by shared
+// memory: the step is a chain of dependent FP64 operations per pair and needs warps, not bandwidth.  The
+// state is published to the batch buffer once per step, which doubles as the restart point of the fallback.
 //
 // Per step (reference order: Simulator.fs:52-56 = resolveAll (CollisionResolver.fs:49-69) then
 // SimulatorState.update (SimulatorState.fs:169-173)):
@@ -40,7 +45,7 @@ using namespace psp;
 
 constexpr int kDynF = 18;       // doubles of dynamic state per body
 constexpr int kParF = 16;       // doubles of parameters per body
-constexpr int kMaxLevels = 1022;
+constexpr int kMaxLevels = 510;
 constexpr int kMaxStatics = 4;  // static bodies per world whose pairs run in parallel (more -> serial walk)
 constexpr int kMaxThreads = 128;
 
@@ -89,73 +94,58 @@ struct KArgs {
     int* rec_counts;          // n_worlds * 2 : pairs, contacts
     int rec_pair_cap, rec_contact_cap;
     int max_n;                // largest world (sizes the shared-memory carve-up)
-    int k_cap;                // near-list capacity in shared memory
-    // overflow lists in global memory for worlds whose near list does not fit (nullptr: serial walk instead)
-    unsigned char* ovf;       // per world: n_pairs * 9 bytes (near u32 | level u16 | order u16 | hit u8)
-    const long long* ovf_off; // n_worlds+1 byte offsets (16-byte aligned)
+    // per-step lists of every world in global memory
+    double* cull;             // [total_bodies*6]: per world sx(3N) | rad_s(N) | rad_b(N) | marg2(N)
+    int* row;                 // [total_bodies + n_worlds]: per world N+1 row offsets of the near list
+    unsigned char* lists;     // per world: n_pairs * 9 bytes (near u32 | level u16 | order u16 | hit u8)
+    const long long* lists_off; // n_worlds+1 byte offsets (16-byte aligned)
 };
 
-// ---- shared-memory carve-up (scheduling data only) ----------------------------------------------
+// ---- per-world working set: pointers into global scratch + a small shared-memory block -------------
 struct Smem {
     double* dyn;     // GLOBAL scratch: 18*N current bodies (body-major)
     double* pred;    // GLOBAL scratch: 18*N predicted bodies
     const double* par;  // GLOBAL: 16*N parameters
     double* S;       // GLOBAL scratch: 3*kMaxStatics*N, [static ordinal][partner]
-    double* sx;      // 3*N cull-sphere centres (predicted positions)
-    double* rad_s;   // N   cull radius against a sphere (margin included)
-    double* rad_b;   // N   cull radius against a box
-    double* marg2;   // N   squared margin
-    unsigned* near;  // k_cap  i | j<<16
-    int* lvl_start;  // kMaxLevels+2
-    int* row;        // N+1
-    unsigned short* level;  // k_cap
-    unsigned short* order;  // k_cap
-    unsigned short* last;   // N
-    unsigned char* pvalid;  // N
-    unsigned char* isstat;  // N   0 dynamic, 1+ordinal static
-    unsigned char* isbox;   // N
-    unsigned char* hit;     // k_cap
-    unsigned char* nhit;    // N   colliding pairs of the body this step (saturating)
-    unsigned char* nprev;   // N   ... during the previous step
+    double* sx;      // GLOBAL scratch: 3*N cull-sphere centres (predicted positions)
+    double* rad_s;   // GLOBAL: N   cull radius against a sphere (margin included)
+    double* rad_b;   // GLOBAL: N   cull radius against a box
+    double* marg2;   // GLOBAL: N   squared margin
+    unsigned* near;  // GLOBAL: n_pairs  i | j<<16
+    unsigned short* level;  // GLOBAL: n_pairs
+    unsigned short* order;  // GLOBAL: n_pairs
+    unsigned char* hit;     // GLOBAL: n_pairs
+    int* row;        // GLOBAL: N+1
+    int* lvl_start;  // shared: kMaxLevels+2
+    unsigned short* last;   // shared: N
+    unsigned char* pvalid;  // shared: N
+    unsigned char* isstat;  // shared: N   0 dynamic, 1+ordinal static
+    unsigned char* isbox;   // shared: N
+    unsigned char* nhit;    // shared: N   colliding pairs of the body this step (saturating)
+    unsigned char* nprev;   // shared: N   ... during the previous step
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline size_t smem_bytes(int N, int k_cap)
+// shared memory of ONE world (a CTA hosts 32/TS of them)
+__host__ __device__ inline size_t smem_bytes(int N)
 {
-    size_t b = 0;
-    b += sizeof(double) * (size_t)(6 * N);
-    b += sizeof(unsigned) * (size_t)k_cap;
-    b += sizeof(int) * (size_t)(kMaxLevels + 2);
-    b += sizeof(int) * (size_t)(N + 1);
-    b += sizeof(unsigned short) * (size_t)(2 * k_cap + N);
-    b += (size_t)(5 * N + k_cap);
-    return align_up(b, 16) + 64;
+    size_t b = sizeof(int) * (size_t)(kMaxLevels + 2) + sizeof(unsigned short) * (size_t)N + (size_t)(5 * N);
+    return align_up(b, 16);
 }
 
-__device__ inline void carve(unsigned char* base, int N, int k_cap, Smem& s)
+__device__ inline void carve(unsigned char* base, int N, Smem& s)
 {
-    double* d = reinterpret_cast<double*>(base);
-    s.sx = d;     d += 3 * N;
-    s.rad_s = d;  d += N;
-    s.rad_b = d;  d += N;
-    s.marg2 = d;  d += N;
-    unsigned* u = reinterpret_cast<unsigned*>(d);
-    s.near = u;   u += k_cap;
-    int* ip = reinterpret_cast<int*>(u);
+    int* ip = reinterpret_cast<int*>(base);
     s.lvl_start = ip; ip += kMaxLevels + 2;
-    s.row = ip;   ip += N + 1;
     unsigned short* h = reinterpret_cast<unsigned short*>(ip);
-    s.level = h;  h += k_cap;
-    s.order = h;  h += k_cap;
     s.last = h;   h += N;
     unsigned char* c = reinterpret_cast<unsigned char*>(h);
     s.pvalid = c; c += N;
     s.isstat = c; c += N;
     s.isbox = c;  c += N;
     s.nhit = c;   c += N;
-    s.nprev = c;  c += N;
-    s.hit = c;
+    s.nprev = c;
 }
 
 // ---- body-major accessors (records are 16-byte aligned: 144 B and 128 B per body) ------------------
@@ -331,31 +321,45 @@ PSD bool near_test(const Smem& s, int N, int i, int j)
     return !(dd > r * r);  // NaN -> near
 }
 
+#ifndef PS_MINB32
+#define PS_MINB32 16  // resident one-warp CTAs per SM the register allocation must allow (65536 / (32 * regs))
+#endif
+// T = lanes per world (tile); the CTA is one warp and hosts 32/T worlds
 template <int T>
-__global__ void __launch_bounds__(T) step_kernel(KArgs a)
+__global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ BlockShared bs;
+    __shared__ BlockShared bs_all[32 / T];
 
-    const int w = blockIdx.x;
-    if (w >= a.n_worlds) return;
-    const int tid = threadIdx.x;
+    const int tile = threadIdx.x / T;
+    const int tid = threadIdx.x % T;
+    const unsigned tmask = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (tile * T));
+    const int w = blockIdx.x * (32 / T) + tile;
+    if (w >= a.n_worlds) return;  // whole tile leaves; tiles never wait for each other
+    BlockShared& bs = bs_all[tile];
     const int off = a.off[w];
     const int N = a.off[w + 1] - off;
     Ctx c;
     c.N = N; c.w = w; c.a = &a; c.bs = &bs;
-    carve(smem_raw, N, a.k_cap, c.s);
+    carve(smem_raw + (size_t)tile * smem_bytes(a.max_n), N, c.s);
     Smem& s = c.s;
+    {
+        double* cu = a.cull + (size_t)off * 6;
+        s.sx = cu; s.rad_s = cu + 3 * N; s.rad_b = cu + 4 * N; s.marg2 = cu + 5 * N;
+        s.row = a.row + off + w;
+        unsigned char* o = a.lists + a.lists_off[w];
+        const size_t np = (size_t)N * (size_t)(N > 0 ? N - 1 : 0) / 2;
+        s.near = reinterpret_cast<unsigned*>(o);
+        s.level = reinterpret_cast<unsigned short*>(o + 4 * np);
+        s.order = reinterpret_cast<unsigned short*>(o + 6 * np);
+        s.hit = o + 8 * np;
+    }
     double* gdyn = a.dyn + (size_t)off * kDynF;
     s.dyn = a.cur + (size_t)off * kDynF;
     s.pred = a.pred + (size_t)off * kDynF;
     s.par = a.par + (size_t)off * kParF;
     s.S = a.S + (size_t)off * 3 * kMaxStatics;
     const StepParams sp = a.sp;
-    unsigned* const sm_near = s.near;
-    unsigned short* const sm_level = s.level;
-    unsigned short* const sm_order = s.order;
-    unsigned char* const sm_hit = s.hit;
 
     // working copy of the world (coalesced, contiguous per world)
     for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
@@ -364,14 +368,14 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
         s.isbox[b] = (__ldg(s.par + (size_t)b * kParF + 15) != 0.0) ? 1 : 0;
         s.isstat[b] = (__ldg(s.par + (size_t)b * kParF) == 0.0) ? 1 : 0;
     }
-    __syncthreads();
+    __syncwarp(tmask);
     if (tid == 0) {  // static ordinals (1-based); more than kMaxStatics -> always the serial walk
         int ns = 0;
         for (int b = 0; b < N; b++)
             if (s.isstat[b]) { ns++; s.isstat[b] = (unsigned char)(ns <= kMaxStatics ? ns : kMaxStatics); }
         bs.nstat = ns;
     }
-    __syncthreads();
+    __syncwarp(tmask);
 
     unsigned long long t_steps = 0, t_tested = 0, t_hits = 0, t_contacts = 0, t_fallback = 0, t_overflow = 0, t_exc = 0;
     unsigned long long t_fbm = 0, t_fbc = 0, t_fbs = 0;
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
             c.tested = c.hits = c.contacts = c.overflow = c.ref_exc = 0;
             c.max_pen = 0.0;
             for (int b = tid; b < N; b += T) { s.pvalid[b] = 0; s.nhit[b] = 0; }
-            __syncthreads();
+            __syncwarp(tmask);
 
             if (attempt < 2) {
                 // ---- A: predicted copy of every body + cull spheres -----------------------------------
@@ -429,9 +433,9 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                     s.marg2[b] = m * m;
                     s.last[b] = 0;
                 }
-                __syncthreads();
+                __syncwarp(tmask);
                 if (bs.need_serial) {  // a static pose still moves under integrate(): exact serial walk this step
-                    __syncthreads();   // every thread has read the flag before thread 0 clears it at the loop top
+                    __syncwarp(tmask);   // every thread has read the flag before thread 0 clears it at the loop top
                     attempt = 1; fb_reason = 3;
                     continue;          // state untouched so far: no reload needed
                 }
@@ -442,31 +446,15 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                     for (int j = i + 1; j < N; j++) cn += near_test(s, N, i, j) ? 1 : 0;
                     s.row[i] = cn;
                 }
-                __syncthreads();
+                __syncwarp(tmask);
                 if (tid == 0) {
                     int acc = 0;
                     for (int i = 0; i < N; i++) { int t = s.row[i]; s.row[i] = acc; acc += t; }
                     s.row[N] = acc;
                     bs.K = acc;
-                    if (acc > a.k_cap && !a.ovf) bs.need_serial = 1;  // list full and no overflow area
                 }
-                __syncthreads();
+                __syncwarp(tmask);
                 const int K = bs.K;
-                if (bs.need_serial) {
-                    __syncthreads();
-                    attempt = 1; fb_reason = 2;
-                    continue;
-                }
-                if (K > a.k_cap) {  // the lists of this step live in the world's overflow area (global memory)
-                    unsigned char* o = a.ovf + a.ovf_off[w];
-                    const size_t np = (size_t)N * (size_t)(N - 1) / 2;
-                    s.near = reinterpret_cast<unsigned*>(o);
-                    s.level = reinterpret_cast<unsigned short*>(o + 4 * np);
-                    s.order = reinterpret_cast<unsigned short*>(o + 6 * np);
-                    s.hit = o + 8 * np;
-                } else {
-                    s.near = sm_near; s.level = sm_level; s.order = sm_order; s.hit = sm_hit;
-                }
                 for (int i = tid; i < N; i += T) {
                     int o = s.row[i];
                     for (int j = i + 1; j < N; j++)
@@ -476,7 +464,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                             o++;
                         }
                 }
-                __syncthreads();
+                __syncwarp(tmask);
                 if (tid == 0) { long long t = clock64(); cyc[1] += t - tk; tk = t; }
                 // ---- C: wavefront levels (serial scan of the ordered list by one thread) ------------------
                 if (tid == 0) {
@@ -495,29 +483,29 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                     bs.maxl = maxl;
                     if (maxl > kMaxLevels) bs.need_serial = 1;
                 }
-                __syncthreads();
+                __syncwarp(tmask);
                 if (bs.need_serial) {
-                    __syncthreads();
+                    __syncwarp(tmask);
                     attempt = 1; fb_reason = 2;
                     continue;
                 }
                 // counting sort of the near list by level (order inside a level is free)
                 const int maxl = bs.maxl;
                 for (int l = tid; l <= maxl + 1; l += T) s.lvl_start[l] = 0;
-                __syncthreads();
+                __syncwarp(tmask);
                 for (int k = tid; k < K; k += T) atomicAdd(&s.lvl_start[s.level[k]], 1);
-                __syncthreads();
+                __syncwarp(tmask);
                 if (tid == 0) {
                     int acc = 0;
                     for (int l = 0; l <= maxl + 1; l++) { int t = s.lvl_start[l]; s.lvl_start[l] = acc; acc += t; }
                 }
-                __syncthreads();
+                __syncwarp(tmask);
                 // scatter; lvl_start[l] is advanced to the END of level l, i.e. the start of l+1
                 for (int k = tid; k < K; k += T) {
                     int pos = atomicAdd(&s.lvl_start[s.level[k]], 1);
                     s.order[pos] = (unsigned short)k;
                 }
-                __syncthreads();
+                __syncwarp(tmask);
                 if (tid == 0) { long long t = clock64(); cyc[2] += t - tk; tk = t; sumK += K; sumL += maxl; }
                 // ---- D: wavefronts ------------------------------------------------------------------------
                 for (int l = 1; l <= maxl; l++) {
@@ -527,12 +515,12 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                         unsigned ij = s.near[k];
                         process_pair(c, ij & 0xffff, ij >> 16, k, true);
                     }
-                    __syncthreads();
+                    __syncwarp(tmask);
                 }
                 if (tid == 0) { long long t = clock64(); cyc[3] += t - tk; tk = t; }
                 if (bs.violate) {  // restart from the published state
                     for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
-                    __syncthreads();
+                    __syncwarp(tmask);
                     fb_reason = 1;
                     continue;
                 }
@@ -559,7 +547,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                     d3 Lf = L + dL;
                     pb[15] = Lf.x; pb[16] = Lf.y; pb[17] = Lf.z;
                 }
-                __syncthreads();
+                __syncwarp(tmask);
             } else {
                 // ---- exact serial walk over ALL pairs in Dummy order (BroadPhase.fs:33-39) -------------------
                 if (tid == 0) {
@@ -570,7 +558,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
                         }
                     long long t = clock64(); cyc[3] += t - tk; tk = t;
                 }
-                __syncthreads();
+                __syncwarp(tmask);
             }
             break;
         }
@@ -579,48 +567,53 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
             if (fb_reason == 1) t_fbm++; else if (fb_reason == 2) t_fbc++; else t_fbs++;
         }
 
-        // ---- J: joints (JointsRestorer.fs:9-26, Joints.fs:26-94) — all read the entry state ----------------
+        // ---- J: joints (JointsRestorer.fs:9-26, Joints.fs:26-94) -----------------------------------------------
+        // Every joint reads the state at ENTRY (Jacobi) and the results are written back in joint-list order, the
+        // last writer of a body wins (the host marks it).  Results are staged in the predicted-copy area of the
+        // bodies they replace and committed after all joints have read their inputs.
         if (a.restore_joints && a.joff) {
-            // every joint reads the state at entry, so a chunk computes, syncs, then writes; the host limits a
-            // world to T joints (ps_batch_create) so that there is exactly one chunk
             const int j0 = a.joff[w], nj = a.joff[w + 1] - j0;
-            Dyn o1, o2;
-            int ba = -1, bb = -1;
-            unsigned char lastf = 0;
-            const bool act = tid < nj;
-            if (act) {
-                int q = j0 + tid;
-                ba = a.ja[q]; bb = a.jb[q];
-                lastf = a.jlast[q];
-                Par p1, p2;
-                ld_par(s.par, N, ba, p1);
-                ld_par(s.par, N, bb, p2);
-                Dyn e1, e2;
-                ld_dyn(s.dyn, N, ba, e1);
-                ld_dyn(s.dyn, N, bb, e2);
-                d3 la = mk(a.jla[3 * q], a.jla[3 * q + 1], a.jla[3 * q + 2]);
-                d3 lb = mk(a.jlb[3 * q], a.jlb[3 * q + 1], a.jlb[3 * q + 2]);
-                m33 Iw1 = inertia_inv_world(e1.R, p1.iinv), Iw2 = inertia_inv_world(e2.R, p2.iinv);
-                d3 aw1 = mulMV(e1.R, la), aw2 = mulMV(e2.R, lb);  // JointImpulseData.init (Joints.fs:26-40)
-                m33 K;
+            for (int b = tid; b < N; b += T) s.last[b] = 0;
+            __syncwarp(tmask);
+            for (int base = 0; base < nj; base += T) {
+                if (base + tid < nj) {
+                    const int q = j0 + base + tid;
+                    const int ba = a.ja[q], bb = a.jb[q];
+                    const unsigned char lastf = a.jlast[q];
+                    Par p1, p2;
+                    ld_par(s.par, N, ba, p1);
+                    ld_par(s.par, N, bb, p2);
+                    Dyn o1, o2;
+                    ld_dyn(s.dyn, N, ba, o1);
+                    ld_dyn(s.dyn, N, bb, o2);
+                    d3 la = mk(a.jla[3 * q], a.jla[3 * q + 1], a.jla[3 * q + 2]);
+                    d3 lb = mk(a.jlb[3 * q], a.jlb[3 * q + 1], a.jlb[3 * q + 2]);
+                    m33 Iw1 = inertia_inv_world(o1.R, p1.iinv), Iw2 = inertia_inv_world(o2.R, p2.iinv);
+                    d3 aw1 = mulMV(o1.R, la), aw2 = mulMV(o2.R, lb);  // JointImpulseData.init (Joints.fs:26-40)
+                    m33 K;
 #pragma unroll
-                for (int k = 0; k < 9; k++) K.a[k] = 0.0;
-                add_K(K, p1, Iw1, aw1);
-                add_K(K, p2, Iw2, aw2);
-                d3 vrel = velocity_at(e2, Iw2, lb) - velocity_at(e1, Iw1, la);  // local offsets (Q14)
-                d3 imp = mulMV(K, mk(0.0, 0.0, 0.0) - vrel);
-                o1 = e1; o2 = e2;
-                for (int it = 0; it < sp.iterations; it++) {
-                    apply_impulse(o1, p1, la, imp);
-                    apply_impulse(o2, p2, lb, -imp);
+                    for (int k = 0; k < 9; k++) K.a[k] = 0.0;
+                    add_K(K, p1, Iw1, aw1);
+                    add_K(K, p2, Iw2, aw2);
+                    d3 vrel = velocity_at(o2, Iw2, lb) - velocity_at(o1, Iw1, la);  // local offsets (Q14)
+                    d3 imp = mulMV(K, mk(0.0, 0.0, 0.0) - vrel);
+                    for (int it = 0; it < sp.iterations; it++) {
+                        apply_impulse(o1, p1, la, imp);
+                        apply_impulse(o2, p2, lb, -imp);
+                    }
+                    if (lastf & 1) { st_dyn(s.pred, N, ba, o1); s.last[ba] = 1; }
+                    if (lastf & 2) { st_dyn(s.pred, N, bb, o2); s.last[bb] = 1; }
                 }
             }
-            __syncthreads();
-            if (act) {
-                if (lastf & 1) { st_dyn(s.dyn, N, ba, o1); s.pvalid[ba] = 0; }
-                if (lastf & 2) { st_dyn(s.dyn, N, bb, o2); s.pvalid[bb] = 0; }
-            }
-            __syncthreads();
+            __syncwarp(tmask);
+            for (int b = tid; b < N; b += T)
+                if (s.last[b]) {
+                    Dyn d;
+                    ld_dyn(s.pred, N, b, d);
+                    st_dyn(s.dyn, N, b, d);
+                    s.pvalid[b] = 0;
+                }
+            __syncwarp(tmask);
         }
 
         // ---- F: final integration of every body (SimulatorState.fs:169-173) -----------------------------------
@@ -636,7 +629,7 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
             st_dyn(s.dyn, N, b, out);
             s.nprev[b] = s.nhit[b];
         }
-        __syncthreads();
+        __syncwarp(tmask);
         // publish the step (also the restart point of the next step's fallback)
         for (int k = tid; k < kDynF * N; k += T) gdyn[k] = s.dyn[k];
 
@@ -645,19 +638,19 @@ __global__ void __launch_bounds__(T) step_kernel(KArgs a)
         atomicAdd(&bs.tested, c.tested); atomicAdd(&bs.hits, c.hits); atomicAdd(&bs.contacts, c.contacts);
         atomicAdd(&bs.overflow, c.overflow); atomicAdd(&bs.ref_exc, c.ref_exc);
         atomicMax(&bs.max_pen_bits, (unsigned long long)__double_as_longlong(c.max_pen));
-        __syncthreads();
+        __syncwarp(tmask);
         if (tid == 0) {
             t_steps++; t_tested += bs.tested; t_hits += bs.hits; t_contacts += bs.contacts;
             t_overflow += bs.overflow; t_exc += bs.ref_exc;
             t_maxpen = fmax(t_maxpen, __longlong_as_double((long long)bs.max_pen_bits));
         }
-        __syncthreads();
+        __syncwarp(tmask);
     }
 
     // NaN/Inf scan + stats write-out
     int bad = 0;
     for (int k = tid; k < kDynF * N; k += T) bad |= !isfinite(s.dyn[k]);
-    bad = __syncthreads_or(bad);
+    bad = (__ballot_sync(tmask, bad) != 0u);
     for (int b = tid; b < N; b += T) a.hitcnt[off + b] = s.nprev[b];
     if (tid == 0) {
         WorldStats& st = a.stats[w];
