@@ -324,21 +324,35 @@ PSD bool near_test(const Smem& s, int N, int i, int j)
 #ifndef PS_MINB32
 #define PS_MINB32 16  // resident one-warp CTAs per SM the register allocation must allow (65536 / (32 * regs))
 #endif
-// T = lanes per world (tile); the CTA is one warp and hosts 32/T worlds
+
+PSD int warp_max(int v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// T = lanes per world (tile); the CTA is one warp and hosts 32/T worlds.
+//
+// Control flow is WARP-uniform: every lane of the warp walks the same phases and the same loops (trip counts are
+// the maximum over the warp's tiles, lanes past their tile's bound are predicated off), so that the heavy routines
+// (integrate, process_pair) are entered by lanes of different worlds at the same program counter and share the
+// warp's instruction issue.  No lane returns early; a tile without a world has N = 0.
 template <int T>
 __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BlockShared bs_all[32 / T];
+    constexpr unsigned FULL = 0xffffffffu;
 
     const int tile = threadIdx.x / T;
     const int tid = threadIdx.x % T;
-    const unsigned tmask = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (tile * T));
-    const int w = blockIdx.x * (32 / T) + tile;
-    if (w >= a.n_worlds) return;  // whole tile leaves; tiles never wait for each other
+    const int wraw = blockIdx.x * (32 / T) + tile;
+    const bool live = wraw < a.n_worlds;
+    const int w = live ? wraw : 0;
     BlockShared& bs = bs_all[tile];
     const int off = a.off[w];
-    const int N = a.off[w + 1] - off;
+    const int N = live ? a.off[w + 1] - off : 0;
     Ctx c;
     c.N = N; c.w = w; c.a = &a; c.bs = &bs;
     carve(smem_raw + (size_t)tile * smem_bytes(a.max_n), N, c.s);
@@ -360,6 +374,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
     s.par = a.par + (size_t)off * kParF;
     s.S = a.S + (size_t)off * 3 * kMaxStatics;
     const StepParams sp = a.sp;
+    const int Nw = warp_max(N);  // loop bound of the per-body phases (warp-uniform)
 
     // working copy of the world (coalesced, contiguous per world)
     for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
@@ -368,93 +383,110 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
         s.isbox[b] = (__ldg(s.par + (size_t)b * kParF + 15) != 0.0) ? 1 : 0;
         s.isstat[b] = (__ldg(s.par + (size_t)b * kParF) == 0.0) ? 1 : 0;
     }
-    __syncwarp(tmask);
+    __syncwarp();
     if (tid == 0) {  // static ordinals (1-based); more than kMaxStatics -> always the serial walk
         int ns = 0;
         for (int b = 0; b < N; b++)
             if (s.isstat[b]) { ns++; s.isstat[b] = (unsigned char)(ns <= kMaxStatics ? ns : kMaxStatics); }
         bs.nstat = ns;
     }
-    __syncwarp(tmask);
+    __syncwarp();
 
     unsigned long long t_steps = 0, t_tested = 0, t_hits = 0, t_contacts = 0, t_fallback = 0, t_overflow = 0, t_exc = 0;
     unsigned long long t_fbm = 0, t_fbc = 0, t_fbs = 0;
     double t_maxpen = 0.0;
-
     unsigned long long cyc[5] = {0, 0, 0, 0, 0}, cyc_max = 0, sumK = 0, sumL = 0;
+
     for (int step = 0; step < a.n_steps; step++) {
         long long tk0 = clock64(), tk = tk0;
-        // attempts: 0 = margin x1, 1 = margin x8, 2 = exact serial walk over all pairs
+        // per tile: attempt 0 = margin x1, 1 = margin x8, 2 = exact serial walk over all pairs
         int attempt = (a.exact_all_pairs || bs.nstat > kMaxStatics) ? 2 : 0;
-        int fb_reason = 0;  // 1 margin, 2 capacity/levels, 3 static pose
-        for (;; attempt++) {
-            if (tid == 0) {
-                bs.violate = 0; bs.need_serial = 0; bs.K = 0; bs.maxl = 0;
-                bs.tested = bs.hits = bs.contacts = bs.overflow = bs.ref_exc = 0;
-                bs.max_pen_bits = 0ull;
-                if (a.rec_counts) { a.rec_counts[2 * w] = 0; a.rec_counts[2 * w + 1] = 0; }
-            }
-            c.tested = c.hits = c.contacts = c.overflow = c.ref_exc = 0;
-            c.max_pen = 0.0;
-            for (int b = tid; b < N; b += T) { s.pvalid[b] = 0; s.nhit[b] = 0; }
-            __syncwarp(tmask);
+        int fb_reason = 0;  // 1 margin, 2 levels, 3 static pose
+        bool finished = !live;
+        c.tested = c.hits = c.contacts = c.overflow = c.ref_exc = 0;
+        c.max_pen = 0.0;
 
-            if (attempt < 2) {
-                // ---- A: predicted copy of every body + cull spheres -----------------------------------
-                // The sphere is centred on the PREDICTED position: a body no pair has changed is tested
-                // exactly there (deviation 0).  A write-back keeps the position, and each further
-                // prediction moves it by dt * (its new velocity): the margin covers n such moves, n
-                // estimated from the number of colliding pairs the body was in during the previous step.
+        for (int pass = 0; pass < 3; pass++) {  // a tile needs at most three attempts
+            if (!__any_sync(FULL, !finished)) break;
+            const bool run = !finished;
+            bool fast = run && attempt < 2;
+            const bool serial = run && attempt == 2;
+            if (run) {
+                if (tid == 0) {
+                    bs.violate = 0; bs.need_serial = 0; bs.K = 0; bs.maxl = 0;
+                    if (a.rec_counts) { a.rec_counts[2 * w] = 0; a.rec_counts[2 * w + 1] = 0; }
+                }
+                c.tested = c.hits = c.contacts = c.overflow = c.ref_exc = 0;
+                c.max_pen = 0.0;
+                for (int b = tid; b < N; b += T) { s.pvalid[b] = 0; s.nhit[b] = 0; }
+            }
+            __syncwarp();
+
+            // ---- A: predicted copy of every body + cull spheres ---------------------------------------
+            // The sphere is centred on the PREDICTED position: a body no pair has changed is tested exactly
+            // there (deviation 0).  A write-back keeps the position, and each further prediction moves it by
+            // dt * (its new velocity): the margin covers n such moves, n estimated from the number of
+            // colliding pairs the body was in during the previous step.
+            {
                 const double mscale = attempt == 0 ? 1.0 : 8.0;
-                for (int b = tid; b < N; b += T) {
-                    Par p; ld_par(s.par, N, b, p);
+                for (int b = tid; b < Nw; b += T) {
+                    const bool on = fast && b < N;
+                    Par p;
                     Dyn cur, pr;
-                    ld_dyn(s.dyn, N, b, cur);
-                    integrate(cur, p, sp, pr);
-                    st_dyn(s.pred, N, b, pr);
-                    s.pvalid[b] = 1;
-                    if (p.is_static && !pose_fixed(cur, pr)) bs.need_serial = 1;
-                    s.sx[b] = pr.x.x; s.sx[N + b] = pr.x.y; s.sx[2 * N + b] = pr.x.z;
-                    double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
-                    double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
-                    double n = (double)(s.nprev[b] < 6 ? s.nprev[b] : 6) + 2.0;
-                    double m = p.is_static ? 0.0 : mscale * (0.01 + n * sp.dt * (speed + n * acc * sp.dt + 0.5));
-                    if (!(m == m)) m = 0.0;  // NaN state: the world is flagged anyway
-                    double rs, rb;
-                    if (p.shape == 0) {
-                        rs = p.dims[0]; rb = 1.7320508075688774 * p.dims[0];
-                    } else {
-                        double hx = 0.5 * p.dims[0], hy = 0.5 * p.dims[1], hz = 0.5 * p.dims[2];
-                        rs = rb = sqrt(hx * hx + hy * hy + hz * hz);
+                    if (on) {
+                        ld_par(s.par, N, b, p);
+                        ld_dyn(s.dyn, N, b, cur);
                     }
-                    const double slack = 1.0 + 1e-6;
-                    s.rad_s[b] = rs * slack + 1e-9 + m;
-                    s.rad_b[b] = rb * slack + 1e-9 + m;
-                    s.marg2[b] = m * m;
-                    s.last[b] = 0;
+                    if (on) integrate(cur, p, sp, pr);  // lanes of all the warp's worlds enter together
+                    if (on) {
+                        st_dyn(s.pred, N, b, pr);
+                        s.pvalid[b] = 1;
+                        if (p.is_static && !pose_fixed(cur, pr)) bs.need_serial = 1;
+                        s.sx[b] = pr.x.x; s.sx[N + b] = pr.x.y; s.sx[2 * N + b] = pr.x.z;
+                        double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
+                        double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
+                        double n = (double)(s.nprev[b] < 6 ? s.nprev[b] : 6) + 2.0;
+                        double m = p.is_static ? 0.0 : mscale * (0.01 + n * sp.dt * (speed + n * acc * sp.dt + 0.5));
+                        if (!(m == m)) m = 0.0;  // NaN state: the world is flagged anyway
+                        double rs, rb;
+                        if (p.shape == 0) {
+                            rs = p.dims[0]; rb = 1.7320508075688774 * p.dims[0];
+                        } else {
+                            double hx = 0.5 * p.dims[0], hy = 0.5 * p.dims[1], hz = 0.5 * p.dims[2];
+                            rs = rb = sqrt(hx * hx + hy * hy + hz * hz);
+                        }
+                        const double slack = 1.0 + 1e-6;
+                        s.rad_s[b] = rs * slack + 1e-9 + m;
+                        s.rad_b[b] = rb * slack + 1e-9 + m;
+                        s.marg2[b] = m * m;
+                        s.last[b] = 0;
+                    }
                 }
-                __syncwarp(tmask);
-                if (bs.need_serial) {  // a static pose still moves under integrate(): exact serial walk this step
-                    __syncwarp(tmask);   // every thread has read the flag before thread 0 clears it at the loop top
-                    attempt = 1; fb_reason = 3;
-                    continue;          // state untouched so far: no reload needed
-                }
-                if (tid == 0) { long long t = clock64(); cyc[0] += t - tk; tk = t; }
-                // ---- B: near list, lexicographic order kept by a row scan -------------------------------
+            }
+            __syncwarp();
+            if (fast && bs.need_serial) {  // a static pose still moves under integrate(): exact serial walk
+                fast = false;              // (state untouched so far: no reload needed)
+                attempt = 2; fb_reason = 3;
+            }
+            if (tid == 0 && live) { long long t = clock64(); cyc[0] += t - tk; tk = t; }
+            // ---- B: near list, lexicographic order kept by a row scan ---------------------------------------
+            if (fast) {
                 for (int i = tid; i < N; i += T) {
                     int cn = 0;
                     for (int j = i + 1; j < N; j++) cn += near_test(s, N, i, j) ? 1 : 0;
                     s.row[i] = cn;
                 }
-                __syncwarp(tmask);
-                if (tid == 0) {
-                    int acc = 0;
-                    for (int i = 0; i < N; i++) { int t = s.row[i]; s.row[i] = acc; acc += t; }
-                    s.row[N] = acc;
-                    bs.K = acc;
-                }
-                __syncwarp(tmask);
-                const int K = bs.K;
+            }
+            __syncwarp();
+            if (fast && tid == 0) {
+                int acc = 0;
+                for (int i = 0; i < N; i++) { int t = s.row[i]; s.row[i] = acc; acc += t; }
+                s.row[N] = acc;
+                bs.K = acc;
+            }
+            __syncwarp();
+            const int K = fast ? bs.K : 0;
+            if (fast) {
                 for (int i = tid; i < N; i += T) {
                     int o = s.row[i];
                     for (int j = i + 1; j < N; j++)
@@ -464,105 +496,139 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                             o++;
                         }
                 }
-                __syncwarp(tmask);
-                if (tid == 0) { long long t = clock64(); cyc[1] += t - tk; tk = t; }
-                // ---- C: wavefront levels (serial scan of the ordered list by one thread) ------------------
-                if (tid == 0) {
-                    int maxl = 0;
-                    for (int k = 0; k < K; k++) {
-                        unsigned ij = s.near[k];
-                        int i = ij & 0xffff, j = ij >> 16;
-                        int li = s.isstat[i] ? 0 : s.last[i];
-                        int lj = s.isstat[j] ? 0 : s.last[j];
-                        int l = (li > lj ? li : lj) + 1;
-                        s.level[k] = (unsigned short)l;
-                        if (!s.isstat[i]) s.last[i] = (unsigned short)l;
-                        if (!s.isstat[j]) s.last[j] = (unsigned short)l;
-                        if (l > maxl) maxl = l;
-                    }
-                    bs.maxl = maxl;
-                    if (maxl > kMaxLevels) bs.need_serial = 1;
+            }
+            __syncwarp();
+            if (tid == 0 && live) { long long t = clock64(); cyc[1] += t - tk; tk = t; }
+            // ---- C: wavefront levels (serial scan of the ordered list by one lane per world) ------------------
+            if (fast && tid == 0) {
+                int maxl = 0;
+                for (int k = 0; k < K; k++) {
+                    unsigned ij = s.near[k];
+                    int i = ij & 0xffff, j = ij >> 16;
+                    int li = s.isstat[i] ? 0 : s.last[i];
+                    int lj = s.isstat[j] ? 0 : s.last[j];
+                    int l = (li > lj ? li : lj) + 1;
+                    s.level[k] = (unsigned short)l;
+                    if (!s.isstat[i]) s.last[i] = (unsigned short)l;
+                    if (!s.isstat[j]) s.last[j] = (unsigned short)l;
+                    if (l > maxl) maxl = l;
                 }
-                __syncwarp(tmask);
-                if (bs.need_serial) {
-                    __syncwarp(tmask);
-                    attempt = 1; fb_reason = 2;
-                    continue;
-                }
-                // counting sort of the near list by level (order inside a level is free)
-                const int maxl = bs.maxl;
+                bs.maxl = maxl;
+                if (maxl > kMaxLevels) bs.need_serial = 1;
+            }
+            __syncwarp();
+            if (fast && bs.need_serial) {  // more levels than the table holds: exact serial walk next pass
+                fast = false;
+                attempt = 2; fb_reason = 2;
+            }
+            // counting sort of the near list by level (order inside a level is free)
+            const int maxl = fast ? bs.maxl : 0;
+            if (fast)
                 for (int l = tid; l <= maxl + 1; l += T) s.lvl_start[l] = 0;
-                __syncwarp(tmask);
+            __syncwarp();
+            if (fast)
                 for (int k = tid; k < K; k += T) atomicAdd(&s.lvl_start[s.level[k]], 1);
-                __syncwarp(tmask);
-                if (tid == 0) {
-                    int acc = 0;
-                    for (int l = 0; l <= maxl + 1; l++) { int t = s.lvl_start[l]; s.lvl_start[l] = acc; acc += t; }
-                }
-                __syncwarp(tmask);
-                // scatter; lvl_start[l] is advanced to the END of level l, i.e. the start of l+1
+            __syncwarp();
+            if (fast && tid == 0) {
+                int acc = 0;
+                for (int l = 0; l <= maxl + 1; l++) { int t = s.lvl_start[l]; s.lvl_start[l] = acc; acc += t; }
+            }
+            __syncwarp();
+            // scatter; lvl_start[l] is advanced to the END of level l, i.e. the start of l+1
+            if (fast)
                 for (int k = tid; k < K; k += T) {
                     int pos = atomicAdd(&s.lvl_start[s.level[k]], 1);
                     s.order[pos] = (unsigned short)k;
                 }
-                __syncwarp(tmask);
-                if (tid == 0) { long long t = clock64(); cyc[2] += t - tk; tk = t; sumK += K; sumL += maxl; }
-                // ---- D: wavefronts ------------------------------------------------------------------------
-                for (int l = 1; l <= maxl; l++) {
-                    int beg = s.lvl_start[l - 1], end = s.lvl_start[l];
-                    for (int q = beg + tid; q < end; q += T) {
-                        int k = s.order[q];
-                        unsigned ij = s.near[k];
-                        process_pair(c, ij & 0xffff, ij >> 16, k, true);
-                    }
-                    __syncwarp(tmask);
-                }
-                if (tid == 0) { long long t = clock64(); cyc[3] += t - tk; tk = t; }
-                if (bs.violate) {  // restart from the published state
-                    for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
-                    __syncwarp(tmask);
-                    fb_reason = 1;
-                    continue;
-                }
-                // ---- E: static bodies: L = fold over their colliding pairs in pair order -------------------
-                for (int b = tid; b < N; b += T) {
-                    if (!s.isstat[b]) continue;
-                    Par p; ld_par(s.par, N, b, p);
-                    double* cb = s.dyn + (size_t)b * kDynF;
-                    double* pb = s.pred + (size_t)b * kDynF;
-                    d3 L = mk(cb[15], cb[16], cb[17]);
-                    d3 dL = scale(sp.dt, p.T);
-                    const double* Sb = s.S + 3 * (s.isstat[b] - 1) * N;
-                    for (int k = 0; k < K; k++) {
-                        if (!s.hit[k]) continue;
-                        unsigned ij = s.near[k];
-                        int i = ij & 0xffff, j = ij >> 16;
-                        int other;
-                        if (i == b) other = j; else if (j == b) other = i; else continue;
-                        L = L + dL;  // the predicted copy's integration
-                        L = L + mk(Sb[3 * other], Sb[3 * other + 1], Sb[3 * other + 2]);
-                    }
-                    cb[15] = L.x; cb[16] = L.y; cb[17] = L.z;
-                    // pose is a fixed point: the final sweep only has to add dt*T to L
-                    d3 Lf = L + dL;
-                    pb[15] = Lf.x; pb[16] = Lf.y; pb[17] = Lf.z;
-                }
-                __syncwarp(tmask);
-            } else {
-                // ---- exact serial walk over ALL pairs in Dummy order (BroadPhase.fs:33-39) -------------------
-                if (tid == 0) {
-                    for (int i = 0; i < N; i++)
-                        for (int j = i + 1; j < N; j++) {
-                            if (s.isstat[i] && s.isstat[j]) continue;
-                            process_pair(c, i, j, 0, false);
+            __syncwarp();
+            if (tid == 0 && live) { long long t = clock64(); cyc[2] += t - tk; tk = t; if (fast) { sumK += K; sumL += maxl; } }
+
+            // ---- D: wavefronts.  Every tile walks ITS levels, T pairs per round; the rounds are warp-uniform ----
+            {
+                int lvl = 1, pos = 0;
+                bool dact = fast && maxl >= 1;
+                for (;;) {
+                    if (!__any_sync(FULL, dact)) break;
+                    int pi_ = 0, pj_ = 0, pk_ = 0;
+                    bool valid = false;
+                    int end = 0, beg = 0;
+                    if (dact) {
+                        beg = s.lvl_start[lvl - 1]; end = s.lvl_start[lvl];
+                        int q = beg + pos + tid;
+                        if (q < end) {
+                            pk_ = s.order[q];
+                            unsigned ij = s.near[pk_];
+                            pi_ = ij & 0xffff; pj_ = ij >> 16;
+                            valid = true;
                         }
-                    long long t = clock64(); cyc[3] += t - tk; tk = t;
+                    }
+                    if (valid) process_pair(c, pi_, pj_, pk_, true);
+                    __syncwarp();
+                    if (dact) {
+                        pos += T;
+                        if (beg + pos >= end) {
+                            lvl++; pos = 0;
+                            if (lvl > maxl) dact = false;
+                        }
+                    }
                 }
-                __syncwarp(tmask);
             }
-            break;
+            // ---- exact serial walk over ALL pairs in Dummy order (BroadPhase.fs:33-39), one lane per world ------
+            {
+                int si = 0, sj = 1;
+                bool sact = serial && tid == 0 && N >= 2;
+                for (;;) {
+                    if (!__any_sync(FULL, sact)) break;
+                    bool valid = sact && !(s.isstat[si] && s.isstat[sj]);
+                    if (valid) process_pair(c, si, sj, 0, false);
+                    if (sact) {
+                        sj++;
+                        if (sj >= N) { si++; sj = si + 1; if (sj >= N) sact = false; }
+                    }
+                }
+            }
+            __syncwarp();
+            if (tid == 0 && live) { long long t = clock64(); cyc[3] += t - tk; tk = t; }
+
+            if (fast) {
+                if (bs.violate) {  // restart from the published state with the wider margin (or serially)
+                    for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
+                    fb_reason = 1;
+                    attempt++;
+                } else {
+                    // ---- E: static bodies: L = fold over their colliding pairs in pair order -------------------
+                    for (int b = tid; b < N; b += T) {
+                        if (!s.isstat[b]) continue;
+                        Par p; ld_par(s.par, N, b, p);
+                        double* cb = s.dyn + (size_t)b * kDynF;
+                        double* pb = s.pred + (size_t)b * kDynF;
+                        d3 L = mk(cb[15], cb[16], cb[17]);
+                        d3 dL = scale(sp.dt, p.T);
+                        const double* Sb = s.S + 3 * (s.isstat[b] - 1) * N;
+                        for (int k = 0; k < K; k++) {
+                            if (!s.hit[k]) continue;
+                            unsigned ij = s.near[k];
+                            int i = ij & 0xffff, j = ij >> 16;
+                            int other;
+                            if (i == b) other = j; else if (j == b) other = i; else continue;
+                            L = L + dL;  // the predicted copy's integration
+                            L = L + mk(Sb[3 * other], Sb[3 * other + 1], Sb[3 * other + 2]);
+                        }
+                        cb[15] = L.x; cb[16] = L.y; cb[17] = L.z;
+                        // pose is a fixed point: the final sweep only has to add dt*T to L
+                        d3 Lf = L + dL;
+                        pb[15] = Lf.x; pb[16] = Lf.y; pb[17] = Lf.z;
+                    }
+                    finished = true;
+                }
+            } else if (serial) {
+                finished = true;
+            }
+            // (a tile that switched to the serial walk above has run == true, fast == false, serial == false:
+            //  it goes round again with attempt == 2)
+            __syncwarp();
         }
-        if (tid == 0 && attempt > 0 && !a.exact_all_pairs) {
+        if (tid == 0 && live && fb_reason != 0 && !a.exact_all_pairs) {
             t_fallback++;
             if (fb_reason == 1) t_fbm++; else if (fb_reason == 2) t_fbc++; else t_fbs++;
         }
@@ -572,9 +638,9 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
         // last writer of a body wins (the host marks it).  Results are staged in the predicted-copy area of the
         // bodies they replace and committed after all joints have read their inputs.
         if (a.restore_joints && a.joff) {
-            const int j0 = a.joff[w], nj = a.joff[w + 1] - j0;
+            const int j0 = a.joff[w], nj = live ? a.joff[w + 1] - j0 : 0;
             for (int b = tid; b < N; b += T) s.last[b] = 0;
-            __syncwarp(tmask);
+            __syncwarp();
             for (int base = 0; base < nj; base += T) {
                 if (base + tid < nj) {
                     const int q = j0 + base + tid;
@@ -605,7 +671,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                     if (lastf & 2) { st_dyn(s.pred, N, bb, o2); s.last[bb] = 1; }
                 }
             }
-            __syncwarp(tmask);
+            __syncwarp();
             for (int b = tid; b < N; b += T)
                 if (s.last[b]) {
                     Dyn d;
@@ -613,46 +679,55 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                     st_dyn(s.dyn, N, b, d);
                     s.pvalid[b] = 0;
                 }
-            __syncwarp(tmask);
+            __syncwarp();
         }
 
         // ---- F: final integration of every body (SimulatorState.fs:169-173) -----------------------------------
-        for (int b = tid; b < N; b += T) {
-            Dyn out;
-            if (s.pvalid[b]) {
-                ld_dyn(s.pred, N, b, out);
-            } else {
-                Par p; ld_par(s.par, N, b, p);
-                Dyn cur; ld_dyn(s.dyn, N, b, cur);
-                integrate(cur, p, sp, out);
+        for (int b = tid; b < Nw; b += T) {
+            const bool on = b < N;
+            const bool need = on && !s.pvalid[b];
+            Dyn out, cur;
+            Par p;
+            if (need) {
+                ld_par(s.par, N, b, p);
+                ld_dyn(s.dyn, N, b, cur);
             }
-            st_dyn(s.dyn, N, b, out);
-            s.nprev[b] = s.nhit[b];
+            if (need) integrate(cur, p, sp, out);
+            if (on) {
+                if (!need) ld_dyn(s.pred, N, b, out);
+                st_dyn(s.dyn, N, b, out);
+                s.nprev[b] = s.nhit[b];
+            }
         }
-        __syncwarp(tmask);
+        __syncwarp();
         // publish the step (also the restart point of the next step's fallback)
         for (int k = tid; k < kDynF * N; k += T) gdyn[k] = s.dyn[k];
+        if (tid == 0 && live) { long long t = clock64(); cyc[4] += t - tk; if ((unsigned long long)(t - tk0) > cyc_max) cyc_max = t - tk0; }
 
-        if (tid == 0) { long long t = clock64(); cyc[4] += t - tk; if ((unsigned long long)(t - tk0) > cyc_max) cyc_max = t - tk0; }
-        // fold per-thread counters
-        atomicAdd(&bs.tested, c.tested); atomicAdd(&bs.hits, c.hits); atomicAdd(&bs.contacts, c.contacts);
-        atomicAdd(&bs.overflow, c.overflow); atomicAdd(&bs.ref_exc, c.ref_exc);
-        atomicMax(&bs.max_pen_bits, (unsigned long long)__double_as_longlong(c.max_pen));
-        __syncwarp(tmask);
-        if (tid == 0) {
+        // fold per-lane counters into the tile's block
+        if (tid == 0) { bs.tested = bs.hits = bs.contacts = bs.overflow = bs.ref_exc = 0; bs.max_pen_bits = 0ull; }
+        __syncwarp();
+        if (live) {
+            atomicAdd(&bs.tested, c.tested); atomicAdd(&bs.hits, c.hits); atomicAdd(&bs.contacts, c.contacts);
+            atomicAdd(&bs.overflow, c.overflow); atomicAdd(&bs.ref_exc, c.ref_exc);
+            atomicMax(&bs.max_pen_bits, (unsigned long long)__double_as_longlong(c.max_pen));
+        }
+        __syncwarp();
+        if (tid == 0 && live) {
             t_steps++; t_tested += bs.tested; t_hits += bs.hits; t_contacts += bs.contacts;
             t_overflow += bs.overflow; t_exc += bs.ref_exc;
             t_maxpen = fmax(t_maxpen, __longlong_as_double((long long)bs.max_pen_bits));
         }
-        __syncwarp(tmask);
+        __syncwarp();
     }
 
     // NaN/Inf scan + stats write-out
     int bad = 0;
     for (int k = tid; k < kDynF * N; k += T) bad |= !isfinite(s.dyn[k]);
-    bad = (__ballot_sync(tmask, bad) != 0u);
+    const unsigned tmask = (T == 32) ? FULL : (((1u << T) - 1u) << (tile * T));
+    bad = (__ballot_sync(FULL, bad) & tmask) != 0u;
     for (int b = tid; b < N; b += T) a.hitcnt[off + b] = s.nprev[b];
-    if (tid == 0) {
+    if (tid == 0 && live) {
         WorldStats& st = a.stats[w];
         st.steps += t_steps; st.tested += t_tested; st.hits += t_hits; st.contacts += t_contacts;
         st.fallback += t_fallback; st.overflow += t_overflow; st.ref_exc += t_exc;
