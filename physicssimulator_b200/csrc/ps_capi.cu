@@ -71,6 +71,7 @@ struct Batch {
     int* d_row = nullptr;             // near-list row offsets
     unsigned char* d_lists = nullptr; // near list | level | order | hit of every world (9 B per pair of the world)
     long long* d_lists_off = nullptr;
+    PairScratch* d_scratch = nullptr; // one record per launched thread
     int *d_joff = nullptr, *d_ja = nullptr, *d_jb = nullptr;
     double *d_jla = nullptr, *d_jlb = nullptr;
     unsigned char* d_jlast = nullptr;
@@ -185,7 +186,7 @@ void dfree(T*& p)
 }
 void free_device(Batch* B)
 {
-    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off);
+    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_scratch);
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
 }
@@ -256,6 +257,8 @@ int upload(Batch* B, bool with_state)
         CK(cudaMemcpy(B->d_lists_off, loff.data(), loff.size() * sizeof(long long), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&B->d_cull, nb * 6 * sizeof(double)));
         CK(cudaMalloc(&B->d_row, (nb + (size_t)B->n_worlds + 1) * sizeof(int)));
+        const size_t wpc = 32 / B->threads, grid = ((size_t)B->n_worlds + wpc - 1) / wpc;
+        CK(cudaMalloc(&B->d_scratch, std::max<size_t>(grid, 1) * 32 * sizeof(PairScratch)));
     }
     CK(cudaMalloc(&B->d_hitcnt, nb));
     CK(cudaMemsetAsync(B->d_hitcnt, 0, nb, B->stream));
@@ -468,7 +471,7 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
     a.max_n = B->max_n;
     a.hitcnt = B->d_hitcnt; a.cur = B->d_cur; a.pred = B->d_pred; a.S = B->d_S;
-    a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off;
+    a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.scratch = B->d_scratch;
     const int wpc = 32 / B->threads;  // worlds per one-warp CTA
     const int grid = (B->n_worlds + wpc - 1) / wpc;
     if (B->threads == 8) step_kernel<8><<<grid, 32, B->smem, st>>>(a);

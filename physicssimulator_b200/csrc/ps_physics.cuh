@@ -42,6 +42,11 @@ struct Contact {
     double pen;
     uint32_t feat;
 };
+// per-contact solver data (ContactPointImpulseData.fs:9-21)
+struct CPData {
+    d3 r1, r2;
+    double bias, mN, mT0, mT1, accN, accT0, accT1;
+};
 
 // Box.fs:23-49 tables.  Vertex k = (sx, sy, sz) signs; kept as bit masks: bit2 = +x, bit1 = +y, bit0 = +z.
 // V = (---)(-+-)(++-)(+--)(--+)(-++)(+++)(+-+)
@@ -111,6 +116,21 @@ PSN void make_obox(const Dyn& b, const Par& p, OBox& ob)
     }
 }
 PSD d3 face_vertex(const OBox& ob, int f, int k) { return ob.v[kFaceVert[f][k]]; }
+
+struct PolyV {
+    d3 p;
+    unsigned tag;
+};
+// Working arrays of ONE pair test.  On the device they live in a per-thread record in GLOBAL memory,
+// contiguous per thread: the compiler's local-memory stack is interleaved across the 32 lanes of a warp,
+// so with a handful of active lanes every 8-byte access drags a 32-byte sector through the caches for 4
+// useful bytes (ncu: 2.7 B per sector, DRAM traffic 44x the algorithmic bytes).
+struct PairScratch {
+    Contact cs[PS_MAX_CONTACTS];
+    CPData cp[PS_MAX_CONTACTS];
+    OBox o1, o2;
+    PolyV bufA[PS_MAX_CONTACTS + 4], bufB[PS_MAX_CONTACTS + 4];
+};
 
 // min/max of the 8 vertex projections in OrientedBox.Vertices order (ties keep the first, values only)
 PSN void project_box(const OBox& ob, d3 axis, double& mn, double& mx)
@@ -199,9 +219,9 @@ PSN int detect_ss(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, Co
 // SAT.SphereBox.tryFindSeparatingAxis (SAT.fs:108-151) + detectedSphereBoxCollision
 // (CollisionDetection.fs:166-184). Normal returned "from box". err set where the reference throws.
 PSN int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Par& bp, double eps, Contact* out,
-                          int& face, int& err)
+                          int& face, int& err, PairScratch& sc)
 {
-    OBox ob;
+    OBox& ob = sc.o1;
     make_obox(bb, bp, ob);
     double r = sp_.dims[0];
     double best_pen = 0.0;
@@ -258,17 +278,14 @@ PSD bool sat_ranges(double a, double b, double c, double d, double& pen, bool& f
     return false;
 }
 
-struct PolyV {
-    d3 p;
-    unsigned tag;
-};
 
 // detectBoxBoxCollision (CollisionDetection.fs:29-164) over SAT.tryFindSeparatingAxis (SAT.fs:206-240)
 // returns #contacts (0 = none); overflow set when the manifold would exceed PS_MAX_CONTACTS
 PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
-                  int& overflow)
+                  int& overflow, PairScratch& sc)
 {
-    OBox o1, o2;
+    OBox& o1 = sc.o1;
+    OBox& o2 = sc.o2;
     make_obox(b1, p1, o1);
     make_obox(b2, p2, o2);
 
@@ -363,9 +380,8 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
             }
         }
         // clip the incident quad by the inverted planes of the adjacent faces (Box.fs:116-124, :56-61)
-        PolyV bufA[PS_MAX_CONTACTS + 4], bufB[PS_MAX_CONTACTS + 4];
-        PolyV* cur = bufA;
-        PolyV* nxt = bufB;
+        PolyV* cur = sc.bufA;
+        PolyV* nxt = sc.bufB;
         int n = 4;
 #pragma unroll 1
         for (int k = 0; k < 4; k++) {
@@ -493,20 +509,20 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
 
 // CollisionDetection.areColliding (CollisionDetection.fs:208-220)
 PSD int detect(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
-               int& overflow)
+               int& overflow, PairScratch& sc)
 {
     if (p1.shape == 0 && p2.shape == 0) return detect_ss(b1, p1, b2, p2, out);
-    if (p1.shape == 1 && p2.shape == 1) return detect_bb(b1, p1, b2, p2, eps, out, err, overflow);
+    if (p1.shape == 1 && p2.shape == 1) return detect_bb(b1, p1, b2, p2, eps, out, err, overflow, sc);
     int face = 0;
     if (p1.shape == 0) {
-        int n = detect_sphere_box(b1, p1, b2, p2, eps, out, face, err);
+        int n = detect_sphere_box(b1, p1, b2, p2, eps, out, face, err, sc);
         if (n) {
             out[0].n = -out[0].n;  // WithInvertedNormals (:217-219)
             out[0].feat = 1u | ((unsigned)face << 4);
         }
         return n;
     }
-    int n = detect_sphere_box(b2, p2, b1, p1, eps, out, face, err);
+    int n = detect_sphere_box(b2, p2, b1, p1, eps, out, face, err, sc);
     if (n) out[0].feat = 2u | ((unsigned)face << 4);
     return n;
 }
@@ -514,10 +530,6 @@ PSD int detect(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, doubl
 // ----------------------------------------------------------------------------------------
 // Per-pair solve (CollisionResponse.fs:73-146, ContactPointImpulseData.fs:23-66, Friction.fs:39-68)
 // ----------------------------------------------------------------------------------------
-struct CPData {
-    d3 r1, r2;
-    double bias, mN, mT0, mT1, accN, accT0, accT1;
-};
 
 // hat(r)^T * Iw * hat(r), products evaluated as dense 3x3 (RigidBody.fs:225-229)
 PSD m33 hat(d3 v)

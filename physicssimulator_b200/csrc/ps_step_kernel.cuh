@@ -99,6 +99,7 @@ struct KArgs {
     int* row;                 // [total_bodies + n_worlds]: per world N+1 row offsets of the near list
     unsigned char* lists;     // per world: n_pairs * 9 bytes (near u32 | level u16 | order u16 | hit u8)
     const long long* lists_off; // n_worlds+1 byte offsets (16-byte aligned)
+    PairScratch* scratch;     // one record per launched thread
 };
 
 // ---- per-world working set: pointers into global scratch + a small shared-memory block -------------
@@ -211,6 +212,7 @@ struct Ctx {
     int N, w;
     const KArgs* a;
     BlockShared* bs;
+    PairScratch* scratch;  // this thread's record in global memory
     // per-thread counters of the current attempt
     unsigned tested, hits, contacts, overflow, ref_exc;
     double max_pen;
@@ -273,10 +275,11 @@ PSN void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
     Dyn di, dj;
     get_pred(c, i, pi, di, fast);
     get_pred(c, j, pj, dj, fast);
-    Contact cs[PS_MAX_CONTACTS];
+    PairScratch& sc = *c.scratch;
+    Contact* cs = sc.cs;
     int err = 0, ovf = 0;
     c.tested++;
-    int nc = detect(di, pi, dj, pj, c.a->sp.eps, cs, err, ovf);
+    int nc = detect(di, pi, dj, pj, c.a->sp.eps, cs, err, ovf, sc);
     if (err) c.ref_exc++;
     if (ovf) c.overflow++;
     if (nc <= 0) return;
@@ -287,8 +290,7 @@ PSN void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
     bool si = fast && pi.is_static, sj = fast && pj.is_static;
     if (si) di.L = mk(0.0, 0.0, 0.0);
     if (sj) dj.L = mk(0.0, 0.0, 0.0);
-    CPData cp[PS_MAX_CONTACTS];
-    resolve(di, pi, dj, pj, cs, nc, cp, c.a->sp);
+    resolve(di, pi, dj, pj, cs, nc, sc.cp, c.a->sp);
     if (fast) c.s.hit[near_k] = 1;
     if (si) {  // a static-static pair never reaches here (canIntersect)
         double* S = c.s.S + 3 * ((c.s.isstat[i] - 1) * c.N + j);
@@ -355,6 +357,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
     const int N = live ? a.off[w + 1] - off : 0;
     Ctx c;
     c.N = N; c.w = w; c.a = &a; c.bs = &bs;
+    c.scratch = a.scratch + ((size_t)blockIdx.x * 32 + threadIdx.x);
     carve(smem_raw + (size_t)tile * smem_bytes(a.max_n), N, c.s);
     Smem& s = c.s;
     {

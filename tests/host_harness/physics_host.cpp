@@ -67,10 +67,11 @@ void hh_world_step(int N, const double* par, double* dyn, const ps_step_config* 
                 Par pi, pj; ld_par(par, N, i, pi); ld_par(par, N, j, pj);
                 if (pi.is_static && pj.is_static) continue;
                 Dyn di, dj; get_pred(i, pi, di); get_pred(j, pj, dj);
-                Contact cs[PS_MAX_CONTACTS];
+                static PairScratch sc;
+                Contact* cs = sc.cs;
                 int err = 0, ovf = 0;
                 counters[0]++;
-                int nc = detect(di, pi, dj, pj, sp.eps, cs, err, ovf);
+                int nc = detect(di, pi, dj, pj, sp.eps, cs, err, ovf, sc);
                 counters[3] += err; counters[4] += ovf;
                 if (nc <= 0) continue;
                 counters[1]++; counters[2] += nc;
@@ -86,8 +87,7 @@ void hh_world_step(int N, const double* par, double* dyn, const ps_step_config* 
                         ncs++;
                     }
                 }
-                CPData cp[PS_MAX_CONTACTS];
-                resolve(di, pi, dj, pj, cs, nc, cp, sp);
+                resolve(di, pi, dj, pj, cs, nc, sc.cp, sp);
                 st_dyn(dyn, N, i, di); pvalid[i] = 0;
                 st_dyn(dyn, N, j, dj); pvalid[j] = 0;
             }
