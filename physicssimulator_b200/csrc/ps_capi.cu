@@ -72,6 +72,8 @@ struct Batch {
     unsigned char* d_lists = nullptr; // near list | level | order | hit of every world (9 B per pair of the world)
     long long* d_lists_off = nullptr;
     PairScratch* d_scratch = nullptr; // one record per launched thread
+    int* d_lvl = nullptr;
+    unsigned short* d_last = nullptr;
     int *d_joff = nullptr, *d_ja = nullptr, *d_jb = nullptr;
     double *d_jla = nullptr, *d_jlb = nullptr;
     unsigned char* d_jlast = nullptr;
@@ -186,7 +188,7 @@ void dfree(T*& p)
 }
 void free_device(Batch* B)
 {
-    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_scratch);
+    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_scratch); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
 }
@@ -232,6 +234,13 @@ int upload(Batch* B, bool with_state)
     CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, B->device));
     if ((long long)B->smem > dev_max)
         return fail(PS_ERR_INVALID_ARGUMENT, "largest world (%d bodies) needs %zu B of shared memory; device allows %d", B->max_n, B->smem, dev_max);
+    {   // the kernel needs little shared memory; give the rest of the unified array to L1 (local stack + scratch)
+        int pct = 12;
+        if (const char* e = getenv("PS_B200_CARVEOUT")) pct = atoi(e);
+        CK(cudaFuncSetAttribute(step_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        CK(cudaFuncSetAttribute(step_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        CK(cudaFuncSetAttribute(step_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     CK(cudaFuncSetAttribute(step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
     CK(cudaFuncSetAttribute(step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
     CK(cudaFuncSetAttribute(step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
@@ -259,6 +268,8 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_row, (nb + (size_t)B->n_worlds + 1) * sizeof(int)));
         const size_t wpc = 32 / B->threads, grid = ((size_t)B->n_worlds + wpc - 1) / wpc;
         CK(cudaMalloc(&B->d_scratch, std::max<size_t>(grid, 1) * 32 * sizeof(PairScratch)));
+        CK(cudaMalloc(&B->d_lvl, (size_t)std::max(1, B->n_worlds) * (kMaxLevels + 2) * sizeof(int)));
+        CK(cudaMalloc(&B->d_last, nb * sizeof(unsigned short)));
     }
     CK(cudaMalloc(&B->d_hitcnt, nb));
     CK(cudaMemsetAsync(B->d_hitcnt, 0, nb, B->stream));
@@ -471,7 +482,7 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
     a.max_n = B->max_n;
     a.hitcnt = B->d_hitcnt; a.cur = B->d_cur; a.pred = B->d_pred; a.S = B->d_S;
-    a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.scratch = B->d_scratch;
+    a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.scratch = B->d_scratch; a.lvl = B->d_lvl; a.last = B->d_last;
     const int wpc = 32 / B->threads;  // worlds per one-warp CTA
     const int grid = (B->n_worlds + wpc - 1) / wpc;
     if (B->threads == 8) step_kernel<8><<<grid, 32, B->smem, st>>>(a);

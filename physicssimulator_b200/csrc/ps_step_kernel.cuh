@@ -45,7 +45,7 @@ using namespace psp;
 
 constexpr int kDynF = 18;       // doubles of dynamic state per body
 constexpr int kParF = 16;       // doubles of parameters per body
-constexpr int kMaxLevels = 510;
+constexpr int kMaxLevels = 1022;
 constexpr int kMaxStatics = 4;  // static bodies per world whose pairs run in parallel (more -> serial walk)
 constexpr int kMaxThreads = 128;
 
@@ -97,6 +97,8 @@ struct KArgs {
     // per-step lists of every world in global memory
     double* cull;             // [total_bodies*6]: per world sx(3N) | rad_s(N) | rad_b(N) | marg2(N)
     int* row;                 // [total_bodies + n_worlds]: per world N+1 row offsets of the near list
+    int* lvl;                 // [n_worlds * (kMaxLevels+2)] level offsets
+    unsigned short* last;     // [total_bodies] level of the last near pair of each body
     unsigned char* lists;     // per world: n_pairs * 9 bytes (near u32 | level u16 | order u16 | hit u8)
     const long long* lists_off; // n_worlds+1 byte offsets (16-byte aligned)
     PairScratch* scratch;     // one record per launched thread
@@ -117,8 +119,8 @@ struct Smem {
     unsigned short* order;  // GLOBAL: n_pairs
     unsigned char* hit;     // GLOBAL: n_pairs
     int* row;        // GLOBAL: N+1
-    int* lvl_start;  // shared: kMaxLevels+2
-    unsigned short* last;   // shared: N
+    int* lvl_start;  // GLOBAL: kMaxLevels+2
+    unsigned short* last;   // GLOBAL: N
     unsigned char* pvalid;  // shared: N
     unsigned char* isstat;  // shared: N   0 dynamic, 1+ordinal static
     unsigned char* isbox;   // shared: N
@@ -131,17 +133,12 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // shared memory of ONE world (a CTA hosts 32/TS of them)
 __host__ __device__ inline size_t smem_bytes(int N)
 {
-    size_t b = sizeof(int) * (size_t)(kMaxLevels + 2) + sizeof(unsigned short) * (size_t)N + (size_t)(5 * N);
-    return align_up(b, 16);
+    return align_up((size_t)(5 * N), 16);
 }
 
 __device__ inline void carve(unsigned char* base, int N, Smem& s)
 {
-    int* ip = reinterpret_cast<int*>(base);
-    s.lvl_start = ip; ip += kMaxLevels + 2;
-    unsigned short* h = reinterpret_cast<unsigned short*>(ip);
-    s.last = h;   h += N;
-    unsigned char* c = reinterpret_cast<unsigned char*>(h);
+    unsigned char* c = base;
     s.pvalid = c; c += N;
     s.isstat = c; c += N;
     s.isbox = c;  c += N;
@@ -275,7 +272,12 @@ PSN void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
     Dyn di, dj;
     get_pred(c, i, pi, di, fast);
     get_pred(c, j, pj, dj, fast);
+#if PS_SCRATCH_GLOBAL
     PairScratch& sc = *c.scratch;
+#else
+    PairScratch sc_local;
+    PairScratch& sc = sc_local;
+#endif
     Contact* cs = sc.cs;
     int err = 0, ovf = 0;
     c.tested++;
@@ -323,6 +325,9 @@ PSD bool near_test(const Smem& s, int N, int i, int j)
     return !(dd > r * r);  // NaN -> near
 }
 
+#ifndef PS_SCRATCH_GLOBAL
+#define PS_SCRATCH_GLOBAL 0  // 1: per-pair working arrays in a per-thread global record instead of the local stack
+#endif
 #ifndef PS_MINB32
 #define PS_MINB32 16  // resident one-warp CTAs per SM the register allocation must allow (65536 / (32 * regs))
 #endif
@@ -364,6 +369,8 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
         double* cu = a.cull + (size_t)off * 6;
         s.sx = cu; s.rad_s = cu + 3 * N; s.rad_b = cu + 4 * N; s.marg2 = cu + 5 * N;
         s.row = a.row + off + w;
+        s.lvl_start = a.lvl + (size_t)w * (kMaxLevels + 2);
+        s.last = a.last + off;
         unsigned char* o = a.lists + a.lists_off[w];
         const size_t np = (size_t)N * (size_t)(N > 0 ? N - 1 : 0) / 2;
         s.near = reinterpret_cast<unsigned*>(o);
