@@ -477,6 +477,8 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
     a.sp.iterations = B->cfg.solver_iterations; a.sp.friction = B->cfg.enable_friction; a.sp.integrator = B->cfg.integrator_kind;
     a.exact_all_pairs = B->cfg.exact_all_pairs;
     a.restore_joints = B->cfg.restore_joints;
+    a.margin_ncap = 16;
+    if (const char* e = getenv("PS_B200_NCAP")) a.margin_ncap = std::max(0, std::min(255, atoi(e)));  // tuning knob
     a.joff = B->d_joff; a.ja = B->d_ja; a.jb = B->d_jb; a.jla = B->d_jla; a.jlb = B->d_jlb; a.jlast = B->d_jlast;
     a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;

@@ -86,7 +86,9 @@ PSN void integrate(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o)
         o.L = b.L + dL;
     }
     double angle = norm(axis);
-    m33 rot = from_axis_angle(normalize(axis), angle);
+    // normalize(axis) = Normalize(2.0): same norm as `angle` (same routine, same input): reuse it
+    d3 u = (angle == 0.0) ? axis : scale(1.0 / angle, axis);
+    m33 rot = from_axis_angle(u, angle);
     o.R = orthonormalize(mulMM(rot, b.R));
 }
 
@@ -226,25 +228,32 @@ PSN int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Pa
     double r = sp_.dims[0];
     double best_pen = 0.0;
     int best = -1;
+    // The six face normals come in +- pairs (f, f+1) and n[f+1] == 0.0 - n[f] bit for bit (Box.fs:42-49, both are
+    // R*(+-e_k) + 0).  A dot product against the negated axis is 0.0 - (the dot product): every product flips
+    // sign and a zero-started sum is never -0.0.  So one projection pass serves both axes of a pair.
 #pragma unroll 1
-    for (int f = 0; f < 6; f++) {
-        d3 axis = ob.n[f];
-        double a, b;
-        project_box(ob, axis, a, b);
-        double c = dot(axis, sb.x);
-        double cp = c + r, cm = c - r;
-        double c1 = (cm < cp) ? cm : cp;  // List.min [c+r; c-r]
-        double c2 = (cm > cp) ? cm : cp;  // List.max
-        double pen;
-        if (c1 >= a && c1 <= b)
-            pen = b - c1;
-        else if (c1 <= a && c2 >= a)
-            pen = c2 - a;
-        else
-            return 0;
-        if (best < 0 || pen < best_pen) {
-            best = f;
-            best_pen = pen;
+    for (int fp = 0; fp < 6; fp += 2) {
+        d3 axis = ob.n[fp];
+        double a0, b0;
+        project_box(ob, axis, a0, b0);
+        double c0 = dot(axis, sb.x);
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            double a = h ? 0.0 - b0 : a0, b = h ? 0.0 - a0 : b0, c = h ? 0.0 - c0 : c0;
+            double cp = c + r, cm = c - r;
+            double c1 = (cm < cp) ? cm : cp;  // List.min [c+r; c-r]
+            double c2 = (cm > cp) ? cm : cp;  // List.max
+            double pen;
+            if (c1 >= a && c1 <= b)
+                pen = b - c1;
+            else if (c1 <= a && c2 >= a)
+                pen = c2 - a;
+            else
+                return 0;
+            if (best < 0 || pen < best_pen) {
+                best = fp + h;
+                best_pen = pen;
+            }
         }
     }
     d3 nb = ob.n[best];
@@ -292,35 +301,58 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
     int best_origin = -1, best_i = 0, best_j = 0;
     double best_pen = 0.0;
     d3 best_n = mk(0, 0, 0);
+    d3 fromFirst = b2.x - b1.x;
 
-    // Face1: axes = normals of box 1, target = box 1 (SAT.fs:230-231)
+    // Early "no collision": any ONE separated axis of the reference's list makes the result None
+    // (SAT.fs:185-198 `sequence`), whichever it is.  Try the face axis of each box that looks most along the
+    // centre offset first, with the reference's own arithmetic for that axis; a miss then costs 2 axes
+    // instead of up to 21.  If neither separates, the full ordered walk below decides (first-min semantics).
 #pragma unroll 1
-    for (int f = 0; f < 6; f++) {
-        d3 axis = o1.n[f];
-        double a, b, c, d, pen;
-        bool flip;
-        project_box(o1, axis, a, b);
-        project_box(o2, axis, c, d);
-        if (!sat_ranges(a, b, c, d, pen, flip)) return 0;
-        if (best_origin < 0 || pen < best_pen) {
-            best_origin = 0;
-            best_pen = pen;
-            best_n = flip ? -axis : axis;
+    for (int side = 0; side < 2; side++) {
+        const Dyn& bb = side == 0 ? b1 : b2;
+        int k = 0;
+        double bestd = -1.0;
+#pragma unroll 1
+        for (int q = 0; q < 3; q++) {
+            double dq = fabs(bb.R.a[q] * fromFirst.x + bb.R.a[3 + q] * fromFirst.y + bb.R.a[6 + q] * fromFirst.z);
+            if (dq > bestd) { bestd = dq; k = q; }
         }
-    }
-    // Face2: axes = normals of box 2, target = box 2 (boxes flipped, :233-234)
-#pragma unroll 1
-    for (int f = 0; f < 6; f++) {
-        d3 axis = o2.n[f];
-        double a, b, c, d, pen;
+        const int f = (k == 0) ? 4 : (k == 1 ? 2 : 1);  // the +e_k face (Box.fs:42-49)
+        const OBox& T = side == 0 ? o1 : o2;
+        const OBox& O = side == 0 ? o2 : o1;
+        double ta, tb, oc, od, pen;
         bool flip;
-        project_box(o2, axis, a, b);
-        project_box(o1, axis, c, d);
-        if (!sat_ranges(a, b, c, d, pen, flip)) return 0;
-        if (pen < best_pen) {
-            best_origin = 1;
-            best_pen = pen;
-            best_n = flip ? -axis : axis;
+        project_box(T, T.n[f], ta, tb);
+        project_box(O, T.n[f], oc, od);
+        if (!sat_ranges(ta, tb, oc, od, pen, flip)) return 0;
+    }
+
+    // Face1 then Face2 (SAT.fs:230-234).  Normals come in +- pairs (f, f+1) with n[f+1] == 0.0 - n[f] bit for
+    // bit, and a projection onto the negated axis is 0.0 - projection (see detect_sphere_box): one pass per pair.
+#pragma unroll 1
+    for (int origin = 0; origin < 2; origin++) {
+        const OBox& T = origin == 0 ? o1 : o2;  // Face2: boxes flipped
+        const OBox& O = origin == 0 ? o2 : o1;
+#pragma unroll 1
+        for (int fp = 0; fp < 6; fp += 2) {
+            d3 axis0 = T.n[fp];
+            double a0, b0, c0, d0;
+            project_box(T, axis0, a0, b0);
+            project_box(O, axis0, c0, d0);
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                double a = h ? 0.0 - b0 : a0, b = h ? 0.0 - a0 : b0;
+                double c = h ? 0.0 - d0 : c0, d = h ? 0.0 - c0 : d0;
+                double pen;
+                bool flip;
+                if (!sat_ranges(a, b, c, d, pen, flip)) return 0;
+                if (best_origin < 0 || pen < best_pen) {
+                    d3 axis = T.n[fp + h];
+                    best_origin = origin;
+                    best_pen = pen;
+                    best_n = flip ? -axis : axis;
+                }
+            }
         }
     }
     // Edge axes (:218-226): RigidBody.Axes = normalize(R e_k + 0) (RigidBody.fs:34-41)
@@ -330,13 +362,17 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
         ax1[k] = normalize(mk(b1.R.a[k], b1.R.a[3 + k], b1.R.a[6 + k]) + mk(0.0, 0.0, 0.0));
         ax2[k] = normalize(mk(b2.R.a[k], b2.R.a[3 + k], b2.R.a[6 + k]) + mk(0.0, 0.0, 0.0));
     }
-    d3 fromFirst = b2.x - b1.x;
 #pragma unroll 1
     for (int i = 0; i < 3; i++)
 #pragma unroll 1
         for (int j = 0; j < 3; j++) {
-            d3 e = normalize(cross(ax2[j], ax1[i]));  // firstAxis |> crossProduct secondAxis = second x first
-            if (near_eq(0.01, 0.0, norm(e))) continue;  // isZero 0.01
+            // normalized(second x first), dropped iff isZero 0.01 of the NORMALISED vector (:223-225): that norm is
+            // ~1 unless the cross product is exactly zero (then Normalize returns the zero vector), so the test is
+            // `norm(cross) == 0` (finite inputs)
+            d3 cr = cross(ax2[j], ax1[i]);
+            double cn = norm(cr);
+            if (cn == 0.0) continue;
+            d3 e = scale(1.0 / cn, cr);
             if (dot(e, fromFirst) < 0.0) e = -e;
             double a, b, c, d, pen;
             bool flip;

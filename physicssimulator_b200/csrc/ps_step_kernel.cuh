@@ -81,6 +81,7 @@ struct KArgs {
     StepParams sp;
     int exact_all_pairs;
     int restore_joints;
+    int margin_ncap;      // cap of the hit count that scales a body's motion margin
     // joints, grouped per world
     const int* joff;      // n_worlds+1 (nullptr when no joints)
     const int* ja;
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                         s.sx[b] = pr.x.x; s.sx[N + b] = pr.x.y; s.sx[2 * N + b] = pr.x.z;
                         double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
                         double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
-                        double n = (double)(s.nprev[b] < 6 ? s.nprev[b] : 6) + 2.0;
+                        double n = (double)(s.nprev[b] < a.margin_ncap ? s.nprev[b] : a.margin_ncap) + 2.0;
                         double m = p.is_static ? 0.0 : mscale * (0.01 + n * sp.dt * (speed + n * acc * sp.dt + 0.5));
                         if (!(m == m)) m = 0.0;  // NaN state: the world is flagged anyway
                         double rs, rb;

@@ -1,6 +1,8 @@
 """CPU check of the DEVICE physics routines: physicssimulator_b200/csrc/ps_physics.cuh compiled with g++
 (tests/host_harness) must reproduce the oracle bit for bit — states, colliding sets, contacts and feature ids.
 This runs without a GPU; the same comparison through the real kernels is tests/test_gpu_parity.py."""
+import math
+
 import numpy as np
 import pytest
 
@@ -65,3 +67,25 @@ def test_free_flight(integrator):
     o.step(500)
     st, _, _ = harness_step(b, nc, 500)
     assert_state_bits(o.get_state(), st, "free flight")
+
+
+def test_random_box_and_sphere_pairs_incl_axis_aligned():
+    """many small random worlds: axis-aligned boxes (exact ties, zero components), rotated boxes, spheres —
+    exercises the +-axis pairing, the early 'separated' exit and the zero-cross-product skip of the device SAT"""
+    rng = scenes.SplitMix64(2024)
+    for trial in range(120):
+        protos = [P.createDefaultBox(6, 6, 1).With(Mass=P.INFINITE, UseGravity=False, Position=(0, 0, -0.5),
+                                                   Yaw=(math.pi if trial % 3 == 0 else 0.0))]
+        for k in range(5):
+            aligned = (trial % 2 == 0)
+            ang = (lambda: 0.0) if aligned else (lambda: rng.uniform(-3.1, 3.1))
+            pos = (rng.uniform(-0.8, 0.8), rng.uniform(-0.8, 0.8), rng.uniform(0.3, 1.6))
+            if aligned:
+                pos = (round(pos[0] * 4) / 4, round(pos[1] * 4) / 4, round(pos[2] * 4) / 4)
+            if k == 4 and trial % 4 == 1:
+                protos.append(P.createDefaultSphere(rng.uniform(0.2, 0.5)).With(Position=pos, Mass=rng.uniform(1, 9)))
+            else:
+                protos.append(P.createDefaultBox(rng.uniform(0.3, 1.0), rng.uniform(0.3, 1.0), rng.uniform(0.3, 1.0)).With(
+                    Position=pos, Yaw=ang(), Pitch=ang(), Roll=ang(), Mass=rng.uniform(1, 50),
+                    Velocity=(rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-1, 1))))
+        _run(protos, Configuration(), [1, 3, 12], f"random trial {trial}")
