@@ -226,9 +226,10 @@ int upload(Batch* B, bool with_state)
     // lanes per world (tile): a wavefront level of a 128-body pile holds ~10 pairs, so 8 lanes per world and 4
     // worlds per warp keep the lanes busy; with few worlds wider tiles give the SMs more warps to overlap
     B->threads = 8;
+    if ((long long)B->n_worlds * 4 / 32 >= 148 * 12) B->threads = 4;
     if ((long long)B->n_worlds * 8 / 32 < 148 * 8) B->threads = 16;
     if ((long long)B->n_worlds * 16 / 32 < 148 * 8) B->threads = 32;
-    if (const char* e = getenv("PS_B200_TILE")) { int t = atoi(e); if (t == 8 || t == 16 || t == 32) B->threads = t; }  // tuning knob
+    if (const char* e = getenv("PS_B200_TILE")) { int t = atoi(e); if (t == 4 || t == 8 || t == 16 || t == 32) B->threads = t; }  // tuning knob
     B->smem = smem_bytes(B->max_n) * (size_t)(32 / B->threads);
     int dev_max = 0;
     CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, B->device));
@@ -241,6 +242,8 @@ int upload(Batch* B, bool with_state)
         CK(cudaFuncSetAttribute(step_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         CK(cudaFuncSetAttribute(step_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
+    CK(cudaFuncSetAttribute(step_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 12));
+    CK(cudaFuncSetAttribute(step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
     CK(cudaFuncSetAttribute(step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
     CK(cudaFuncSetAttribute(step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
     CK(cudaFuncSetAttribute(step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
@@ -487,7 +490,8 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
     a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.scratch = B->d_scratch; a.lvl = B->d_lvl; a.last = B->d_last;
     const int wpc = 32 / B->threads;  // worlds per one-warp CTA
     const int grid = (B->n_worlds + wpc - 1) / wpc;
-    if (B->threads == 8) step_kernel<8><<<grid, 32, B->smem, st>>>(a);
+    if (B->threads == 4) step_kernel<4><<<grid, 32, B->smem, st>>>(a);
+    else if (B->threads == 8) step_kernel<8><<<grid, 32, B->smem, st>>>(a);
     else if (B->threads == 16) step_kernel<16><<<grid, 32, B->smem, st>>>(a);
     else step_kernel<32><<<grid, 32, B->smem, st>>>(a);
     CK(cudaGetLastError());
