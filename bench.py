@@ -258,7 +258,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{name}: {WORKLOADS[name][3]}", "worlds_per_gpu": per_gpu, "dynamic_bodies_per_world": n_dyn,
-                       "settle_steps": args.settle, "launch": "1 step_kernel launch per step, block per world, state staged in SMEM",
+                       "settle_steps": args.settle, "launch": "1 step_kernel launch per step (one sub-warp tile per world, several worlds per warp)",
                        "l2": "256 MiB buffer written between timed iterations (outside the CUDA-event pairs)",
                        "parallelism": f"worlds sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": bytes_state, "d2h_bytes_per_step": bytes_state,
@@ -267,6 +267,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "psk::step_kernel", "algorithmic_bytes_per_body_step": B_ALG, "kernel_ms": kernel_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "traffic_note": "ncu dram bytes per launch of this workload (profiles/traffic.json); far above the algorithmic bytes: the per-pair routines spill their working arrays to the local-memory stack",
                          "note": "the per-world ordered contact solve is a dependent FP64 chain: the HBM roofline is the metric's denominator, not the kernel's limiter"},
             "cpu_baseline": cpu,
             "clocks": clocks,

@@ -235,14 +235,18 @@ int upload(Batch* B, bool with_state)
     CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, B->device));
     if ((long long)B->smem > dev_max)
         return fail(PS_ERR_INVALID_ARGUMENT, "largest world (%d bodies) needs %zu B of shared memory; device allows %d", B->max_n, B->smem, dev_max);
-    {   // the kernel needs little shared memory; give the rest of the unified array to L1 (local stack + scratch)
-        int pct = 12;
+    {   // the kernel needs little shared memory: reserve what PS_RESIDENT CTAs per SM need and leave the rest of the
+        // unified array to L1 (local stack of the per-pair routines)
+        int resident = 12;
+        if (const char* e = getenv("PS_B200_RESIDENT")) resident = std::max(1, atoi(e));
+        size_t need = (size_t)resident * (B->smem + 1024 + 256);
+        int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 1);
         if (const char* e = getenv("PS_B200_CARVEOUT")) pct = atoi(e);
+        CK(cudaFuncSetAttribute(step_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         CK(cudaFuncSetAttribute(step_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         CK(cudaFuncSetAttribute(step_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         CK(cudaFuncSetAttribute(step_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
-    CK(cudaFuncSetAttribute(step_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 12));
     CK(cudaFuncSetAttribute(step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
     CK(cudaFuncSetAttribute(step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
     CK(cudaFuncSetAttribute(step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
