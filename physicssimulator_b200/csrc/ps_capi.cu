@@ -15,6 +15,7 @@
 
 #include "../../include/ps_b200.h"
 #include "ps_step_kernel.cuh"
+#include "ps_wide.cuh"
 
 using namespace psk;
 
@@ -74,6 +75,16 @@ struct Batch {
     PairScratch* d_scratch = nullptr; // one record per launched thread
     int* d_lvl = nullptr;
     unsigned short* d_last = nullptr;
+    // batch-wide path (ps_wide.cuh)
+    bool wide = false;
+    int* d_body_world = nullptr;
+    unsigned char *d_pvalid = nullptr, *d_nhit = nullptr, *d_isstat = nullptr, *d_isbox = nullptr, *d_always_fused = nullptr;
+    int *d_K = nullptr, *d_maxl = nullptr;
+    unsigned *d_wflags = nullptr, *d_bucket = nullptr, *d_bucket_cur = nullptr, *d_hit_cnt = nullptr, *d_hitlist = nullptr, *d_cpool_cur = nullptr;
+    psw::Entry* d_entries = nullptr;
+    Contact* d_cpool = nullptr;
+    unsigned entries_cap = 0, cpool_cap = 0;
+    unsigned* h_bucket = nullptr;  // pinned
     int *d_joff = nullptr, *d_ja = nullptr, *d_jb = nullptr;
     double *d_jla = nullptr, *d_jlb = nullptr;
     unsigned char* d_jlast = nullptr;
@@ -189,6 +200,10 @@ void dfree(T*& p)
 void free_device(Batch* B)
 {
     dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_scratch); dfree(B->d_lvl); dfree(B->d_last);
+    dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
+    dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
+    dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool);
+    if (B->h_bucket) { cudaFreeHost(B->h_bucket); B->h_bucket = nullptr; }
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
 }
@@ -277,6 +292,40 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_scratch, std::max<size_t>(grid, 1) * 32 * sizeof(PairScratch)));
         CK(cudaMalloc(&B->d_lvl, (size_t)std::max(1, B->n_worlds) * (kMaxLevels + 2) * sizeof(int)));
         CK(cudaMalloc(&B->d_last, nb * sizeof(unsigned short)));
+    }
+    {   // batch-wide path: per-body flags, per-world tables, the (level, kind)-sorted pair list
+        std::vector<int> bw(nb, 0);
+        std::vector<unsigned char> isstat(nb, 0), isbox(nb, 0), af(std::max(1, B->n_worlds), 0);
+        for (int w = 0; w < B->n_worlds; w++) {
+            int ns = 0;
+            for (int g = h.off[w]; g < h.off[w + 1]; g++) {
+                bw[g] = w;
+                isbox[g] = h.shape[g] != 0;
+                if (std::isinf(h.mass[g])) { ns++; isstat[g] = (unsigned char)std::min(ns, kMaxStatics); }
+            }
+            af[w] = ns > kMaxStatics;
+        }
+        size_t nw = (size_t)std::max(1, B->n_worlds);
+        CK(cudaMalloc(&B->d_body_world, nb * sizeof(int)));
+        CK(cudaMalloc(&B->d_pvalid, nb)); CK(cudaMalloc(&B->d_nhit, nb)); CK(cudaMalloc(&B->d_isstat, nb)); CK(cudaMalloc(&B->d_isbox, nb));
+        CK(cudaMalloc(&B->d_always_fused, nw));
+        CK(cudaMalloc(&B->d_K, nw * sizeof(int))); CK(cudaMalloc(&B->d_maxl, nw * sizeof(int))); CK(cudaMalloc(&B->d_wflags, nw * sizeof(unsigned)));
+        CK(cudaMalloc(&B->d_bucket, (psw::kBuckets + 1) * sizeof(unsigned))); CK(cudaMalloc(&B->d_bucket_cur, psw::kBuckets * sizeof(unsigned)));
+        CK(cudaMalloc(&B->d_hit_cnt, (psw::kWideMaxLevels + 2) * sizeof(unsigned))); CK(cudaMalloc(&B->d_cpool_cur, (psw::kWideMaxLevels + 2) * sizeof(unsigned)));
+        B->entries_cap = (unsigned)std::min<size_t>(8 * nb + 1024, 400u << 20);
+        B->cpool_cap = (unsigned)std::min<size_t>(4 * nb + 4096, 200u << 20);
+        CK(cudaMalloc(&B->d_entries, (size_t)B->entries_cap * sizeof(psw::Entry)));
+        CK(cudaMalloc(&B->d_hitlist, (size_t)B->entries_cap * sizeof(unsigned)));
+        CK(cudaMalloc(&B->d_cpool, (size_t)B->cpool_cap * sizeof(Contact)));
+        CK(cudaMallocHost(&B->h_bucket, (psw::kBuckets + 1) * sizeof(unsigned)));
+        CK(cudaMemcpy(B->d_body_world, bw.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B->d_isstat, isstat.data(), nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B->d_isbox, isbox.data(), nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B->d_always_fused, af.data(), nw, cudaMemcpyHostToDevice));
+        // the wide path pays one pass through memory per stage and ~5 launches per level: it wins when the batch
+        // is large enough to fill the GPU per round
+        B->wide = !B->cfg.exact_all_pairs && !(B->cfg.restore_joints && !B->joints.a.empty()) && B->n_worlds >= 512;
+        if (const char* e = getenv("PS_B200_PATH")) { if (!strcmp(e, "fused")) B->wide = false; else if (!strcmp(e, "wide")) B->wide = !B->cfg.exact_all_pairs && !(B->cfg.restore_joints && !B->joints.a.empty()); }
     }
     CK(cudaMalloc(&B->d_hitcnt, nb));
     CK(cudaMemsetAsync(B->d_hitcnt, 0, nb, B->stream));
@@ -472,11 +521,8 @@ int ps_batch_destroy(void* handle)
     return PS_OK;
 }
 
-static int launch_step(Batch* B, int n_steps, cudaStream_t st)
+static void fill_kargs(Batch* B, KArgs& a, int n_steps)
 {
-    if (n_steps < 0) return fail(PS_ERR_INVALID_ARGUMENT, "n_steps must be >= 0");
-    if (n_steps == 0 || B->n_worlds == 0) return PS_OK;
-    KArgs a{};
     a.dyn = B->d_dyn; a.par = B->d_par; a.off = B->d_off; a.stats = B->d_stats;
     a.n_worlds = B->n_worlds; a.n_steps = n_steps;
     a.sp.eps = B->cfg.epsilon; a.sp.baumgarte = B->cfg.baumgarte; a.sp.slop = B->cfg.allowed_penetration;
@@ -492,14 +538,91 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
     a.max_n = B->max_n;
     a.hitcnt = B->d_hitcnt; a.cur = B->d_cur; a.pred = B->d_pred; a.S = B->d_S;
     a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.scratch = B->d_scratch; a.lvl = B->d_lvl; a.last = B->d_last;
+    a.only_flagged = nullptr;
+}
+
+static void launch_fused(Batch* B, const KArgs& a, cudaStream_t st)
+{
     const int wpc = 32 / B->threads;  // worlds per one-warp CTA
     const int grid = (B->n_worlds + wpc - 1) / wpc;
     if (B->threads == 4) step_kernel<4><<<grid, 32, B->smem, st>>>(a);
     else if (B->threads == 8) step_kernel<8><<<grid, 32, B->smem, st>>>(a);
     else if (B->threads == 16) step_kernel<16><<<grid, 32, B->smem, st>>>(a);
     else step_kernel<32><<<grid, 32, B->smem, st>>>(a);
-    CK(cudaGetLastError());
     B->launches++;
+}
+
+// one step of the batch-wide path (ps_wide.cuh)
+static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
+{
+    using namespace psw;
+    WArgs a{};
+    a.n_worlds = B->n_worlds; a.n_bodies = B->n_bodies; a.off = B->d_off; a.body_world = B->d_body_world;
+    a.dyn = B->d_dyn; a.cur = B->d_cur; a.pred = B->d_pred; a.par = B->d_par; a.S = B->d_S; a.cull = B->d_cull;
+    a.pvalid = B->d_pvalid; a.nhit = B->d_nhit; a.nprev = B->d_hitcnt; a.isstat = B->d_isstat; a.isbox = B->d_isbox;
+    a.last = B->d_last; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off;
+    a.K = B->d_K; a.maxl = B->d_maxl; a.wflags = B->d_wflags; a.always_fused = B->d_always_fused;
+    a.bucket = B->d_bucket; a.bucket_cur = B->d_bucket_cur; a.entries = B->d_entries; a.entries_cap = B->entries_cap;
+    a.hit_cnt = B->d_hit_cnt; a.hitlist = B->d_hitlist; a.cpool = B->d_cpool; a.cpool_cap = B->cpool_cap; a.cpool_cur = B->d_cpool_cur;
+    a.stats = B->d_stats;
+    a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
+    a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
+    a.sp = ka.sp; a.margin_ncap = ka.margin_ncap;
+    const int nb = B->n_bodies, nw = B->n_worlds;
+    const int gb = (nb + 127) / 128, gw = (nw + 63) / 64;
+    const int greset = (std::max(nw, kBuckets + 1) + 255) / 256;
+    wide_reset<<<greset, 256, 0, st>>>(a);
+    wide_predict<<<gb, 128, 0, st>>>(a);
+    wide_near_count<<<gb, 128, 0, st>>>(a);
+    wide_near_scan<<<gw, 64, 0, st>>>(a);
+    wide_near_fill<<<gb, 128, 0, st>>>(a);
+    wide_levels<<<gw, 64, 0, st>>>(a);
+    wide_bucket_scan<<<1, 1, 0, st>>>(a);
+    wide_scatter<<<gw, 64, 0, st>>>(a);
+    CK(cudaMemcpyAsync(B->h_bucket, B->d_bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    B->launches += 8;
+    const unsigned* hb = B->h_bucket;
+    for (int r = 1; r <= kWideMaxLevels; r++) {
+        unsigned first = hb[r * 4], total = hb[(r + 1) * 4] - first;
+        if (first >= hb[kBuckets]) break;  // no pair at this or any later level
+        if (total == 0) continue;
+        unsigned c0 = hb[r * 4 + 1] - hb[r * 4], c1 = hb[r * 4 + 2] - hb[r * 4 + 1], c2 = hb[r * 4 + 3] - hb[r * 4 + 2];
+        wide_integrate<<<(2 * total + 127) / 128, 128, 0, st>>>(a, first, total);
+        if (c0) wide_detect<0><<<(c0 + 127) / 128, 128, 0, st>>>(a, first, c0, first, r);
+        if (c1) wide_detect<1><<<(c1 + 127) / 128, 128, 0, st>>>(a, first + c0, c1, first, r);
+        if (c2) wide_detect<2><<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, c2, first, r);
+        wide_resolve<<<(total + 127) / 128, 128, 0, st>>>(a, first, r);
+        B->launches += 2 + (c0 != 0) + (c1 != 0) + (c2 != 0);
+    }
+    wide_static_fold<<<gb, 128, 0, st>>>(a);
+    wide_final<<<gb, 128, 0, st>>>(a);
+    wide_account<<<gw, 64, 0, st>>>(a);
+    B->launches += 3;
+    // worlds the wide pass gave up on: redo from the published state with the fused kernel
+    KArgs kf = ka;
+    kf.n_steps = 1;
+    kf.only_flagged = B->d_wflags;
+    launch_fused(B, kf, st);
+    CK(cudaGetLastError());
+    return PS_OK;
+}
+
+static int launch_step(Batch* B, int n_steps, cudaStream_t st)
+{
+    if (n_steps < 0) return fail(PS_ERR_INVALID_ARGUMENT, "n_steps must be >= 0");
+    if (n_steps == 0 || B->n_worlds == 0) return PS_OK;
+    KArgs a{};
+    fill_kargs(B, a, n_steps);
+    if (B->wide) {
+        for (int s = 0; s < n_steps; s++) {
+            int rc = launch_wide_step(B, a, st);
+            if (rc) return rc;
+        }
+        return PS_OK;
+    }
+    launch_fused(B, a, st);
+    CK(cudaGetLastError());
     return PS_OK;
 }
 

@@ -103,6 +103,9 @@ struct KArgs {
     unsigned char* lists;     // per world: n_pairs * 9 bytes (near u32 | level u16 | order u16 | hit u8)
     const long long* lists_off; // n_worlds+1 byte offsets (16-byte aligned)
     PairScratch* scratch;     // one record per launched thread
+    // when set: only worlds with a non-zero flag are stepped (the batch-wide path hands its failed worlds over);
+    // bit0 margin violated -> start at the 8x margin, bit1 static pose / too many statics -> exact serial walk
+    const unsigned* only_flagged;
 };
 
 // ---- per-world working set: pointers into global scratch + a small shared-memory block -------------
@@ -356,7 +359,8 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
     const int tile = threadIdx.x / T;
     const int tid = threadIdx.x % T;
     const int wraw = blockIdx.x * (32 / T) + tile;
-    const bool live = wraw < a.n_worlds;
+    const unsigned wflag = (wraw < a.n_worlds && a.only_flagged) ? a.only_flagged[wraw] : 0u;
+    const bool live = wraw < a.n_worlds && (!a.only_flagged || wflag != 0u);
     const int w = live ? wraw : 0;
     BlockShared& bs = bs_all[tile];
     const int off = a.off[w];
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
     for (int step = 0; step < a.n_steps; step++) {
         long long tk0 = clock64(), tk = tk0;
         // per tile: attempt 0 = margin x1, 1 = margin x8, 2 = exact serial walk over all pairs
-        int attempt = (a.exact_all_pairs || bs.nstat > kMaxStatics) ? 2 : 0;
+        int attempt = (a.exact_all_pairs || bs.nstat > kMaxStatics || (wflag & 2u)) ? 2 : ((wflag & 1u) ? 1 : 0);
         int fb_reason = 0;  // 1 margin, 2 levels, 3 static pose
         bool finished = !live;
         c.tested = c.hits = c.contacts = c.overflow = c.ref_exc = 0;
@@ -639,7 +643,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
             //  it goes round again with attempt == 2)
             __syncwarp();
         }
-        if (tid == 0 && live && fb_reason != 0 && !a.exact_all_pairs) {
+        if (tid == 0 && live && fb_reason != 0 && !a.exact_all_pairs && !a.only_flagged) {
             t_fallback++;
             if (fb_reason == 1) t_fbm++; else if (fb_reason == 2) t_fbc++; else t_fbs++;
         }

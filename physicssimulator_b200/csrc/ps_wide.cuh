@@ -1,0 +1,422 @@
+// ps_wide.cuh — the batch-wide ("breadth-first") form of the step: the same per-body and per-pair routines as
+// the fused per-world kernel (ps_step_kernel.cuh), but every stage is its own dense kernel over ALL worlds of the
+// batch, and the wavefront levels become rounds of the whole batch:
+//
+//   wide_predict      thread per body : predicted copy + cull sphere                                   (phase A)
+//   wide_near_count / wide_near_scan / wide_near_fill  : ordered near list per world                  (phase B)
+//   wide_levels       thread per world: level of every near pair, bucket = (level, pair kind)          (phase C)
+//   wide_bucket_scan, wide_scatter    : all near pairs of the batch sorted by (level, kind)
+//   per round r = 1..max level, over the pairs of that level in ALL worlds:
+//     wide_integrate    thread per (pair, side): re-integrate a body an earlier round changed
+//     wide_detect<kind> thread per pair, one launch per kind (sphere-sphere, sphere-box, box-box): narrow phase;
+//                       colliding pairs are appended to the round's hit list, contacts go to a pool
+//     wide_resolve      thread per colliding pair: N-iteration solve + write-back
+//   wide_static_fold  thread per static body : angular-momentum fold in pair order                    (phase E)
+//   wide_final        thread per body : final integration + publish                                   (phase F)
+//
+// Why: a pair is a long chain of dependent FP64 operations and a world offers ~10 independent pairs at a time, so
+// inside one CTA most lanes idle or diverge (ncu, fused kernel: 9 of 32 threads per instruction).  Across the
+// batch a round holds 10^5 pairs; sorted by kind, every warp runs 32 pairs of the same kind through the same code.
+// The price is one pass through L2/HBM per stage instead of registers — this is the part of the path where the
+// HBM roofline starts to mean something.
+//
+// Exactness is the fused kernel's: pairs of one level touch disjoint dynamic bodies (so a round may run them in
+// any order), the cull is conservative and verified on every re-integration.  A world that violates its margin,
+// whose static bodies do not sit at a fixed point of integrate(), or that overflows a table is flagged and redone
+// from the published state by the fused kernel (which owns the 8x-margin and exact-serial fallbacks).
+#pragma once
+#include "ps_step_kernel.cuh"
+
+namespace psw {
+using namespace psk;
+
+constexpr int kWideMaxLevels = 1022;
+constexpr int kBuckets = (kWideMaxLevels + 2) * 4;
+
+struct Entry {       // one near pair of the batch, sorted by (level, kind)
+    int w;           // world
+    unsigned ij;     // i | j<<16 (ids inside the world)
+    unsigned k;      // index in the world's near list (for the hit flag)
+    unsigned nc;     // contacts found by the narrow phase
+    unsigned cfirst; // first contact in the pool
+};
+
+struct WArgs {
+    int n_worlds, n_bodies;
+    const int* off;
+    const int* body_world;       // [NB]
+    double* dyn; double* cur; double* pred; const double* par; double* S; double* cull;
+    unsigned char* pvalid; unsigned char* nhit; unsigned char* nprev; const unsigned char* isstat; const unsigned char* isbox;  // [NB]
+    unsigned short* last;        // [NB]
+    int* row;                    // per world N+1 at off+w
+    unsigned char* lists; const long long* lists_off;
+    int* K; int* maxl;           // per world
+    unsigned* wflags;            // per world: != 0 -> redo with the fused kernel
+    const unsigned char* always_fused;  // per world
+    unsigned* bucket;            // [kBuckets+1] counts, then exclusive starts
+    unsigned* bucket_cur;        // [kBuckets]
+    Entry* entries; unsigned entries_cap;
+    unsigned* hit_cnt;           // per level
+    unsigned* hitlist;           // [entries_cap], a round uses [round start, ...)
+    Contact* cpool; unsigned cpool_cap; unsigned* cpool_cur;  // cursor per level
+    WorldStats* stats;
+    RecPair* rec_pairs; RecContact* rec_contacts; int* rec_counts; int rec_pair_cap, rec_contact_cap;
+    StepParams sp;
+    int margin_ncap;
+};
+
+enum { WF_MARGIN = 1, WF_STATIC = 2, WF_CAPACITY = 4 };
+
+PSD unsigned* w_near(const WArgs& a, int w) { return reinterpret_cast<unsigned*>(a.lists + a.lists_off[w]); }
+PSD size_t w_np(const WArgs& a, int w) { size_t N = (size_t)(a.off[w + 1] - a.off[w]); return N * (N > 0 ? N - 1 : 0) / 2; }
+PSD unsigned short* w_level(const WArgs& a, int w) { return reinterpret_cast<unsigned short*>(a.lists + a.lists_off[w] + 4 * w_np(a, w)); }
+PSD unsigned char* w_hit(const WArgs& a, int w) { return a.lists + a.lists_off[w] + 8 * w_np(a, w); }
+
+// ---- per step reset ------------------------------------------------------------------------------------
+__global__ void wide_reset(WArgs a)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= kBuckets) a.bucket[t] = 0;
+    if (t < kBuckets) a.bucket_cur[t] = 0;
+    if (t < kWideMaxLevels + 2) { a.hit_cnt[t] = 0; a.cpool_cur[t] = 0; }
+    if (t < a.n_worlds) {
+        a.wflags[t] = a.always_fused[t] ? WF_STATIC : 0u;
+        a.K[t] = 0; a.maxl[t] = 0;
+        a.stats[t].nan_flag = 0;
+        if (a.rec_counts) { a.rec_counts[2 * t] = 0; a.rec_counts[2 * t + 1] = 0; }
+    }
+}
+
+// ---- A: predicted copies + cull spheres (thread per body) -------------------------------------------------
+__global__ void __launch_bounds__(128) wide_predict(WArgs a)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n_bodies) return;
+    const int w = a.body_world[g], o = a.off[w], N = a.off[w + 1] - o, b = g - o;
+    Par p; Dyn cur, pr;
+    ld_par(a.par, 0, g, p);
+    ld_dyn(a.dyn, 0, g, cur);   // the published state is the step's input
+    st_dyn(a.cur, 0, g, cur);
+    integrate(cur, p, a.sp, pr);
+    st_dyn(a.pred, 0, g, pr);
+    a.pvalid[g] = 1; a.nhit[g] = 0; a.last[g] = 0;
+    if (p.is_static && !pose_fixed(cur, pr)) atomicOr(&a.wflags[w], (unsigned)WF_STATIC);
+    double* cu = a.cull + (size_t)o * 6;
+    cu[b] = pr.x.x; cu[N + b] = pr.x.y; cu[2 * N + b] = pr.x.z;
+    double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
+    double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
+    int np_ = a.nprev[g];
+    double n = (double)(np_ < a.margin_ncap ? np_ : a.margin_ncap) + 2.0;
+    double m = p.is_static ? 0.0 : (0.01 + n * a.sp.dt * (speed + n * acc * a.sp.dt + 0.5));
+    if (!(m == m)) m = 0.0;
+    double rs, rb;
+    if (p.shape == 0) { rs = p.dims[0]; rb = 1.7320508075688774 * p.dims[0]; }
+    else { double hx = 0.5 * p.dims[0], hy = 0.5 * p.dims[1], hz = 0.5 * p.dims[2]; rs = rb = sqrt(hx * hx + hy * hy + hz * hz); }
+    const double slack = 1.0 + 1e-6;
+    cu[3 * N + b] = rs * slack + 1e-9 + m;
+    cu[4 * N + b] = rb * slack + 1e-9 + m;
+    cu[5 * N + b] = m * m;
+}
+
+// ---- B: near list ---------------------------------------------------------------------------------------
+PSD bool wide_near_test(const WArgs& a, const double* cu, int o, int N, int i, int j)
+{
+    if (a.isstat[o + i] && a.isstat[o + j]) return false;
+    double dx = cu[i] - cu[j], dy = cu[N + i] - cu[N + j], dz = cu[2 * N + i] - cu[2 * N + j];
+    double dd = dx * dx + dy * dy + dz * dz;
+    double ri = a.isbox[o + j] ? cu[4 * N + i] : cu[3 * N + i];
+    double rj = a.isbox[o + i] ? cu[4 * N + j] : cu[3 * N + j];
+    double r = ri + rj;
+    return !(dd > r * r);
+}
+__global__ void __launch_bounds__(128) wide_near_count(WArgs a)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n_bodies) return;
+    const int w = a.body_world[g], o = a.off[w], N = a.off[w + 1] - o, i = g - o;
+    const double* cu = a.cull + (size_t)o * 6;
+    int cn = 0;
+    for (int j = i + 1; j < N; j++) cn += wide_near_test(a, cu, o, N, i, j) ? 1 : 0;
+    a.row[o + w + i] = cn;
+}
+__global__ void wide_near_scan(WArgs a)  // thread per world
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.n_worlds) return;
+    const int o = a.off[w], N = a.off[w + 1] - o;
+    int* row = a.row + o + w;
+    int acc = 0;
+    for (int i = 0; i < N; i++) { int t = row[i]; row[i] = acc; acc += t; }
+    row[N] = acc;
+    a.K[w] = acc;
+}
+__global__ void __launch_bounds__(128) wide_near_fill(WArgs a)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n_bodies) return;
+    const int w = a.body_world[g], o = a.off[w], N = a.off[w + 1] - o, i = g - o;
+    const double* cu = a.cull + (size_t)o * 6;
+    unsigned* near = w_near(a, w);
+    unsigned char* hit = w_hit(a, w);
+    int q = a.row[o + w + i];
+    for (int j = i + 1; j < N; j++)
+        if (wide_near_test(a, cu, o, N, i, j)) {
+            near[q] = (unsigned)i | ((unsigned)j << 16);
+            hit[q] = 0;
+            q++;
+        }
+}
+
+// ---- C: levels + buckets (thread per world) ----------------------------------------------------------------
+PSD int pair_kind(const WArgs& a, int o, int i, int j)  // 0 sphere-sphere, 1 sphere/box mixed, 2 box-box
+{
+    return (int)a.isbox[o + i] + (int)a.isbox[o + j];
+}
+__global__ void wide_levels(WArgs a)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.n_worlds) return;
+    if (a.wflags[w]) return;  // already condemned to the fused kernel
+    const int o = a.off[w], K = a.K[w];
+    const unsigned* near = w_near(a, w);
+    unsigned short* level = w_level(a, w);
+    int maxl = 0;
+    for (int k = 0; k < K; k++) {
+        unsigned ij = near[k];
+        int i = ij & 0xffff, j = ij >> 16;
+        int li = a.isstat[o + i] ? 0 : a.last[o + i];
+        int lj = a.isstat[o + j] ? 0 : a.last[o + j];
+        int l = (li > lj ? li : lj) + 1;
+        level[k] = (unsigned short)l;
+        if (!a.isstat[o + i]) a.last[o + i] = (unsigned short)l;
+        if (!a.isstat[o + j]) a.last[o + j] = (unsigned short)l;
+        if (l > maxl) maxl = l;
+    }
+    if (maxl > kWideMaxLevels) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); return; }
+    a.maxl[w] = maxl;
+    for (int k = 0; k < K; k++) {
+        unsigned ij = near[k];
+        atomicAdd(&a.bucket[level[k] * 4 + pair_kind(a, o, ij & 0xffff, ij >> 16)], 1u);
+    }
+}
+__global__ void wide_bucket_scan(WArgs a)  // one thread: kBuckets is ~4 K
+{
+    unsigned acc = 0;
+    for (int b = 0; b < kBuckets; b++) { unsigned t = a.bucket[b]; a.bucket[b] = acc; acc += t; }
+    a.bucket[kBuckets] = acc;
+}
+__global__ void wide_scatter(WArgs a)  // thread per world
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.n_worlds) return;
+    if (a.wflags[w]) return;
+    if (a.bucket[kBuckets] > a.entries_cap) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); return; }
+    const int o = a.off[w], K = a.K[w];
+    const unsigned* near = w_near(a, w);
+    const unsigned short* level = w_level(a, w);
+    for (int k = 0; k < K; k++) {
+        unsigned ij = near[k];
+        int b = level[k] * 4 + pair_kind(a, o, ij & 0xffff, ij >> 16);
+        unsigned pos = a.bucket[b] + atomicAdd(&a.bucket_cur[b], 1u);
+        Entry e; e.w = w; e.ij = ij; e.k = (unsigned)k; e.nc = 0; e.cfirst = 0;
+        a.entries[pos] = e;
+    }
+}
+
+// ---- rounds ---------------------------------------------------------------------------------------------
+// re-integrate the bodies of this round's pairs that an earlier round changed: thread per (entry, side)
+__global__ void __launch_bounds__(128) wide_integrate(WArgs a, unsigned first, unsigned count)
+{
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * count) return;
+    const Entry& e = a.entries[first + (t >> 1)];
+    if (a.wflags[e.w]) return;
+    const int o = a.off[e.w], N = a.off[e.w + 1] - o;
+    const int b = (t & 1) ? (int)(e.ij >> 16) : (int)(e.ij & 0xffff);
+    const int g = o + b;
+    if (a.pvalid[g]) return;  // static bodies stay valid for the whole step
+    Par p; Dyn cur, pr;
+    ld_par(a.par, 0, g, p);
+    ld_dyn(a.cur, 0, g, cur);
+    integrate(cur, p, a.sp, pr);
+    st_dyn(a.pred, 0, g, pr);
+    a.pvalid[g] = 1;
+    const double* cu = a.cull + (size_t)o * 6;
+    d3 d = pr.x - mk(cu[b], cu[N + b], cu[2 * N + b]);
+    double dd = d.x * d.x + d.y * d.y + d.z * d.z;
+    if (!(dd <= cu[5 * N + b])) atomicOr(&a.wflags[e.w], (unsigned)WF_MARGIN);
+}
+
+// narrow phase of one kind: thread per entry of bucket (level, kind)
+template <int KIND>
+__global__ void __launch_bounds__(128) wide_detect(WArgs a, unsigned first, unsigned count, unsigned round_first, int level)
+{
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    Entry& e = a.entries[first + t];
+    const int w = e.w;
+    if (a.wflags[w]) return;
+    const int o = a.off[w];
+    const int i = e.ij & 0xffff, j = e.ij >> 16;
+    Par pi, pj; Dyn di, dj;
+    ld_par(a.par, 0, o + i, pi);
+    ld_par(a.par, 0, o + j, pj);
+    ld_dyn(a.pred, 0, o + i, di);
+    ld_dyn(a.pred, 0, o + j, dj);
+    PairScratch sc;
+    int err = 0, ovf = 0, nc;
+    if (KIND == 0) {
+        nc = detect_ss(di, pi, dj, pj, sc.cs);
+    } else if (KIND == 2) {
+        nc = detect_bb(di, pi, dj, pj, a.sp.eps, sc.cs, err, ovf, sc);
+    } else {
+        nc = detect(di, pi, dj, pj, a.sp.eps, sc.cs, err, ovf, sc);
+    }
+    WorldStats& st = a.stats[w];
+    atomicAdd(&st.tested, 1ull);
+    if (err) atomicAdd(&st.ref_exc, 1ull);
+    if (ovf) atomicAdd(&st.overflow, 1ull);
+    if (nc <= 0) return;
+    unsigned cf = atomicAdd(&a.cpool_cur[level], (unsigned)nc);
+    if (cf + (unsigned)nc > a.cpool_cap) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); return; }
+    for (int k = 0; k < nc; k++) a.cpool[cf + k] = sc.cs[k];
+    e.nc = (unsigned)nc; e.cfirst = cf;
+    unsigned slot = atomicAdd(&a.hit_cnt[level], 1u);
+    a.hitlist[round_first + slot] = first + t;
+    atomicAdd(&st.hits, 1ull);
+    atomicAdd(&st.contacts, (unsigned long long)nc);
+    double mp = 0.0;
+    for (int k = 0; k < nc; k++) mp = fmax(mp, fabs(sc.cs[k].pen));
+    atomicMax((unsigned long long*)&st.max_pen, (unsigned long long)__double_as_longlong(mp));
+    if (a.rec_pairs) {
+        int* cnt = a.rec_counts + 2 * w;
+        int slot2 = atomicAdd(&cnt[0], 1);
+        int f2 = atomicAdd(&cnt[1], nc);
+        if (slot2 < a.rec_pair_cap && f2 + nc <= a.rec_contact_cap) {
+            RecPair rp; rp.i = i; rp.j = j; rp.first = f2; rp.count = nc;
+            a.rec_pairs[(size_t)w * a.rec_pair_cap + slot2] = rp;
+            RecContact* out = a.rec_contacts + (size_t)w * a.rec_contact_cap + f2;
+            for (int k = 0; k < nc; k++) {
+                RecContact r;
+                r.n[0] = sc.cs[k].n.x; r.n[1] = sc.cs[k].n.y; r.n[2] = sc.cs[k].n.z;
+                r.p[0] = sc.cs[k].p.x; r.p[1] = sc.cs[k].p.y; r.p[2] = sc.cs[k].p.z;
+                r.pen = sc.cs[k].pen; r.feat = sc.cs[k].feat; r.pad = 0;
+                out[k] = r;
+            }
+        }
+    }
+}
+
+// solve + write-back: thread per colliding pair of the round
+__global__ void __launch_bounds__(128) wide_resolve(WArgs a, unsigned round_first, int level)
+{
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.hit_cnt[level]) return;
+    const Entry& e = a.entries[a.hitlist[round_first + t]];
+    const int w = e.w;
+    if (a.wflags[w]) return;
+    const int o = a.off[w], N = a.off[w + 1] - o;
+    const int i = e.ij & 0xffff, j = e.ij >> 16;
+    Par pi, pj; Dyn di, dj;
+    ld_par(a.par, 0, o + i, pi);
+    ld_par(a.par, 0, o + j, pj);
+    ld_dyn(a.pred, 0, o + i, di);
+    ld_dyn(a.pred, 0, o + j, dj);
+    const int nc = (int)e.nc;
+    Contact cs[PS_MAX_CONTACTS];
+    CPData cp[PS_MAX_CONTACTS];
+    for (int k = 0; k < nc; k++) cs[k] = a.cpool[e.cfirst + k];
+    const bool si = pi.is_static, sj = pj.is_static;
+    if (si) di.L = mk(0.0, 0.0, 0.0);
+    if (sj) dj.L = mk(0.0, 0.0, 0.0);
+    resolve(di, pi, dj, pj, cs, nc, cp, a.sp);
+    w_hit(a, w)[e.k] = 1;
+    double* Sw = a.S + (size_t)o * 3 * kMaxStatics;
+    if (si) {
+        double* S = Sw + 3 * ((a.isstat[o + i] - 1) * N + j);
+        S[0] = di.L.x; S[1] = di.L.y; S[2] = di.L.z;
+    } else {
+        st_dyn(a.cur, 0, o + i, di);
+        a.pvalid[o + i] = 0;
+        bump(&a.nhit[o + i]);
+    }
+    if (sj) {
+        double* S = Sw + 3 * ((a.isstat[o + j] - 1) * N + i);
+        S[0] = dj.L.x; S[1] = dj.L.y; S[2] = dj.L.z;
+    } else {
+        st_dyn(a.cur, 0, o + j, dj);
+        a.pvalid[o + j] = 0;
+        bump(&a.nhit[o + j]);
+    }
+}
+
+// ---- E: static bodies: L = fold over their colliding pairs in pair order (thread per body, statics only) -----
+__global__ void __launch_bounds__(128) wide_static_fold(WArgs a)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n_bodies) return;
+    if (!a.isstat[g]) return;
+    const int w = a.body_world[g];
+    if (a.wflags[w]) return;
+    const int o = a.off[w], N = a.off[w + 1] - o, b = g - o, K = a.K[w];
+    Par p; ld_par(a.par, 0, g, p);
+    double* cb = a.cur + (size_t)g * kDynF;
+    double* pb = a.pred + (size_t)g * kDynF;
+    d3 L = mk(cb[15], cb[16], cb[17]);
+    d3 dL = scale(a.sp.dt, p.T);
+    const double* Sb = a.S + (size_t)o * 3 * kMaxStatics + 3 * (a.isstat[g] - 1) * N;
+    const unsigned* near = w_near(a, w);
+    const unsigned char* hit = w_hit(a, w);
+    for (int k = 0; k < K; k++) {
+        if (!hit[k]) continue;
+        unsigned ij = near[k];
+        int i = ij & 0xffff, j = ij >> 16;
+        int other;
+        if (i == b) other = j; else if (j == b) other = i; else continue;
+        L = L + dL;
+        L = L + mk(Sb[3 * other], Sb[3 * other + 1], Sb[3 * other + 2]);
+    }
+    cb[15] = L.x; cb[16] = L.y; cb[17] = L.z;
+    d3 Lf = L + dL;
+    pb[15] = Lf.x; pb[16] = Lf.y; pb[17] = Lf.z;
+}
+
+// ---- F: final integration + publish (thread per body) ---------------------------------------------------------
+__global__ void __launch_bounds__(128) wide_final(WArgs a)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n_bodies) return;
+    const int w = a.body_world[g];
+    if (a.wflags[w]) return;  // the fused kernel redoes this world from the published state
+    Dyn out;
+    if (a.pvalid[g]) {
+        ld_dyn(a.pred, 0, g, out);
+    } else {
+        Par p; ld_par(a.par, 0, g, p);
+        Dyn cur; ld_dyn(a.cur, 0, g, cur);
+        integrate(cur, p, a.sp, out);
+    }
+    st_dyn(a.dyn, 0, g, out);
+    a.nprev[g] = a.nhit[g];
+    bool bad = !(isfinite(out.x.x) && isfinite(out.x.y) && isfinite(out.x.z) && isfinite(out.v.x) && isfinite(out.v.y) && isfinite(out.v.z) &&
+                 isfinite(out.L.x) && isfinite(out.L.y) && isfinite(out.L.z));
+    for (int k = 0; k < 9; k++) bad = bad || !isfinite(out.R.a[k]);
+    if (bad) a.stats[w].nan_flag = 1;
+    if (g == a.off[w]) atomicAdd(&a.stats[w].steps, 1ull);
+}
+
+// account the worlds handed over to the fused kernel (thread per world)
+__global__ void wide_account(WArgs a)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.n_worlds) return;
+    unsigned f = a.wflags[w];
+    if (!f || a.always_fused[w]) return;
+    WorldStats& st = a.stats[w];
+    st.fallback++;
+    if (f & WF_STATIC) st.fb_static++;
+    else if (f & WF_MARGIN) st.fb_margin++;
+    else st.fb_capacity++;
+}
+
+}  // namespace psw
