@@ -85,6 +85,10 @@ struct Batch {
     Contact* d_cpool = nullptr;
     unsigned entries_cap = 0, cpool_cap = 0;
     unsigned* h_bucket = nullptr;  // pinned
+    unsigned* d_tmp = nullptr;
+    unsigned long long* d_tmp_pen = nullptr;
+    double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // PS_B200_WIDE_PROF: setup, integrate, ss, sb, bb, resolve, tail, fused
+    long long prof_steps = 0, prof_rounds = 0;
     int *d_joff = nullptr, *d_ja = nullptr, *d_jb = nullptr;
     double *d_jla = nullptr, *d_jlb = nullptr;
     unsigned char* d_jlast = nullptr;
@@ -202,7 +206,7 @@ void free_device(Batch* B)
     dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_scratch); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
-    dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool);
+    dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen);
     if (B->h_bucket) { cudaFreeHost(B->h_bucket); B->h_bucket = nullptr; }
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
@@ -311,13 +315,15 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_always_fused, nw));
         CK(cudaMalloc(&B->d_K, nw * sizeof(int))); CK(cudaMalloc(&B->d_maxl, nw * sizeof(int))); CK(cudaMalloc(&B->d_wflags, nw * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_bucket, (psw::kBuckets + 1) * sizeof(unsigned))); CK(cudaMalloc(&B->d_bucket_cur, psw::kBuckets * sizeof(unsigned)));
-        CK(cudaMalloc(&B->d_hit_cnt, (psw::kWideMaxLevels + 2) * sizeof(unsigned))); CK(cudaMalloc(&B->d_cpool_cur, (psw::kWideMaxLevels + 2) * sizeof(unsigned)));
-        B->entries_cap = (unsigned)std::min<size_t>(8 * nb + 1024, 400u << 20);
+        CK(cudaMalloc(&B->d_hit_cnt, psw::kBuckets * sizeof(unsigned))); CK(cudaMalloc(&B->d_cpool_cur, (psw::kWideMaxLevels + 2) * sizeof(unsigned)));
+        B->entries_cap = (unsigned)std::min<size_t>(16 * nb + 1024, 400u << 20);
         B->cpool_cap = (unsigned)std::min<size_t>(4 * nb + 4096, 200u << 20);
         CK(cudaMalloc(&B->d_entries, (size_t)B->entries_cap * sizeof(psw::Entry)));
         CK(cudaMalloc(&B->d_hitlist, (size_t)B->entries_cap * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_cpool, (size_t)B->cpool_cap * sizeof(Contact)));
         CK(cudaMallocHost(&B->h_bucket, (psw::kBuckets + 1) * sizeof(unsigned)));
+        CK(cudaMalloc(&B->d_tmp, nw * 6 * sizeof(unsigned)));
+        CK(cudaMalloc(&B->d_tmp_pen, nw * sizeof(unsigned long long)));
         CK(cudaMemcpy(B->d_body_world, bw.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B->d_isstat, isstat.data(), nb, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B->d_isbox, isbox.data(), nb, cudaMemcpyHostToDevice));
@@ -515,6 +521,10 @@ int ps_batch_destroy(void* handle)
     Batch* B = (Batch*)handle;
     cudaSetDevice(B->device);
     cudaStreamSynchronize(B->stream);
+    if (getenv("PS_B200_WIDE_PROF") && B->prof_steps > 0)
+        fprintf(stderr, "[ps_b200 wide profile] steps %lld rounds/step %.1f | ms/step: setup %.3f resolve_sphere %.3f detect_ss %.3f detect_sb %.3f detect_bb %.3f resolve_bb %.3f tail %.3f fused %.3f\n",
+                B->prof_steps, (double)B->prof_rounds / B->prof_steps, B->prof_ms[0] / B->prof_steps, B->prof_ms[1] / B->prof_steps, B->prof_ms[2] / B->prof_steps,
+                B->prof_ms[3] / B->prof_steps, B->prof_ms[4] / B->prof_steps, B->prof_ms[5] / B->prof_steps, B->prof_ms[6] / B->prof_steps, B->prof_ms[7] / B->prof_steps);
     free_device(B);
     cudaStreamDestroy(B->stream);
     delete B;
@@ -564,12 +574,24 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     a.K = B->d_K; a.maxl = B->d_maxl; a.wflags = B->d_wflags; a.always_fused = B->d_always_fused;
     a.bucket = B->d_bucket; a.bucket_cur = B->d_bucket_cur; a.entries = B->d_entries; a.entries_cap = B->entries_cap;
     a.hit_cnt = B->d_hit_cnt; a.hitlist = B->d_hitlist; a.cpool = B->d_cpool; a.cpool_cap = B->cpool_cap; a.cpool_cur = B->d_cpool_cur;
-    a.stats = B->d_stats;
+    a.stats = B->d_stats; a.tmp = B->d_tmp; a.tmp_pen = B->d_tmp_pen;
     a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
     a.sp = ka.sp; a.margin_ncap = ka.margin_ncap;
+    a.margin_scale = 2.0;
+    if (const char* e = getenv("PS_B200_MSCALE")) a.margin_scale = atof(e);  // tuning knob
     const int nb = B->n_bodies, nw = B->n_worlds;
     const int gb = (nb + 127) / 128, gw = (nw + 63) / 64;
+    const bool prof = getenv("PS_B200_WIDE_PROF") != nullptr;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
+    auto lap = [&](int cat) {  // profiling only: serialises the stream
+        if (!prof) return;
+        cudaEventRecord(pe1, st); cudaEventSynchronize(pe1);
+        float ms = 0.f; cudaEventElapsedTime(&ms, pe0, pe1);
+        B->prof_ms[cat] += ms;
+        cudaEventRecord(pe0, st);
+    };
     const int greset = (std::max(nw, kBuckets + 1) + 255) / 256;
     wide_reset<<<greset, 256, 0, st>>>(a);
     wide_predict<<<gb, 128, 0, st>>>(a);
@@ -582,28 +604,41 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     CK(cudaMemcpyAsync(B->h_bucket, B->d_bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     B->launches += 8;
+    lap(0);
     const unsigned* hb = B->h_bucket;
-    for (int r = 1; r <= kWideMaxLevels; r++) {
+    const bool overflow = hb[kBuckets] > B->entries_cap;  // wide_scatter flagged every world: the fused kernel takes the step
+    for (int r = 1; r <= kWideMaxLevels && !overflow; r++) {
         unsigned first = hb[r * 4], total = hb[(r + 1) * 4] - first;
         if (first >= hb[kBuckets]) break;  // no pair at this or any later level
         if (total == 0) continue;
         unsigned c0 = hb[r * 4 + 1] - hb[r * 4], c1 = hb[r * 4 + 2] - hb[r * 4 + 1], c2 = hb[r * 4 + 3] - hb[r * 4 + 2];
-        wide_integrate<<<(2 * total + 127) / 128, 128, 0, st>>>(a, first, total);
-        if (c0) wide_detect<0><<<(c0 + 127) / 128, 128, 0, st>>>(a, first, c0, first, r);
-        if (c1) wide_detect<1><<<(c1 + 127) / 128, 128, 0, st>>>(a, first + c0, c1, first, r);
-        if (c2) wide_detect<2><<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, c2, first, r);
-        wide_resolve<<<(total + 127) / 128, 128, 0, st>>>(a, first, r);
-        B->launches += 2 + (c0 != 0) + (c1 != 0) + (c2 != 0);
+        if (c0) wide_detect<0><<<(c0 + 127) / 128, 128, 0, st>>>(a, first, c0, r);
+        lap(2);
+        if (c1) wide_detect<1><<<(c1 + 127) / 128, 128, 0, st>>>(a, first + c0, c1, r);
+        lap(3);
+        if (c2) wide_detect<2><<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, c2, r);
+        lap(4);
+        if (c0) wide_resolve<0><<<(c0 + 127) / 128, 128, 0, st>>>(a, first, r);
+        if (c1) wide_resolve<1><<<(c1 + 127) / 128, 128, 0, st>>>(a, first + c0, r);
+        lap(1);
+        if (c2) wide_resolve<2><<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, r);
+        lap(5);
+        B->prof_rounds++;
+        B->launches += 2 * ((c0 != 0) + (c1 != 0) + (c2 != 0));
     }
     wide_static_fold<<<gb, 128, 0, st>>>(a);
     wide_final<<<gb, 128, 0, st>>>(a);
     wide_account<<<gw, 64, 0, st>>>(a);
     B->launches += 3;
+    lap(6);
     // worlds the wide pass gave up on: redo from the published state with the fused kernel
     KArgs kf = ka;
     kf.n_steps = 1;
     kf.only_flagged = B->d_wflags;
     launch_fused(B, kf, st);
+    lap(7);
+    B->prof_steps++;
+    if (prof) { cudaEventDestroy(pe0); cudaEventDestroy(pe1); }
     CK(cudaGetLastError());
     return PS_OK;
 }

@@ -95,29 +95,38 @@ PSN void integrate(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o)
 // ----------------------------------------------------------------------------------------
 // Oriented box in world space (OrientedBox.fs:10-27 over Box.fs:100-111)
 // ----------------------------------------------------------------------------------------
+// The 8 world vertices are never stored: vertex k = R*(+-hx,+-hy,+-hz) + x evaluated as MathNet does,
+//   v_i = (((0.0 + R_i0*lx) + R_i1*ly) + R_i2*lz) + x_i ,   R_i0*(+-hx) = +-(R_i0*hx) exactly,
+// so the box keeps the nine products A = R col0 * hx, B = R col1 * hy, C = R col2 * hz and the centre, and a
+// vertex costs four additions per component.  (The stored form was 2 x 336 B of local memory per box-box test and
+// every projection re-read all of it.)
 struct OBox {
-    d3 v[8];  // world vertices, Box.fs:23-32 index
-    d3 n[6];  // world face normals
+    d3 A, B, C, x;
+    d3 n[6];  // world face normals (Box.fs:42-49 order)
 };
 PSN void make_obox(const Dyn& b, const Par& p, OBox& ob)
 {
     double hx = p.dims[0] / 2.0, hy = p.dims[1] / 2.0, hz = p.dims[2] / 2.0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        unsigned s = kVertSign[k];
-        // PointwiseMultiply of (+-1,+-1,+-1) by the half sizes: exact
-        d3 local = mk((s & 4) ? hx : -hx, (s & 2) ? hy : -hy, (s & 1) ? hz : -hz);
-        ob.v[k] = mulMV(b.R, local) + b.x;  // toWorldCoordinates (GraphicsUtils.fs:109-110)
-    }
+    ob.A = mk(b.R.a[0] * hx, b.R.a[3] * hx, b.R.a[6] * hx);
+    ob.B = mk(b.R.a[1] * hy, b.R.a[4] * hy, b.R.a[7] * hy);
+    ob.C = mk(b.R.a[2] * hz, b.R.a[5] * hz, b.R.a[8] * hz);
+    ob.x = b.x;
 #pragma unroll
     for (int f = 0; f < 6; f++) {
         int ax = kFaceAxis[f];
         double sg = (double)kFaceSign[f];
         d3 local = mk(ax == 0 ? sg : 0.0, ax == 1 ? sg : 0.0, ax == 2 ? sg : 0.0);
-        ob.n[f] = mulMV(b.R, local) + mk(0.0, 0.0, 0.0);
+        ob.n[f] = mulMV(b.R, local) + mk(0.0, 0.0, 0.0);  // toWorldCoordinates orientation zero (OrientedBox.fs:18-21)
     }
 }
-PSD d3 face_vertex(const OBox& ob, int f, int k) { return ob.v[kFaceVert[f][k]]; }
+// world vertex k of Box.fs:23-32 (PointwiseMultiply by the half sizes, then toWorldCoordinates)
+PSD d3 box_vertex(const OBox& ob, int k)
+{
+    unsigned s = kVertSign[k];
+    d3 a = (s & 4) ? ob.A : -ob.A, b = (s & 2) ? ob.B : -ob.B, c = (s & 1) ? ob.C : -ob.C;
+    return mk((((0.0 + a.x) + b.x) + c.x) + ob.x.x, (((0.0 + a.y) + b.y) + c.y) + ob.x.y, (((0.0 + a.z) + b.z) + c.z) + ob.x.z);
+}
+PSD d3 face_vertex(const OBox& ob, int f, int k) { return box_vertex(ob, kFaceVert[f][k]); }
 
 struct PolyV {
     d3 p;
@@ -134,18 +143,33 @@ struct PairScratch {
     PolyV bufA[PS_MAX_CONTACTS + 4], bufB[PS_MAX_CONTACTS + 4];
 };
 
-// min/max of the 8 vertex projections in OrientedBox.Vertices order (ties keep the first, values only)
+// min/max of the 8 vertex projections (OrientedBox.Vertices order is irrelevant: only the two values are used).
+// The partial sums of the vertex formula are shared down the sign tree: 2 + 4 + 8 additions per component.
 PSN void project_box(const OBox& ob, d3 axis, double& mn, double& mx)
 {
-    double p0 = dot(axis, ob.v[0]);
-    mn = p0;
-    mx = p0;
+    const d3 A = ob.A, B = ob.B, C = ob.C, x = ob.x;
+    bool first = true;
+    double lo = 0.0, hi = 0.0;
 #pragma unroll
-    for (int k = 1; k < 8; k++) {
-        double p = dot(axis, ob.v[kDistinctVert[k]]);
-        if (p < mn) mn = p;
-        if (p > mx) mx = p;
+    for (int sa = 0; sa < 2; sa++) {
+        d3 p0 = sa ? mk(0.0 + A.x, 0.0 + A.y, 0.0 + A.z) : mk(0.0 + -A.x, 0.0 + -A.y, 0.0 + -A.z);
+#pragma unroll
+        for (int sb = 0; sb < 2; sb++) {
+            d3 p1 = sb ? p0 + B : p0 + (-B);
+#pragma unroll
+            for (int sc = 0; sc < 2; sc++) {
+                d3 v = (sc ? p1 + C : p1 + (-C)) + x;
+                double p = dot(axis, v);
+                if (first) { lo = p; hi = p; first = false; }
+                else {
+                    if (p < lo) lo = p;
+                    if (p > hi) hi = p;
+                }
+            }
+        }
     }
+    mn = lo;
+    mx = hi;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -608,9 +632,12 @@ PSD void apply_impulse(Dyn& b, const Par& p, d3 off, d3 P)
 PSD d3 velocity_at(const Dyn& b, const m33& Iw, d3 off) { return b.v + cross(mulMV(Iw, b.L), off); }
 
 // resolves one pair in place; b1/b2 are the predicted bodies
-PSN void resolve(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* cs, int nc, CPData* cp,
-                 const StepParams& sp)
+// FIX = 0: nc contacts at run time; FIX = 1: exactly one contact (every sphere pair), arrays collapse to registers
+template <int FIX>
+PSD void resolve_t(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* cs, int nc_in, CPData* cp,
+                   const StepParams& sp)
 {
+    const int nc = FIX ? FIX : nc_in;
     // orientation is constant during the solve, so R Ip^-1 R^T is evaluated once per body (exact)
     m33 Iw1 = inertia_inv_world(b1.R, p1.iinv);
     m33 Iw2 = inertia_inv_world(b2.R, p2.iinv);
@@ -677,6 +704,12 @@ PSN void resolve(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* 
             cp[k].accT1 = d.accT1;
         }
     }
+}
+
+PSN void resolve(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* cs, int nc, CPData* cp,
+                 const StepParams& sp)
+{
+    resolve_t<0>(b1, p1, b2, p2, cs, nc, cp, sp);
 }
 
 }  // namespace psp

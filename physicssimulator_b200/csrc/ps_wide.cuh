@@ -56,13 +56,16 @@ struct WArgs {
     unsigned* bucket;            // [kBuckets+1] counts, then exclusive starts
     unsigned* bucket_cur;        // [kBuckets]
     Entry* entries; unsigned entries_cap;
-    unsigned* hit_cnt;           // per level
-    unsigned* hitlist;           // [entries_cap], a round uses [round start, ...)
+    unsigned* hit_cnt;           // per (level, kind) bucket
+    unsigned* hitlist;           // [entries_cap], a bucket's hits are listed from the bucket's start
     Contact* cpool; unsigned cpool_cap; unsigned* cpool_cur;  // cursor per level
     WorldStats* stats;
+    unsigned* tmp;               // per world x 6: tested, hits, contacts, overflow, ref_exc, (pad) of THIS step's wide pass
+    unsigned long long* tmp_pen; // per world: max |penetration| bits of this step
     RecPair* rec_pairs; RecContact* rec_contacts; int* rec_counts; int rec_pair_cap, rec_contact_cap;
     StepParams sp;
     int margin_ncap;
+    double margin_scale;         // safety factor on the motion margin (a violated margin costs a whole fused redo)
 };
 
 enum { WF_MARGIN = 1, WF_STATIC = 2, WF_CAPACITY = 4 };
@@ -78,11 +81,14 @@ __global__ void wide_reset(WArgs a)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t <= kBuckets) a.bucket[t] = 0;
     if (t < kBuckets) a.bucket_cur[t] = 0;
-    if (t < kWideMaxLevels + 2) { a.hit_cnt[t] = 0; a.cpool_cur[t] = 0; }
+    if (t < kBuckets) a.hit_cnt[t] = 0;
+    if (t < kWideMaxLevels + 2) a.cpool_cur[t] = 0;
     if (t < a.n_worlds) {
         a.wflags[t] = a.always_fused[t] ? WF_STATIC : 0u;
         a.K[t] = 0; a.maxl[t] = 0;
         a.stats[t].nan_flag = 0;
+        for (int k = 0; k < 6; k++) a.tmp[6 * t + k] = 0;
+        a.tmp_pen[t] = 0ull;
         if (a.rec_counts) { a.rec_counts[2 * t] = 0; a.rec_counts[2 * t + 1] = 0; }
     }
 }
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(128) wide_predict(WArgs a)
     double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
     int np_ = a.nprev[g];
     double n = (double)(np_ < a.margin_ncap ? np_ : a.margin_ncap) + 2.0;
-    double m = p.is_static ? 0.0 : (0.01 + n * a.sp.dt * (speed + n * acc * a.sp.dt + 0.5));
+    double m = p.is_static ? 0.0 : a.margin_scale * (0.01 + n * a.sp.dt * (speed + n * acc * a.sp.dt + 0.5));
     if (!(m == m)) m = 0.0;
     double rs, rb;
     if (p.shape == 0) { rs = p.dims[0]; rb = 1.7320508075688774 * p.dims[0]; }
@@ -224,32 +230,9 @@ __global__ void wide_scatter(WArgs a)  // thread per world
 }
 
 // ---- rounds ---------------------------------------------------------------------------------------------
-// re-integrate the bodies of this round's pairs that an earlier round changed: thread per (entry, side)
-__global__ void __launch_bounds__(128) wide_integrate(WArgs a, unsigned first, unsigned count)
-{
-    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * count) return;
-    const Entry& e = a.entries[first + (t >> 1)];
-    if (a.wflags[e.w]) return;
-    const int o = a.off[e.w], N = a.off[e.w + 1] - o;
-    const int b = (t & 1) ? (int)(e.ij >> 16) : (int)(e.ij & 0xffff);
-    const int g = o + b;
-    if (a.pvalid[g]) return;  // static bodies stay valid for the whole step
-    Par p; Dyn cur, pr;
-    ld_par(a.par, 0, g, p);
-    ld_dyn(a.cur, 0, g, cur);
-    integrate(cur, p, a.sp, pr);
-    st_dyn(a.pred, 0, g, pr);
-    a.pvalid[g] = 1;
-    const double* cu = a.cull + (size_t)o * 6;
-    d3 d = pr.x - mk(cu[b], cu[N + b], cu[2 * N + b]);
-    double dd = d.x * d.x + d.y * d.y + d.z * d.z;
-    if (!(dd <= cu[5 * N + b])) atomicOr(&a.wflags[e.w], (unsigned)WF_MARGIN);
-}
-
 // narrow phase of one kind: thread per entry of bucket (level, kind)
 template <int KIND>
-__global__ void __launch_bounds__(128) wide_detect(WArgs a, unsigned first, unsigned count, unsigned round_first, int level)
+__global__ void __launch_bounds__(128) wide_detect(WArgs a, unsigned first, unsigned count, int level)
 {
     unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
@@ -272,22 +255,22 @@ __global__ void __launch_bounds__(128) wide_detect(WArgs a, unsigned first, unsi
     } else {
         nc = detect(di, pi, dj, pj, a.sp.eps, sc.cs, err, ovf, sc);
     }
-    WorldStats& st = a.stats[w];
-    atomicAdd(&st.tested, 1ull);
-    if (err) atomicAdd(&st.ref_exc, 1ull);
-    if (ovf) atomicAdd(&st.overflow, 1ull);
+    unsigned* tm = a.tmp + 6 * (size_t)w;
+    atomicAdd(&tm[0], 1u);
+    if (err) atomicAdd(&tm[4], 1u);
+    if (ovf) atomicAdd(&tm[3], 1u);
     if (nc <= 0) return;
     unsigned cf = atomicAdd(&a.cpool_cur[level], (unsigned)nc);
     if (cf + (unsigned)nc > a.cpool_cap) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); return; }
     for (int k = 0; k < nc; k++) a.cpool[cf + k] = sc.cs[k];
     e.nc = (unsigned)nc; e.cfirst = cf;
-    unsigned slot = atomicAdd(&a.hit_cnt[level], 1u);
-    a.hitlist[round_first + slot] = first + t;
-    atomicAdd(&st.hits, 1ull);
-    atomicAdd(&st.contacts, (unsigned long long)nc);
+    unsigned slot = atomicAdd(&a.hit_cnt[level * 4 + KIND], 1u);
+    a.hitlist[first + slot] = first + t;
+    atomicAdd(&tm[1], 1u);
+    atomicAdd(&tm[2], (unsigned)nc);
     double mp = 0.0;
     for (int k = 0; k < nc; k++) mp = fmax(mp, fabs(sc.cs[k].pen));
-    atomicMax((unsigned long long*)&st.max_pen, (unsigned long long)__double_as_longlong(mp));
+    atomicMax(&a.tmp_pen[w], (unsigned long long)__double_as_longlong(mp));
     if (a.rec_pairs) {
         int* cnt = a.rec_counts + 2 * w;
         int slot2 = atomicAdd(&cnt[0], 1);
@@ -307,12 +290,15 @@ __global__ void __launch_bounds__(128) wide_detect(WArgs a, unsigned first, unsi
     }
 }
 
-// solve + write-back: thread per colliding pair of the round
-__global__ void __launch_bounds__(128) wide_resolve(WArgs a, unsigned round_first, int level)
+// solve + write-back: thread per colliding pair of bucket (level, kind).  A body the solve changed is integrated
+// again right here (its next use — the next pair or the final sweep — needs exactly this predicted copy), which
+// keeps that work in a dense kernel; its margin only matters if a later near pair will test it.
+template <int KIND>
+__global__ void __launch_bounds__(128) wide_resolve(WArgs a, unsigned first, int level)
 {
     unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.hit_cnt[level]) return;
-    const Entry& e = a.entries[a.hitlist[round_first + t]];
+    if (t >= a.hit_cnt[level * 4 + KIND]) return;
+    const Entry& e = a.entries[a.hitlist[first + t]];
     const int w = e.w;
     if (a.wflags[w]) return;
     const int o = a.off[w], N = a.off[w + 1] - o;
@@ -322,31 +308,45 @@ __global__ void __launch_bounds__(128) wide_resolve(WArgs a, unsigned round_firs
     ld_par(a.par, 0, o + j, pj);
     ld_dyn(a.pred, 0, o + i, di);
     ld_dyn(a.pred, 0, o + j, dj);
-    const int nc = (int)e.nc;
-    Contact cs[PS_MAX_CONTACTS];
-    CPData cp[PS_MAX_CONTACTS];
-    for (int k = 0; k < nc; k++) cs[k] = a.cpool[e.cfirst + k];
     const bool si = pi.is_static, sj = pj.is_static;
     if (si) di.L = mk(0.0, 0.0, 0.0);
     if (sj) dj.L = mk(0.0, 0.0, 0.0);
-    resolve(di, pi, dj, pj, cs, nc, cp, a.sp);
+    if (KIND == 2) {
+        const int nc = (int)e.nc;
+        Contact cs[PS_MAX_CONTACTS];
+        CPData cp[PS_MAX_CONTACTS];
+        for (int k = 0; k < nc; k++) cs[k] = a.cpool[e.cfirst + k];
+        resolve_t<0>(di, pi, dj, pj, cs, nc, cp, a.sp);
+    } else {  // sphere pairs always carry exactly one contact
+        Contact cs[1];
+        CPData cp[1];
+        cs[0] = a.cpool[e.cfirst];
+        resolve_t<1>(di, pi, dj, pj, cs, 1, cp, a.sp);
+    }
     w_hit(a, w)[e.k] = 1;
     double* Sw = a.S + (size_t)o * 3 * kMaxStatics;
-    if (si) {
-        double* S = Sw + 3 * ((a.isstat[o + i] - 1) * N + j);
-        S[0] = di.L.x; S[1] = di.L.y; S[2] = di.L.z;
-    } else {
-        st_dyn(a.cur, 0, o + i, di);
-        a.pvalid[o + i] = 0;
-        bump(&a.nhit[o + i]);
-    }
-    if (sj) {
-        double* S = Sw + 3 * ((a.isstat[o + j] - 1) * N + i);
-        S[0] = dj.L.x; S[1] = dj.L.y; S[2] = dj.L.z;
-    } else {
-        st_dyn(a.cur, 0, o + j, dj);
-        a.pvalid[o + j] = 0;
-        bump(&a.nhit[o + j]);
+    const double* cu = a.cull + (size_t)o * 6;
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+        const int b = side ? j : i, other = side ? i : j;
+        const bool stat = side ? sj : si;
+        Dyn& d = side ? dj : di;
+        const Par& p = side ? pj : pi;
+        if (stat) {
+            double* S = Sw + 3 * ((a.isstat[o + b] - 1) * N + other);
+            S[0] = d.L.x; S[1] = d.L.y; S[2] = d.L.z;
+            continue;
+        }
+        st_dyn(a.cur, 0, o + b, d);  // write back (CollisionResolver.fs:27-31)
+        bump(&a.nhit[o + b]);
+        Dyn pr;
+        integrate(d, p, a.sp, pr);
+        st_dyn(a.pred, 0, o + b, pr);  // pvalid stays 1: the predicted copy is current again
+        if ((int)a.last[o + b] > level) {  // a later near pair will test this body at pr.x
+            d3 dd = pr.x - mk(cu[b], cu[N + b], cu[2 * N + b]);
+            double q = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
+            if (!(q <= cu[5 * N + b])) atomicOr(&a.wflags[w], (unsigned)WF_MARGIN);
+        }
     }
 }
 
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(128) wide_final(WArgs a)
                  isfinite(out.L.x) && isfinite(out.L.y) && isfinite(out.L.z));
     for (int k = 0; k < 9; k++) bad = bad || !isfinite(out.R.a[k]);
     if (bad) a.stats[w].nan_flag = 1;
-    if (g == a.off[w]) atomicAdd(&a.stats[w].steps, 1ull);
+
 }
 
 // account the worlds handed over to the fused kernel (thread per world)
@@ -411,8 +411,14 @@ __global__ void wide_account(WArgs a)
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.n_worlds) return;
     unsigned f = a.wflags[w];
-    if (!f || a.always_fused[w]) return;
     WorldStats& st = a.stats[w];
+    if (!f) {  // the wide pass stands: commit its counters
+        const unsigned* tm = a.tmp + 6 * (size_t)w;
+        st.steps++; st.tested += tm[0]; st.hits += tm[1]; st.contacts += tm[2]; st.overflow += tm[3]; st.ref_exc += tm[4];
+        st.max_pen = fmax(st.max_pen, __longlong_as_double((long long)a.tmp_pen[w]));
+        return;
+    }
+    if (a.always_fused[w]) return;
     st.fallback++;
     if (f & WF_STATIC) st.fb_static++;
     else if (f & WF_MARGIN) st.fb_margin++;
