@@ -86,6 +86,7 @@ struct Batch {
     unsigned entries_cap = 0, cpool_cap = 0;
     unsigned* h_bucket = nullptr;  // pinned
     unsigned* d_tmp = nullptr;
+    unsigned *d_surv = nullptr, *d_surv_cnt = nullptr;
     unsigned long long* d_tmp_pen = nullptr;
     double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // PS_B200_WIDE_PROF: setup, integrate, ss, sb, bb, resolve, tail, fused
     long long prof_steps = 0, prof_rounds = 0;
@@ -206,7 +207,7 @@ void free_device(Batch* B)
     dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_scratch); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
-    dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen);
+    dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt);
     if (B->h_bucket) { cudaFreeHost(B->h_bucket); B->h_bucket = nullptr; }
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
@@ -323,6 +324,8 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_cpool, (size_t)B->cpool_cap * sizeof(Contact)));
         CK(cudaMallocHost(&B->h_bucket, (psw::kBuckets + 1) * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_tmp, nw * 6 * sizeof(unsigned)));
+        CK(cudaMalloc(&B->d_surv, (size_t)B->entries_cap * sizeof(unsigned)));
+        CK(cudaMalloc(&B->d_surv_cnt, (psw::kWideMaxLevels + 2) * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_tmp_pen, nw * sizeof(unsigned long long)));
         CK(cudaMemcpy(B->d_body_world, bw.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B->d_isstat, isstat.data(), nb, cudaMemcpyHostToDevice));
@@ -574,7 +577,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     a.K = B->d_K; a.maxl = B->d_maxl; a.wflags = B->d_wflags; a.always_fused = B->d_always_fused;
     a.bucket = B->d_bucket; a.bucket_cur = B->d_bucket_cur; a.entries = B->d_entries; a.entries_cap = B->entries_cap;
     a.hit_cnt = B->d_hit_cnt; a.hitlist = B->d_hitlist; a.cpool = B->d_cpool; a.cpool_cap = B->cpool_cap; a.cpool_cur = B->d_cpool_cur;
-    a.stats = B->d_stats; a.tmp = B->d_tmp; a.tmp_pen = B->d_tmp_pen;
+    a.stats = B->d_stats; a.tmp = B->d_tmp; a.tmp_pen = B->d_tmp_pen; a.surv = B->d_surv; a.surv_cnt = B->d_surv_cnt;
     a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
     a.sp = ka.sp; a.margin_ncap = ka.margin_ncap;
@@ -616,7 +619,10 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
         lap(2);
         if (c1) wide_detect<1><<<(c1 + 127) / 128, 128, 0, st>>>(a, first + c0, c1, r);
         lap(3);
-        if (c2) wide_detect<2><<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, c2, r);
+        if (c2) {
+            wide_bb_quick<<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, c2, r);
+            wide_detect<2><<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, c2, r);  // threads past the survivor count exit
+        }
         lap(4);
         if (c0) wide_resolve<0><<<(c0 + 127) / 128, 128, 0, st>>>(a, first, r);
         if (c1) wide_resolve<1><<<(c1 + 127) / 128, 128, 0, st>>>(a, first + c0, r);

@@ -312,25 +312,13 @@ PSD bool sat_ranges(double a, double b, double c, double d, double& pen, bool& f
 }
 
 
-// detectBoxBoxCollision (CollisionDetection.fs:29-164) over SAT.tryFindSeparatingAxis (SAT.fs:206-240)
-// returns #contacts (0 = none); overflow set when the manifold would exceed PS_MAX_CONTACTS
-PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
-                  int& overflow, PairScratch& sc)
+// Early "no collision" for box-box: any ONE separated axis of the reference's list makes the result None
+// (SAT.fs:185-198 `sequence`), whichever it is.  Tries the face axis of each box that looks most along the centre
+// offset, with the reference's own arithmetic for that axis.  true = proven separated (exactly what the full walk
+// would conclude); false = undecided.
+PSN bool bb_quick_separated(const Dyn& b1, const Dyn& b2, const OBox& o1, const OBox& o2)
 {
-    OBox& o1 = sc.o1;
-    OBox& o2 = sc.o2;
-    make_obox(b1, p1, o1);
-    make_obox(b2, p2, o2);
-
-    int best_origin = -1, best_i = 0, best_j = 0;
-    double best_pen = 0.0;
-    d3 best_n = mk(0, 0, 0);
     d3 fromFirst = b2.x - b1.x;
-
-    // Early "no collision": any ONE separated axis of the reference's list makes the result None
-    // (SAT.fs:185-198 `sequence`), whichever it is.  Try the face axis of each box that looks most along the
-    // centre offset first, with the reference's own arithmetic for that axis; a miss then costs 2 axes
-    // instead of up to 21.  If neither separates, the full ordered walk below decides (first-min semantics).
 #pragma unroll 1
     for (int side = 0; side < 2; side++) {
         const Dyn& bb = side == 0 ? b1 : b2;
@@ -348,8 +336,30 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
         bool flip;
         project_box(T, T.n[f], ta, tb);
         project_box(O, T.n[f], oc, od);
-        if (!sat_ranges(ta, tb, oc, od, pen, flip)) return 0;
+        if (!sat_ranges(ta, tb, oc, od, pen, flip)) return true;
     }
+    return false;
+}
+
+// detectBoxBoxCollision (CollisionDetection.fs:29-164) over SAT.tryFindSeparatingAxis (SAT.fs:206-240)
+// returns #contacts (0 = none); overflow set when the manifold would exceed PS_MAX_CONTACTS
+// boxes_ready: sc.o1/sc.o2 are already built and the quick test has already failed to separate them
+PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+                  int& overflow, PairScratch& sc, bool boxes_ready = false)
+{
+    OBox& o1 = sc.o1;
+    OBox& o2 = sc.o2;
+    if (!boxes_ready) {
+        make_obox(b1, p1, o1);
+        make_obox(b2, p2, o2);
+    }
+
+    int best_origin = -1, best_i = 0, best_j = 0;
+    double best_pen = 0.0;
+    d3 best_n = mk(0, 0, 0);
+    d3 fromFirst = b2.x - b1.x;
+
+    if (!boxes_ready && bb_quick_separated(b1, b2, o1, o2)) return 0;
 
     // Face1 then Face2 (SAT.fs:230-234).  Normals come in +- pairs (f, f+1) with n[f+1] == 0.0 - n[f] bit for
     // bit, and a projection onto the negated axis is 0.0 - projection (see detect_sphere_box): one pass per pair.
