@@ -262,3 +262,26 @@ def test_tile_widths_and_multi_step_launches_agree(monkeypatch):
         else:
             for k in ("pos", "vel", "rot"):
                 assert same_bits(st[k], ref[k]), f"tile {tile}: {k}"
+
+
+@pytest.mark.parametrize("path", ["wide", "fused"])
+def test_both_step_paths_against_the_oracle(monkeypatch, path):
+    """the batch-wide (breadth-first) path and the fused per-world kernel, forced explicitly, on the scenes, the C2/C3
+    slices and the box cases: same bits as the oracle (small batches default to the fused kernel, so the wide path
+    would otherwise only be exercised by bench-size runs)"""
+    monkeypatch.setenv("PS_B200_PATH", path)
+    s, _ = scenes.stack_scene()
+    d, _ = scenes.domino_scene()
+    c1, _ = scenes.c1_stack20()
+    _run([s, d, c1], Configuration(), [1, 4, 45, 150], f"scenes/{path}")
+    w3 = [scenes.c3_mixed128(w)[0] for w in range(3)]
+    _run(w3, scenes.c3_mixed128(0)[1], [1, 19, 100], f"C3/{path}")
+    w2 = [scenes.c2_spheres64(w)[0] for w in range(4)]
+    _run(w2, scenes.c2_spheres64(0)[1], [1, 19, 120], f"C2/{path}")
+
+
+def test_wide_path_second_order_integrator_and_many_worlds(monkeypatch):
+    monkeypatch.setenv("PS_B200_PATH", "wide")
+    cfg = Configuration(StepConfig=StepConfiguration(RigidBodyIntegratorKind=1))
+    worlds = [scenes.c3_mixed128(w, n_boxes=12, n_spheres=12)[0] for w in range(40)]
+    _run(worlds, cfg, [1, 30, 90], "wide/second order", contacts=False)

@@ -18,11 +18,15 @@ ap.add_argument("--worlds", type=int, default=32)
 ap.add_argument("--first", type=int, default=0)
 ap.add_argument("--steps", type=int, default=260)
 ap.add_argument("--chunk", type=int, default=10)
+ap.add_argument("--path", default="", help="force PS_B200_PATH for the fast batch (wide|fused)")
 args = ap.parse_args()
 fn = {"c2": scenes.c2_spheres64, "c3": scenes.c3_mixed128}[args.workload]
 worlds = [fn(w)[0] for w in range(args.first, args.first + args.worlds)]
 cfg = fn(0)[1]
+if args.path:
+    os.environ['PS_B200_PATH'] = args.path
 a = BatchSimulator(worlds, cfg, device=0)
+os.environ.pop('PS_B200_PATH', None)
 b = BatchSimulator(worlds, cfg, device=0, exact_all_pairs=True)
 off = a._offsets
 done = 0
