@@ -525,7 +525,7 @@ int ps_batch_destroy(void* handle)
     cudaSetDevice(B->device);
     cudaStreamSynchronize(B->stream);
     if (getenv("PS_B200_WIDE_PROF") && B->prof_steps > 0)
-        fprintf(stderr, "[ps_b200 wide profile] steps %lld rounds/step %.1f | ms/step: setup %.3f resolve_sphere %.3f detect_ss %.3f detect_sb %.3f detect_bb %.3f resolve_bb %.3f tail %.3f fused %.3f\n",
+        fprintf(stderr, "[ps_b200 wide profile] steps %lld rounds/step %.1f | ms/step: setup %.3f (-) %.3f detect_stage1 %.3f (-) %.3f bb_full %.3f resolve %.3f tail %.3f fused %.3f\n",
                 B->prof_steps, (double)B->prof_rounds / B->prof_steps, B->prof_ms[0] / B->prof_steps, B->prof_ms[1] / B->prof_steps, B->prof_ms[2] / B->prof_steps,
                 B->prof_ms[3] / B->prof_steps, B->prof_ms[4] / B->prof_steps, B->prof_ms[5] / B->prof_steps, B->prof_ms[6] / B->prof_steps, B->prof_ms[7] / B->prof_steps);
     free_device(B);
@@ -601,9 +601,9 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     wide_near_count<<<gb, 128, 0, st>>>(a);
     wide_near_scan<<<gw, 64, 0, st>>>(a);
     wide_near_fill<<<gb, 128, 0, st>>>(a);
-    wide_levels<<<gw, 64, 0, st>>>(a);
-    wide_bucket_scan<<<1, 1, 0, st>>>(a);
-    wide_scatter<<<gw, 64, 0, st>>>(a);
+    wide_levels<<<gw, psw::kLvlThreads, 0, st>>>(a);
+    wide_bucket_scan<<<1, 32, 0, st>>>(a);
+    wide_scatter<<<gw, psw::kLvlThreads, 0, st>>>(a);
     CK(cudaMemcpyAsync(B->h_bucket, B->d_bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     B->launches += 8;
@@ -615,22 +615,15 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
         if (first >= hb[kBuckets]) break;  // no pair at this or any later level
         if (total == 0) continue;
         unsigned c0 = hb[r * 4 + 1] - hb[r * 4], c1 = hb[r * 4 + 2] - hb[r * 4 + 1], c2 = hb[r * 4 + 3] - hb[r * 4 + 2];
-        if (c0) wide_detect<0><<<(c0 + 127) / 128, 128, 0, st>>>(a, first, c0, r);
+        const unsigned nblk = (c0 + 127) / 128 + (c1 + 127) / 128 + (c2 + 127) / 128;
+        wide_round_detect<<<nblk, 128, 0, st>>>(a, first, c0, c1, c2, r);
         lap(2);
-        if (c1) wide_detect<1><<<(c1 + 127) / 128, 128, 0, st>>>(a, first + c0, c1, r);
-        lap(3);
-        if (c2) {
-            wide_bb_quick<<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, c2, r);
-            wide_detect<2><<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, c2, r);  // threads past the survivor count exit
-        }
+        if (c2) wide_round_bb<<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, c2, r);  // threads past the survivor count exit
         lap(4);
-        if (c0) wide_resolve<0><<<(c0 + 127) / 128, 128, 0, st>>>(a, first, r);
-        if (c1) wide_resolve<1><<<(c1 + 127) / 128, 128, 0, st>>>(a, first + c0, r);
-        lap(1);
-        if (c2) wide_resolve<2><<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, r);
+        wide_round_resolve<<<nblk, 128, 0, st>>>(a, first, c0, c1, c2, r);
         lap(5);
         B->prof_rounds++;
-        B->launches += 2 * ((c0 != 0) + (c1 != 0) + (c2 != 0));
+        B->launches += 2 + (c2 != 0);
     }
     wide_static_fold<<<gb, 128, 0, st>>>(a);
     wide_final<<<gb, 128, 0, st>>>(a);

@@ -180,52 +180,83 @@ PSD int pair_kind(const WArgs& a, int o, int i, int j)  // 0 sphere-sphere, 1 sp
 {
     return (int)a.isbox[o + i] + (int)a.isbox[o + j];
 }
-__global__ void wide_levels(WArgs a)
+// Buckets are counted per CTA in shared memory first (64 worlds per CTA): 6 M pairs hammering ~150 global counters
+// took 2 ms per pass.
+constexpr int kLvlThreads = 64;
+__global__ void __launch_bounds__(kLvlThreads) wide_levels(WArgs a)
 {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= a.n_worlds) return;
-    if (a.wflags[w]) return;  // already condemned to the fused kernel
-    const int o = a.off[w], K = a.K[w];
-    const unsigned* near = w_near(a, w);
-    unsigned short* level = w_level(a, w);
-    int maxl = 0;
+    __shared__ unsigned hist[kBuckets];
+    for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads) hist[b] = 0;
+    __syncthreads();
+    int w = blockIdx.x * kLvlThreads + threadIdx.x;
+    if (w < a.n_worlds && !a.wflags[w]) {
+        const int o = a.off[w], K = a.K[w];
+        const unsigned* near = w_near(a, w);
+        unsigned short* level = w_level(a, w);
+        int maxl = 0;
+        for (int k = 0; k < K; k++) {
+            unsigned ij = near[k];
+            int i = ij & 0xffff, j = ij >> 16;
+            int li = a.isstat[o + i] ? 0 : a.last[o + i];
+            int lj = a.isstat[o + j] ? 0 : a.last[o + j];
+            int l = (li > lj ? li : lj) + 1;
+            level[k] = (unsigned short)l;
+            if (!a.isstat[o + i]) a.last[o + i] = (unsigned short)l;
+            if (!a.isstat[o + j]) a.last[o + j] = (unsigned short)l;
+            if (l > maxl) maxl = l;
+        }
+        if (maxl > kWideMaxLevels) {
+            atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY);
+        } else {
+            a.maxl[w] = maxl;
+            for (int k = 0; k < K; k++) {
+                unsigned ij = near[k];
+                atomicAdd(&hist[level[k] * 4 + pair_kind(a, o, ij & 0xffff, ij >> 16)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads)
+        if (hist[b]) atomicAdd(&a.bucket[b], hist[b]);
+}
+__global__ void wide_bucket_scan(WArgs a)  // one warp: kBuckets is ~4 K
+{
+    __shared__ unsigned part[32];
+    const int lane = threadIdx.x, per = kBuckets / 32;
+    unsigned s = 0;
+    for (int b = lane * per; b < (lane + 1) * per; b++) s += a.bucket[b];
+    part[lane] = s;
+    __syncwarp();
+    unsigned base = 0;
+    for (int l = 0; l < lane; l++) base += part[l];
+    for (int b = lane * per; b < (lane + 1) * per; b++) { unsigned t = a.bucket[b]; a.bucket[b] = base; base += t; }
+    if (lane == 31) a.bucket[kBuckets] = base;
+}
+__global__ void __launch_bounds__(kLvlThreads) wide_scatter(WArgs a)  // thread per world, CTA-local reservation of ranges
+{
+    __shared__ unsigned cnt[kBuckets];   // pairs of this CTA per bucket, then the CTA's base inside the bucket
+    __shared__ unsigned cur[kBuckets];
+    for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads) { cnt[b] = 0; cur[b] = 0; }
+    __syncthreads();
+    const int w = blockIdx.x * kLvlThreads + threadIdx.x;
+    const bool over = a.bucket[kBuckets] > a.entries_cap;
+    bool live = w < a.n_worlds && !a.wflags[w];
+    if (live && over) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); live = false; }
+    const int o = live ? a.off[w] : 0, K = live ? a.K[w] : 0;
+    const unsigned* near = live ? w_near(a, w) : nullptr;
+    const unsigned short* level = live ? w_level(a, w) : nullptr;
     for (int k = 0; k < K; k++) {
         unsigned ij = near[k];
-        int i = ij & 0xffff, j = ij >> 16;
-        int li = a.isstat[o + i] ? 0 : a.last[o + i];
-        int lj = a.isstat[o + j] ? 0 : a.last[o + j];
-        int l = (li > lj ? li : lj) + 1;
-        level[k] = (unsigned short)l;
-        if (!a.isstat[o + i]) a.last[o + i] = (unsigned short)l;
-        if (!a.isstat[o + j]) a.last[o + j] = (unsigned short)l;
-        if (l > maxl) maxl = l;
+        atomicAdd(&cnt[level[k] * 4 + pair_kind(a, o, ij & 0xffff, ij >> 16)], 1u);
     }
-    if (maxl > kWideMaxLevels) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); return; }
-    a.maxl[w] = maxl;
-    for (int k = 0; k < K; k++) {
-        unsigned ij = near[k];
-        atomicAdd(&a.bucket[level[k] * 4 + pair_kind(a, o, ij & 0xffff, ij >> 16)], 1u);
-    }
-}
-__global__ void wide_bucket_scan(WArgs a)  // one thread: kBuckets is ~4 K
-{
-    unsigned acc = 0;
-    for (int b = 0; b < kBuckets; b++) { unsigned t = a.bucket[b]; a.bucket[b] = acc; acc += t; }
-    a.bucket[kBuckets] = acc;
-}
-__global__ void wide_scatter(WArgs a)  // thread per world
-{
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= a.n_worlds) return;
-    if (a.wflags[w]) return;
-    if (a.bucket[kBuckets] > a.entries_cap) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); return; }
-    const int o = a.off[w], K = a.K[w];
-    const unsigned* near = w_near(a, w);
-    const unsigned short* level = w_level(a, w);
+    __syncthreads();
+    for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads)
+        if (cnt[b]) cnt[b] = a.bucket[b] + atomicAdd(&a.bucket_cur[b], cnt[b]);
+    __syncthreads();
     for (int k = 0; k < K; k++) {
         unsigned ij = near[k];
         int b = level[k] * 4 + pair_kind(a, o, ij & 0xffff, ij >> 16);
-        unsigned pos = a.bucket[b] + atomicAdd(&a.bucket_cur[b], 1u);
+        unsigned pos = cnt[b] + atomicAdd(&cur[b], 1u);
         Entry e; e.w = w; e.ij = ij; e.k = (unsigned)k; e.nc = 0; e.cfirst = 0;
         a.entries[pos] = e;
     }
@@ -235,9 +266,8 @@ __global__ void wide_scatter(WArgs a)  // thread per world
 // box-box, stage 1: the two most promising axes.  Most near box pairs are separated and end here; the rest are
 // compacted so that stage 2 (full SAT + contact generation, wide_detect<2>) runs on dense warps
 // (ncu before the split: 5 of 32 threads per instruction in the box-box kernel).
-__global__ void __launch_bounds__(128) wide_bb_quick(WArgs a, unsigned first, unsigned count, int level)
+__device__ __forceinline__ void wide_bb_quick_body(const WArgs& a, unsigned first, unsigned count, int level, unsigned t)
 {
-    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const Entry& e = a.entries[first + t];
     const int w = e.w;
@@ -262,9 +292,8 @@ __global__ void __launch_bounds__(128) wide_bb_quick(WArgs a, unsigned first, un
 
 // narrow phase of one kind: thread per entry of bucket (level, kind)
 template <int KIND>
-__global__ void __launch_bounds__(128) wide_detect(WArgs a, unsigned first, unsigned count, int level)
+__device__ __forceinline__ void wide_detect_body(const WArgs& a, unsigned first, unsigned count, int level, unsigned t)
 {
-    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned ei = first + t;
     if (KIND == 2) {  // box-box: only the pairs stage 1 could not separate
         if (t >= a.surv_cnt[level]) return;
@@ -330,9 +359,8 @@ __global__ void __launch_bounds__(128) wide_detect(WArgs a, unsigned first, unsi
 // again right here (its next use — the next pair or the final sweep — needs exactly this predicted copy), which
 // keeps that work in a dense kernel; its margin only matters if a later near pair will test it.
 template <int KIND>
-__global__ void __launch_bounds__(128) wide_resolve(WArgs a, unsigned first, int level)
+__device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first, int level, unsigned t)
 {
-    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.hit_cnt[level * 4 + KIND]) return;
     const Entry& e = a.entries[a.hitlist[first + t]];
     const int w = e.w;
@@ -384,6 +412,32 @@ __global__ void __launch_bounds__(128) wide_resolve(WArgs a, unsigned first, int
             if (!(q <= cu[5 * N + b])) atomicOr(&a.wflags[w], (unsigned)WF_MARGIN);
         }
     }
+}
+
+// One launch per stage and round: the CTA index selects the kind (CTA-uniform branch), so a round costs three
+// launches instead of seven.
+// stage 1: sphere-sphere + sphere-box narrow phase + box-box quick test
+__global__ void __launch_bounds__(128) wide_round_detect(WArgs a, unsigned first, unsigned c0, unsigned c1, unsigned c2, int level)
+{
+    const unsigned b0 = (c0 + 127) / 128, b1 = (c1 + 127) / 128;
+    const unsigned blk = blockIdx.x;
+    if (blk < b0) wide_detect_body<0>(a, first, c0, level, blk * 128 + threadIdx.x);
+    else if (blk < b0 + b1) wide_detect_body<1>(a, first + c0, c1, level, (blk - b0) * 128 + threadIdx.x);
+    else wide_bb_quick_body(a, first + c0 + c1, c2, level, (blk - b0 - b1) * 128 + threadIdx.x);
+}
+// stage 2: full box-box SAT + contact generation on the survivors of the quick test
+__global__ void __launch_bounds__(128) wide_round_bb(WArgs a, unsigned first_bb, unsigned c2, int level)
+{
+    wide_detect_body<2>(a, first_bb, c2, level, blockIdx.x * 128 + threadIdx.x);
+}
+// stage 3: solve + write-back of every colliding pair of the round
+__global__ void __launch_bounds__(128) wide_round_resolve(WArgs a, unsigned first, unsigned c0, unsigned c1, unsigned c2, int level)
+{
+    const unsigned b0 = (c0 + 127) / 128, b1 = (c1 + 127) / 128;
+    const unsigned blk = blockIdx.x;
+    if (blk < b0) wide_resolve_body<0>(a, first, level, blk * 128 + threadIdx.x);
+    else if (blk < b0 + b1) wide_resolve_body<1>(a, first + c0, level, (blk - b0) * 128 + threadIdx.x);
+    else wide_resolve_body<2>(a, first + c0 + c1, level, (blk - b0 - b1) * 128 + threadIdx.x);
 }
 
 // ---- E: static bodies: L = fold over their colliding pairs in pair order (thread per body, statics only) -----
