@@ -245,9 +245,8 @@ PSN int detect_ss(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, Co
 // SAT.SphereBox.tryFindSeparatingAxis (SAT.fs:108-151) + detectedSphereBoxCollision
 // (CollisionDetection.fs:166-184). Normal returned "from box". err set where the reference throws.
 PSN int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Par& bp, double eps, Contact* out,
-                          int& face, int& err, PairScratch& sc)
+                          int& face, int& err, OBox& ob)
 {
-    OBox& ob = sc.o1;
     make_obox(bb, bp, ob);
     double r = sp_.dims[0];
     double best_pen = 0.0;
@@ -585,14 +584,33 @@ PSD int detect(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, doubl
     if (p1.shape == 1 && p2.shape == 1) return detect_bb(b1, p1, b2, p2, eps, out, err, overflow, sc);
     int face = 0;
     if (p1.shape == 0) {
-        int n = detect_sphere_box(b1, p1, b2, p2, eps, out, face, err, sc);
+        int n = detect_sphere_box(b1, p1, b2, p2, eps, out, face, err, sc.o1);
         if (n) {
             out[0].n = -out[0].n;  // WithInvertedNormals (:217-219)
             out[0].feat = 1u | ((unsigned)face << 4);
         }
         return n;
     }
-    int n = detect_sphere_box(b2, p2, b1, p1, eps, out, face, err, sc);
+    int n = detect_sphere_box(b2, p2, b1, p1, eps, out, face, err, sc.o1);
+    if (n) out[0].feat = 2u | ((unsigned)face << 4);
+    return n;
+}
+
+// areColliding for a pair with at least one sphere: exactly one contact, no clip buffers needed
+PSD int detect_sphere_pair(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+                           OBox& ob)
+{
+    if (p1.shape == 0 && p2.shape == 0) return detect_ss(b1, p1, b2, p2, out);
+    int face = 0;
+    if (p1.shape == 0) {
+        int n = detect_sphere_box(b1, p1, b2, p2, eps, out, face, err, ob);
+        if (n) {
+            out[0].n = -out[0].n;  // WithInvertedNormals (CollisionDetection.fs:217-219)
+            out[0].feat = 1u | ((unsigned)face << 4);
+        }
+        return n;
+    }
+    int n = detect_sphere_box(b2, p2, b1, p1, eps, out, face, err, ob);
     if (n) out[0].feat = 2u | ((unsigned)face << 4);
     return n;
 }

@@ -276,27 +276,45 @@ PSN void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
     Dyn di, dj;
     get_pred(c, i, pi, di, fast);
     get_pred(c, j, pj, dj, fast);
-#if PS_SCRATCH_GLOBAL
-    PairScratch& sc = *c.scratch;
-#else
-    PairScratch sc_local;
-    PairScratch& sc = sc_local;
-#endif
-    Contact* cs = sc.cs;
-    int err = 0, ovf = 0;
+    const bool bb = (pi.shape == 1) && (pj.shape == 1);
+    int err = 0, ovf = 0, nc;
     c.tested++;
-    int nc = detect(di, pi, dj, pj, c.a->sp.eps, cs, err, ovf, sc);
-    if (err) c.ref_exc++;
-    if (ovf) c.overflow++;
-    if (nc <= 0) return;
-    c.hits++;
-    c.contacts += nc;
-    for (int k = 0; k < nc; k++) c.max_pen = fmax(c.max_pen, fabs(cs[k].pen));
-    record_pair(c, i, j, cs, nc);
     bool si = fast && pi.is_static, sj = fast && pj.is_static;
-    if (si) di.L = mk(0.0, 0.0, 0.0);
-    if (sj) dj.L = mk(0.0, 0.0, 0.0);
-    resolve(di, pi, dj, pj, cs, nc, sc.cp, c.a->sp);
+    if (!bb) {
+        // a pair with a sphere: one contact; everything stays in registers / a 240-byte box record
+        Contact cs[1];
+        CPData cp[1];
+        OBox ob;
+        nc = detect_sphere_pair(di, pi, dj, pj, c.a->sp.eps, cs, err, ob);
+        if (err) c.ref_exc++;
+        if (nc <= 0) return;
+        c.hits++;
+        c.contacts += 1;
+        c.max_pen = fmax(c.max_pen, fabs(cs[0].pen));
+        record_pair(c, i, j, cs, 1);
+        if (si) di.L = mk(0.0, 0.0, 0.0);
+        if (sj) dj.L = mk(0.0, 0.0, 0.0);
+        resolve_t<1>(di, pi, dj, pj, cs, 1, cp, c.a->sp);
+    } else {
+#if PS_SCRATCH_GLOBAL
+        PairScratch& sc = *c.scratch;
+#else
+        PairScratch sc_local;
+        PairScratch& sc = sc_local;
+#endif
+        Contact* cs = sc.cs;
+        nc = detect_bb(di, pi, dj, pj, c.a->sp.eps, cs, err, ovf, sc);
+        if (err) c.ref_exc++;
+        if (ovf) c.overflow++;
+        if (nc <= 0) return;
+        c.hits++;
+        c.contacts += nc;
+        for (int k = 0; k < nc; k++) c.max_pen = fmax(c.max_pen, fabs(cs[k].pen));
+        record_pair(c, i, j, cs, nc);
+        if (si) di.L = mk(0.0, 0.0, 0.0);
+        if (sj) dj.L = mk(0.0, 0.0, 0.0);
+        resolve(di, pi, dj, pj, cs, nc, sc.cp, c.a->sp);
+    }
     if (fast) c.s.hit[near_k] = 1;
     if (si) {  // a static-static pair never reaches here (canIntersect)
         double* S = c.s.S + 3 * ((c.s.isstat[i] - 1) * c.N + j);
