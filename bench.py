@@ -192,6 +192,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    launches0 = sim.batch.schedule()["kernel_launches"]
     t0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xff)           # L2 flush between timed iterations (outside the event pair)
@@ -202,6 +203,8 @@ def main():
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - t0
+    sched = sim.batch.schedule()
+    gpu_launches = sched["kernel_launches"] - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -211,6 +214,15 @@ def main():
     total_body_steps = n_dyn * per_gpu * world * args.steps
     value = total_body_steps / (dev_ms_max * 1e-3)
     kernel_ms = dev_ms / args.steps  # this rank's average launch duration
+
+    # informational: the same K steps in ONE call (fused path: one launch, worlds do not wait for each other between steps)
+    ms0, ms1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ms0.record()
+    sim.batch.step_async(args.steps, stream)
+    ms1.record()
+    torch.cuda.synchronize()
+    multi_ms = ms0.elapsed_time(ms1)
 
     # end to end through the public API with HOST buffers: H2D of the step's input state from pinned memory,
     # the step, D2H of the resulting state — all inside the timed region
@@ -258,17 +270,19 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{name}: {WORKLOADS[name][3]}", "worlds_per_gpu": per_gpu, "dynamic_bodies_per_world": n_dyn,
-                       "settle_steps": args.settle, "launch": "1 step_kernel launch per step (one sub-warp tile per world, several worlds per warp)",
+                       "settle_steps": args.settle, "launch": ("fused: 1 step_kernel launch per step, %d lanes per world" % sched["lanes_per_world"]) if sched["path"] == "fused" else "wide: per-stage kernels over the whole batch, 3 launches per wavefront round + the fused kernel for flagged worlds", "path": sched["path"],
                        "l2": "256 MiB buffer written between timed iterations (outside the CUDA-event pairs)",
                        "parallelism": f"worlds sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": bytes_state, "d2h_bytes_per_step": bytes_state,
                     "steps": e2e_steps, "what": "ps_batch_set_state(host pinned) + ps_batch_step(1) + ps_batch_get_state(host) per step"},
-            "gpu_launches": args.steps,
+            "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "psk::step_kernel", "algorithmic_bytes_per_body_step": B_ALG, "kernel_ms": kernel_ms,
+                         "kernel": "psk::step_kernel" if sched["path"] == "fused" else "psw::wide_* stages + psk::step_kernel (one step)", "algorithmic_bytes_per_body_step": B_ALG, "kernel_ms": kernel_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "traffic_note": "ncu dram bytes per launch of this workload (profiles/traffic.json); far above the algorithmic bytes: the per-pair routines spill their working arrays to the local-memory stack",
                          "note": "the per-world ordered contact solve is a dependent FP64 chain: the HBM roofline is the metric's denominator, not the kernel's limiter"},
+            "multi_step_call": {"steps": args.steps, "ms_per_step": multi_ms / args.steps, "value_this_rank": n_dyn * per_gpu * args.steps / (multi_ms * 1e-3),
+                                "what": "ps_batch_step(K) in one call, no L2 flush between steps; informational, not the headline"},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "stats": stats,

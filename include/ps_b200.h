@@ -175,6 +175,9 @@ int ps_batch_reset(void* handle);
 
 int ps_batch_stats(void* handle, ps_stats* out);
 int ps_batch_num_bodies(void* handle, int32_t* n_bodies_total, int32_t* n_dynamic_total);
+/* how this batch is scheduled: path 0 = fused per-world kernel, 1 = batch-wide stages;
+ * lanes per world of the fused kernel; kernels launched by this handle so far (all entry points) */
+int ps_batch_schedule(void* handle, int32_t* path, int32_t* lanes_per_world, int64_t* kernel_launches);
 /* profiling aid: per world 8 x uint64 = SM cycles of the step phases (predict+cull spheres, near list, levels+sort,
  * wavefronts, rest), the slowest single step, sum of near-list lengths, sum of level counts */
 int ps_batch_debug_cycles(void* handle, unsigned long long* out);

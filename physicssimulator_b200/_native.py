@@ -26,7 +26,7 @@ EXPORTS = (
     "ps_batch_step_async", "ps_batch_synchronize", "ps_batch_get_state", "ps_batch_set_state",
     "ps_batch_get_state_device", "ps_batch_get_contacts", "ps_batch_get_candidates", "ps_batch_apply_impulse",
     "ps_batch_add_body", "ps_batch_reset", "ps_batch_stats", "ps_batch_num_bodies", "ps_broadphase_pairs",
-    "ps_batch_debug_cycles",
+    "ps_batch_debug_cycles", "ps_batch_schedule",
 )
 
 
@@ -209,6 +209,11 @@ class Batch:
         s = ps_stats()
         check(lib().ps_batch_stats(self.h, ctypes.byref(s)))
         return {k: getattr(s, k) for k, _ in ps_stats._fields_}
+
+    def schedule(self):
+        p, l, k = c_int32(0), c_int32(0), c_int64(0)
+        check(lib().ps_batch_schedule(self.h, ctypes.byref(p), ctypes.byref(l), ctypes.byref(k)))
+        return {"path": "wide" if p.value else "fused", "lanes_per_world": l.value, "kernel_launches": k.value}
 
     def debug_cycles(self):
         out = np.zeros((self.n_worlds, 8), dtype=np.uint64)

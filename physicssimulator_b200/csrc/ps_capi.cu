@@ -885,6 +885,16 @@ int ps_batch_stats(void* handle, ps_stats* out)
     return PS_OK;
 }
 
+int ps_batch_schedule(void* handle, int32_t* path, int32_t* lanes_per_world, int64_t* kernel_launches)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    if (path) *path = B->wide ? 1 : 0;
+    if (lanes_per_world) *lanes_per_world = B->threads;
+    if (kernel_launches) *kernel_launches = B->launches;
+    return PS_OK;
+}
+
 // debug/profiling: per-world phase cycles (8 x u64 per world: cyc[0..4], slowest step, sum K, sum levels)
 int ps_batch_debug_cycles(void* handle, unsigned long long* out)
 {
