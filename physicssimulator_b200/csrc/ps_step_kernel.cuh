@@ -82,6 +82,7 @@ struct KArgs {
     int exact_all_pairs;
     int restore_joints;
     int margin_ncap;      // cap of the hit count that scales a body's motion margin
+    double margin_scale;  // safety factor on the motion margin (a violated margin costs the world a second attempt)
     // joints, grouped per world
     const int* joff;      // n_worlds+1 (nullptr when no joints)
     const int* ja;
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
             // dt * (its new velocity): the margin covers n such moves, n estimated from the number of
             // colliding pairs the body was in during the previous step.
             {
-                const double mscale = attempt == 0 ? 1.0 : 8.0;
+                const double mscale = (attempt == 0 ? 1.0 : 8.0) * a.margin_scale;
                 for (int b = tid; b < Nw; b += T) {
                     const bool on = fast && b < N;
                     Par p;
