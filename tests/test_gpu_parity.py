@@ -285,3 +285,14 @@ def test_wide_path_second_order_integrator_and_many_worlds(monkeypatch):
     cfg = Configuration(StepConfig=StepConfiguration(RigidBodyIntegratorKind=1))
     worlds = [scenes.c3_mixed128(w, n_boxes=12, n_spheres=12)[0] for w in range(40)]
     _run(worlds, cfg, [1, 30, 90], "wide/second order", contacts=False)
+
+
+def test_joints_in_chunks_of_the_tile_width(monkeypatch):
+    """more joints per world than lanes per world: results are staged and committed after every joint has read"""
+    monkeypatch.setenv("PS_B200_TILE", "4")
+    worlds, joints = [], []
+    for w in range(5):
+        p, cfg, j = scenes.c4_chain32(w, n_links=11)
+        worlds.append(p)
+        joints.append(j)
+    _run(worlds, cfg, [1, 5, 12], "C4 chains, 4 lanes per world", joints=joints)
