@@ -62,7 +62,7 @@ PS_TABLE signed char kFaceSign[6] = {-1, 1, 1, -1, 1, -1};
 // ----------------------------------------------------------------------------------------
 // Integration (RigidBody.fs:202-220 -> Particle.fs:25-30 + RigidBody.fs:142-190)
 // ----------------------------------------------------------------------------------------
-PSN void integrate(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o)
+PSI void integrate(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o)
 {
     const double dt = sp.dt;
     d3 acc = scale(p.inv_mass, p.F);       // RigidBody.fs:210  totalForce / mass

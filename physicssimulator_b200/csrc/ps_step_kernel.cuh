@@ -243,7 +243,7 @@ PSD void record_pair(const Ctx& c, int i, int j, const Contact* cs, int nc)
 
 // predicted copy of body b, integrating it first if an earlier pair changed it (lazy refresh).
 // check_margin: the position is about to be used for detection under a culled pair list.
-PSN void get_pred(Ctx& c, int b, const Par& p, Dyn& out, bool check_margin)
+PSI void get_pred(Ctx& c, int b, const Par& p, Dyn& out, bool check_margin)
 {
     if (c.s.pvalid[b]) {
         ld_dyn(c.s.pred, c.N, b, out);
