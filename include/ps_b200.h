@@ -109,9 +109,12 @@ typedef struct {
                                      Seq.find / List.maxBy on nothing); treated as "no collision" here */
     double max_penetration;   /* max |penetration| seen */
     /* why a world-step left the wavefront path (sum = fallback_steps) */
-    int64_t fallback_margin_steps;   /* a motion margin was violated: retried with an 8x margin */
+    int64_t fallback_margin_steps;   /* a culled pair could not be ruled out any more: retried with an 8x margin */
     int64_t fallback_capacity_steps; /* near list or level table full: exact serial walk */
     int64_t fallback_static_steps;   /* a static body's pose still moved under integrate(): exact serial walk */
+    /* world-steps in which a body left its motion margin and its culled pairs were re-examined with the grown
+     * sphere; only those where a culled pair could no longer be ruled out count as fallback_margin_steps */
+    int64_t margin_verified_steps;
 } ps_stats;
 
 #define PS_MAX_CONTACTS 20 /* worst case of the reference clipper is 19 */

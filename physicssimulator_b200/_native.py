@@ -47,7 +47,8 @@ class ps_stats(ctypes.Structure):
     _fields_ = [("steps", c_int64), ("body_steps", c_int64), ("pairs_tested", c_int64), ("pairs_colliding", c_int64),
                 ("contacts", c_int64), ("fallback_steps", c_int64), ("nan_worlds", c_int64), ("contact_overflow", c_int64),
                 ("reference_exceptions", c_int64), ("max_penetration", c_double),
-                ("fallback_margin_steps", c_int64), ("fallback_capacity_steps", c_int64), ("fallback_static_steps", c_int64)]
+                ("fallback_margin_steps", c_int64), ("fallback_capacity_steps", c_int64), ("fallback_static_steps", c_int64),
+                ("margin_verified_steps", c_int64)]
 
 
 class NativeError(RuntimeError):

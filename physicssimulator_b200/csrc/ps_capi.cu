@@ -90,6 +90,7 @@ struct Batch {
     unsigned long long* d_tmp_pen = nullptr;
     double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // PS_B200_WIDE_PROF: setup, integrate, ss, sb, bb, resolve, tail, fused
     long long prof_steps = 0, prof_rounds = 0;
+    std::vector<float> prof_round;  // last profiled step: per round c0, c1, c2, detect ms, bb ms, resolve ms
     int *d_joff = nullptr, *d_ja = nullptr, *d_jb = nullptr;
     double *d_jla = nullptr, *d_jlb = nullptr;
     unsigned char* d_jlast = nullptr;
@@ -167,13 +168,13 @@ __global__ void apply_impulse_kernel(double* dyn, const double* par, const int* 
 __global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const double* par, int n_worlds, ps_stats* out)
 {
     unsigned long long steps = 0, tested = 0, hits = 0, contacts = 0, fallback = 0, overflow = 0, exc = 0, nanw = 0, bsteps = 0;
-    unsigned long long fbm = 0, fbc = 0, fbs = 0;
+    unsigned long long fbm = 0, fbc = 0, fbs = 0, ver = 0;
     double mp = 0.0;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_worlds; w += gridDim.x * blockDim.x) {
         const WorldStats& s = ws[w];
         steps += s.steps; tested += s.tested; hits += s.hits; contacts += s.contacts;
         fallback += s.fallback; overflow += s.overflow; exc += s.ref_exc; nanw += s.nan_flag ? 1 : 0;
-        fbm += s.fb_margin; fbc += s.fb_capacity; fbs += s.fb_static;
+        fbm += s.fb_margin; fbc += s.fb_capacity; fbs += s.fb_static; ver += s.verified;
         mp = fmax(mp, s.max_pen);
         int o = off[w], N = off[w + 1] - o, dynb = 0;
         const double* p = par + (size_t)o * kParF;
@@ -192,6 +193,7 @@ __global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const 
     atomicAdd((unsigned long long*)&out->fallback_margin_steps, fbm);
     atomicAdd((unsigned long long*)&out->fallback_capacity_steps, fbc);
     atomicAdd((unsigned long long*)&out->fallback_static_steps, fbs);
+    atomicAdd((unsigned long long*)&out->margin_verified_steps, ver);
     atomicMax((unsigned long long*)&out->max_penetration, (unsigned long long)__double_as_longlong(mp));
 }
 
@@ -291,7 +293,7 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_lists, (size_t)std::max<long long>(loff[B->n_worlds], 16)));
         CK(cudaMalloc(&B->d_lists_off, loff.size() * sizeof(long long)));
         CK(cudaMemcpy(B->d_lists_off, loff.data(), loff.size() * sizeof(long long), cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&B->d_cull, nb * 6 * sizeof(double)));
+        CK(cudaMalloc(&B->d_cull, nb * kCullF * sizeof(double)));
         CK(cudaMalloc(&B->d_row, (nb + (size_t)B->n_worlds + 1) * sizeof(int)));
         const size_t wpc = 32 / B->threads, grid = ((size_t)B->n_worlds + wpc - 1) / wpc;
         CK(cudaMalloc(&B->d_scratch, std::max<size_t>(grid, 1) * 32 * sizeof(PairScratch)));
@@ -331,6 +333,7 @@ int upload(Batch* B, bool with_state)
         CK(cudaMemcpy(B->d_isstat, isstat.data(), nb, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B->d_isbox, isbox.data(), nb, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B->d_always_fused, af.data(), nw, cudaMemcpyHostToDevice));
+        CK(cudaFuncSetAttribute(psw::wide_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psw::lvl_smem_bytes(B->max_n)));
         // the wide path pays one pass through memory per stage and ~5 launches per level: it wins when the batch
         // is large enough to fill the GPU per round
         B->wide = !B->cfg.exact_all_pairs && !(B->cfg.restore_joints && !B->joints.a.empty()) && B->n_bodies >= 500000;  // measured: C3 (2.1 M bodies) 24 vs 53 ms per step, C2 (0.27 M bodies) 3.9 vs 3.4 ms
@@ -528,6 +531,17 @@ int ps_batch_destroy(void* handle)
         fprintf(stderr, "[ps_b200 wide profile] steps %lld rounds/step %.1f | ms/step: setup %.3f (-) %.3f detect_stage1 %.3f (-) %.3f bb_full %.3f resolve %.3f tail %.3f fused %.3f\n",
                 B->prof_steps, (double)B->prof_rounds / B->prof_steps, B->prof_ms[0] / B->prof_steps, B->prof_ms[1] / B->prof_steps, B->prof_ms[2] / B->prof_steps,
                 B->prof_ms[3] / B->prof_steps, B->prof_ms[4] / B->prof_steps, B->prof_ms[5] / B->prof_steps, B->prof_ms[6] / B->prof_steps, B->prof_ms[7] / B->prof_steps);
+    if (getenv("PS_B200_WIDE_PROF") && !B->prof_round.empty()) {
+        std::vector<unsigned> hc(psw::kBuckets), sc(psw::kWideMaxLevels + 2);
+        cudaMemcpy(hc.data(), B->d_hit_cnt, hc.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
+        cudaMemcpy(sc.data(), B->d_surv_cnt, sc.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ps_b200 wide profile] last step, per round: pairs ss/sb/bb | bb survivors | hits ss/sb/bb | ms detect, bb, resolve\n");
+        for (size_t r = 0; r * 6 < B->prof_round.size(); r++) {
+            const float* q = &B->prof_round[r * 6];
+            fprintf(stderr, "  round %3zu: %7.0f %7.0f %7.0f | %7u | %7u %7u %7u | %.3f %.3f %.3f\n", r + 1, q[0], q[1], q[2], sc[r + 1],
+                    hc[(r + 1) * 4], hc[(r + 1) * 4 + 1], hc[(r + 1) * 4 + 2], q[3], q[4], q[5]);
+        }
+    }
     free_device(B);
     cudaStreamDestroy(B->stream);
     delete B;
@@ -572,10 +586,10 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
 {
     using namespace psw;
     WArgs a{};
-    a.n_worlds = B->n_worlds; a.n_bodies = B->n_bodies; a.off = B->d_off; a.body_world = B->d_body_world;
+    a.n_worlds = B->n_worlds; a.n_bodies = B->n_bodies; a.max_n = B->max_n; a.off = B->d_off; a.body_world = B->d_body_world;
     a.dyn = B->d_dyn; a.cur = B->d_cur; a.pred = B->d_pred; a.par = B->d_par; a.S = B->d_S; a.cull = B->d_cull;
     a.pvalid = B->d_pvalid; a.nhit = B->d_nhit; a.nprev = B->d_hitcnt; a.isstat = B->d_isstat; a.isbox = B->d_isbox;
-    a.last = B->d_last; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off;
+    a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off;
     a.K = B->d_K; a.maxl = B->d_maxl; a.wflags = B->d_wflags; a.always_fused = B->d_always_fused;
     a.bucket = B->d_bucket; a.bucket_cur = B->d_bucket_cur; a.entries = B->d_entries; a.entries_cap = B->entries_cap;
     a.hit_cnt = B->d_hit_cnt; a.hitlist = B->d_hitlist; a.cpool = B->d_cpool; a.cpool_cap = B->cpool_cap; a.cpool_cur = B->d_cpool_cur;
@@ -585,26 +599,29 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     a.sp = ka.sp; a.margin_ncap = ka.margin_ncap;
     a.margin_scale = ka.margin_scale;
     const int nb = B->n_bodies, nw = B->n_worlds;
-    const int gb = (nb + 127) / 128, gw = (nw + 63) / 64;
+    const int gb = (nb + 127) / 128, gw = (nw + 63) / 64, gl = (nw + psw::kLvlWorlds - 1) / psw::kLvlWorlds;
     const bool prof = getenv("PS_B200_WIDE_PROF") != nullptr;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
+    float lap_ms = 0.f;
     auto lap = [&](int cat) {  // profiling only: serialises the stream
         if (!prof) return;
         cudaEventRecord(pe1, st); cudaEventSynchronize(pe1);
         float ms = 0.f; cudaEventElapsedTime(&ms, pe0, pe1);
         B->prof_ms[cat] += ms;
+        lap_ms = ms;
         cudaEventRecord(pe0, st);
     };
+    if (prof) B->prof_round.clear();
     const int greset = (std::max(nw, kBuckets + 1) + 255) / 256;
     wide_reset<<<greset, 256, 0, st>>>(a);
     wide_predict<<<gb, 128, 0, st>>>(a);
     wide_near_count<<<gb, 128, 0, st>>>(a);
     wide_near_scan<<<gw, 64, 0, st>>>(a);
     wide_near_fill<<<gb, 128, 0, st>>>(a);
-    wide_levels<<<gw, psw::kLvlThreads, 0, st>>>(a);
+    wide_levels<<<gl, psw::kLvlThreads, psw::lvl_smem_bytes(B->max_n), st>>>(a);
     wide_bucket_scan<<<1, 32, 0, st>>>(a);
-    wide_scatter<<<gw, psw::kLvlThreads, 0, st>>>(a);
+    wide_scatter<<<gl, psw::kLvlThreads, 0, st>>>(a);
     CK(cudaMemcpyAsync(B->h_bucket, B->d_bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     B->launches += 8;
@@ -619,17 +636,21 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
         const unsigned nblk = (c0 + 127) / 128 + (c1 + 127) / 128 + (c2 + 127) / 128;
         wide_round_detect<<<nblk, 128, 0, st>>>(a, first, c0, c1, c2, r);
         lap(2);
+        if (prof) { B->prof_round.push_back((float)c0); B->prof_round.push_back((float)c1); B->prof_round.push_back((float)c2); B->prof_round.push_back(lap_ms); }
         if (c2) wide_round_bb<<<(c2 + 127) / 128, 128, 0, st>>>(a, first + c0 + c1, c2, r);  // threads past the survivor count exit
         lap(4);
+        if (prof) B->prof_round.push_back(c2 ? lap_ms : 0.f);
         wide_round_resolve<<<nblk, 128, 0, st>>>(a, first, c0, c1, c2, r);
         lap(5);
+        if (prof) B->prof_round.push_back(lap_ms);
         B->prof_rounds++;
         B->launches += 2 + (c2 != 0);
     }
+    wide_verify<<<gb, 128, 0, st>>>(a);
     wide_static_fold<<<gb, 128, 0, st>>>(a);
     wide_final<<<gb, 128, 0, st>>>(a);
     wide_account<<<gw, 64, 0, st>>>(a);
-    B->launches += 3;
+    B->launches += 4;
     lap(6);
     // worlds the wide pass gave up on: redo from the published state with the fused kernel
     KArgs kf = ka;

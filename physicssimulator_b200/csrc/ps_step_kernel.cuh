@@ -48,10 +48,12 @@ constexpr int kParF = 16;       // doubles of parameters per body
 constexpr int kMaxLevels = 1022;
 constexpr int kMaxStatics = 4;  // static bodies per world whose pairs run in parallel (more -> serial walk)
 constexpr int kMaxThreads = 128;
+constexpr int kCullF = 7;       // doubles of cull-sphere data per body: centre 3, radius vs sphere, radius vs box, margin^2, max deviation^2
 
 struct WorldStats {  // per world, accumulated over steps
     unsigned long long steps, tested, hits, contacts, fallback, overflow, ref_exc;
     unsigned long long fb_margin, fb_capacity, fb_static;
+    unsigned long long verified;  // world-steps in which a body left its margin and the culled pairs were re-examined
     double max_pen;
     int nan_flag, pad;
     // SM cycles of thread 0 per phase, summed over steps: predict+cull spheres, near list, levels+sort,
@@ -97,7 +99,7 @@ struct KArgs {
     int rec_pair_cap, rec_contact_cap;
     int max_n;                // largest world (sizes the shared-memory carve-up)
     // per-step lists of every world in global memory
-    double* cull;             // [total_bodies*6]: per world sx(3N) | rad_s(N) | rad_b(N) | marg2(N)
+    double* cull;             // [total_bodies*kCullF]: per world sx(3N) | rad_s(N) | rad_b(N) | marg2(N) | dev2(N)
     int* row;                 // [total_bodies + n_worlds]: per world N+1 row offsets of the near list
     int* lvl;                 // [n_worlds * (kMaxLevels+2)] level offsets
     unsigned short* last;     // [total_bodies] level of the last near pair of each body
@@ -119,6 +121,7 @@ struct Smem {
     double* rad_s;   // GLOBAL: N   cull radius against a sphere (margin included)
     double* rad_b;   // GLOBAL: N   cull radius against a box
     double* marg2;   // GLOBAL: N   squared margin
+    double* dev2;    // GLOBAL: N   largest squared distance of a predicted position from the sphere centre, once it exceeds marg2
     unsigned* near;  // GLOBAL: n_pairs  i | j<<16
     unsigned short* level;  // GLOBAL: n_pairs
     unsigned short* order;  // GLOBAL: n_pairs
@@ -202,7 +205,8 @@ PSD bool pose_fixed(const Dyn& a, const Dyn& b)
 
 // block-wide flags / counters in static shared memory
 struct BlockShared {
-    int violate;      // a margin was violated -> restart with a wider one
+    int violate;      // a body left its margin -> its culled pairs are re-examined after the wavefronts (phase V)
+    int redo;         // ... and one of them can no longer be ruled out -> restart with a wider margin
     int need_serial;  // a static pose moves / list full / too many levels -> exact serial walk
     int K, maxl, nstat;
     unsigned tested, hits, contacts, overflow, ref_exc;
@@ -241,6 +245,20 @@ PSD void record_pair(const Ctx& c, int i, int j, const Contact* cs, int nc)
     }
 }
 
+// A predicted position is what the reference tests in every pair of the body that comes up before its next
+// write-back, culled pairs included.  Inside the margin the cull stands; outside, the largest deviation is kept and
+// phase V re-examines the body's culled pairs with the sphere grown to it.  (The owner of the body at this level is
+// the only writer.)
+PSD void track_margin(Ctx& c, int b, d3 x)
+{
+    d3 d = x - mk(c.s.sx[b], c.s.sx[c.N + b], c.s.sx[2 * c.N + b]);
+    double dd = d.x * d.x + d.y * d.y + d.z * d.z;
+    if (!(dd <= c.s.marg2[b])) {
+        c.bs->violate = 1;
+        if (!(dd <= c.s.dev2[b])) c.s.dev2[b] = dd;  // a NaN sticks
+    }
+}
+
 // predicted copy of body b, integrating it first if an earlier pair changed it (lazy refresh).
 // check_margin: the position is about to be used for detection under a culled pair list.
 PSI void get_pred(Ctx& c, int b, const Par& p, Dyn& out, bool check_margin)
@@ -254,11 +272,7 @@ PSI void get_pred(Ctx& c, int b, const Par& p, Dyn& out, bool check_margin)
     integrate(cur, p, c.a->sp, out);
     st_dyn(c.s.pred, c.N, b, out);
     c.s.pvalid[b] = 1;
-    if (check_margin) {
-        d3 d = out.x - mk(c.s.sx[b], c.s.sx[c.N + b], c.s.sx[2 * c.N + b]);
-        double dd = d.x * d.x + d.y * d.y + d.z * d.z;
-        if (!(dd <= c.s.marg2[b])) c.bs->violate = 1;
-    }
+    if (check_margin) track_margin(c, b, out.x);
 }
 
 PSD void bump(unsigned char* p)  // saturating per-body hit counter (the body is owned by this thread at this level)
@@ -349,6 +363,23 @@ PSD bool near_test(const Smem& s, int N, int i, int j)
     return !(dd > r * r);  // NaN -> near
 }
 
+// phase V: how far the cull sphere of body y has to grow to hold every position y was predicted at
+PSD double cull_growth(double dev2, double marg2)
+{
+    if (dev2 <= marg2) return 0.0;
+    double g = sqrt(dev2) * (1.0 + 1e-6) + 1e-9 - sqrt(marg2) * (1.0 - 1e-6);  // rounded outwards
+    return g > 0.0 ? g : 0.0;
+}
+PSD bool near_test_grown(const Smem& s, int N, int i, int j, double gi, double gj)
+{
+    double dx = s.sx[i] - s.sx[j], dy = s.sx[N + i] - s.sx[N + j], dz = s.sx[2 * N + i] - s.sx[2 * N + j];
+    double dd = dx * dx + dy * dy + dz * dz;
+    double ri = (s.isbox[j] ? s.rad_b[i] : s.rad_s[i]) + gi;
+    double rj = (s.isbox[i] ? s.rad_b[j] : s.rad_s[j]) + gj;
+    double r = ri + rj;
+    return !(dd > r * r);
+}
+
 #ifndef PS_SCRATCH_GLOBAL
 #define PS_SCRATCH_GLOBAL 0  // 1: per-pair working arrays in a per-thread global record instead of the local stack
 #endif
@@ -391,8 +422,8 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
     carve(smem_raw + (size_t)tile * smem_bytes(a.max_n), N, c.s);
     Smem& s = c.s;
     {
-        double* cu = a.cull + (size_t)off * 6;
-        s.sx = cu; s.rad_s = cu + 3 * N; s.rad_b = cu + 4 * N; s.marg2 = cu + 5 * N;
+        double* cu = a.cull + (size_t)off * kCullF;
+        s.sx = cu; s.rad_s = cu + 3 * N; s.rad_b = cu + 4 * N; s.marg2 = cu + 5 * N; s.dev2 = cu + 6 * N;
         s.row = a.row + off + w;
         s.lvl_start = a.lvl + (size_t)w * (kMaxLevels + 2);
         s.last = a.last + off;
@@ -428,7 +459,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
     __syncwarp();
 
     unsigned long long t_steps = 0, t_tested = 0, t_hits = 0, t_contacts = 0, t_fallback = 0, t_overflow = 0, t_exc = 0;
-    unsigned long long t_fbm = 0, t_fbc = 0, t_fbs = 0;
+    unsigned long long t_fbm = 0, t_fbc = 0, t_fbs = 0, t_ver = 0;
     double t_maxpen = 0.0;
     unsigned long long cyc[5] = {0, 0, 0, 0, 0}, cyc_max = 0, sumK = 0, sumL = 0;
 
@@ -448,7 +479,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
             const bool serial = run && attempt == 2;
             if (run) {
                 if (tid == 0) {
-                    bs.violate = 0; bs.need_serial = 0; bs.K = 0; bs.maxl = 0;
+                    bs.violate = 0; bs.redo = 0; bs.need_serial = 0; bs.K = 0; bs.maxl = 0;
                     if (a.rec_counts) { a.rec_counts[2 * w] = 0; a.rec_counts[2 * w + 1] = 0; }
                 }
                 c.tested = c.hits = c.contacts = c.overflow = c.ref_exc = 0;
@@ -494,6 +525,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                         s.rad_s[b] = rs * slack + 1e-9 + m;
                         s.rad_b[b] = rb * slack + 1e-9 + m;
                         s.marg2[b] = m * m;
+                        s.dev2[b] = 0.0;
                         s.last[b] = 0;
                     }
                 }
@@ -625,8 +657,44 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
             __syncwarp();
             if (tid == 0 && live) { long long t = clock64(); cyc[3] += t - tk; tk = t; }
 
+            // ---- R: predicted copy of every body a pair changed after its last prediction: the position the reference
+            // tests in the body's remaining (culled) pairs, so it is held to the margin as well.  The final sweep (F)
+            // reuses the copy.
+            for (int b = tid; b < Nw; b += T) {
+                const bool need = fast && b < N && !s.pvalid[b];
+                Par p;
+                Dyn cur, pr;
+                if (need) {
+                    ld_par(s.par, N, b, p);
+                    ld_dyn(s.dyn, N, b, cur);
+                }
+                if (need) integrate(cur, p, sp, pr);
+                if (need) {
+                    st_dyn(s.pred, N, b, pr);
+                    s.pvalid[b] = 1;
+                    track_margin(c, b, pr.x);
+                }
+            }
+            __syncwarp();
+            // ---- V: a body left its margin.  A culled pair (b, x) stays impossible if the spheres grown to the largest
+            // deviations still do not touch; only a pair that was culled and now touches voids the step.
+            if (fast && bs.violate) {
+                for (int b = tid; b < N; b += T) {
+                    const double d2 = s.dev2[b], m2 = s.marg2[b];
+                    if (d2 <= m2) continue;
+                    if (!(d2 == d2)) { bs.redo = 1; continue; }
+                    const double gb = cull_growth(d2, m2);
+                    for (int x = 0; x < N; x++) {
+                        if (x == b || (s.isstat[b] && s.isstat[x])) continue;
+                        if (near_test(s, N, b, x)) continue;  // on the near list: tested where it stood
+                        if (near_test_grown(s, N, b, x, gb, cull_growth(s.dev2[x], s.marg2[x]))) { bs.redo = 1; break; }
+                    }
+                }
+                if (tid == 0 && live) t_ver++;
+            }
+            __syncwarp();  // (all lanes of the warp: tiles diverge above)
             if (fast) {
-                if (bs.violate) {  // restart from the published state with the wider margin (or serially)
+                if (bs.redo) {  // restart from the published state with the wider margin (or serially)
                     for (int k = tid; k < kDynF * N; k += T) s.dyn[k] = gdyn[k];
                     fb_reason = 1;
                     attempt++;
@@ -766,7 +834,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
         WorldStats& st = a.stats[w];
         st.steps += t_steps; st.tested += t_tested; st.hits += t_hits; st.contacts += t_contacts;
         st.fallback += t_fallback; st.overflow += t_overflow; st.ref_exc += t_exc;
-        st.fb_margin += t_fbm; st.fb_capacity += t_fbc; st.fb_static += t_fbs;
+        st.fb_margin += t_fbm; st.fb_capacity += t_fbc; st.fb_static += t_fbs; st.verified += t_ver;
         st.max_pen = fmax(st.max_pen, t_maxpen);
         st.nan_flag = bad ? 1 : 0;
         for (int k = 0; k < 5; k++) st.cyc[k] += cyc[k];

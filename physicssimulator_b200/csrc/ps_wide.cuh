@@ -33,21 +33,19 @@ using namespace psk;
 constexpr int kWideMaxLevels = 1022;
 constexpr int kBuckets = (kWideMaxLevels + 2) * 4;
 
-struct Entry {       // one near pair of the batch, sorted by (level, kind)
+struct __align__(16) Entry {  // one near pair of the batch, sorted by (level, kind); written and read as one uint4
     int w;           // world
     unsigned ij;     // i | j<<16 (ids inside the world)
-    unsigned k;      // index in the world's near list (for the hit flag)
-    unsigned nc;     // contacts found by the narrow phase
+    unsigned knc;    // index in the world's near list (for the hit flag, 24 bits) | contacts found by the narrow phase << 24
     unsigned cfirst; // first contact in the pool
 };
 
 struct WArgs {
-    int n_worlds, n_bodies;
+    int n_worlds, n_bodies, max_n;
     const int* off;
     const int* body_world;       // [NB]
     double* dyn; double* cur; double* pred; const double* par; double* S; double* cull;
     unsigned char* pvalid; unsigned char* nhit; unsigned char* nprev; const unsigned char* isstat; const unsigned char* isbox;  // [NB]
-    unsigned short* last;        // [NB]
     int* row;                    // per world N+1 at off+w
     unsigned char* lists; const long long* lists_off;
     int* K; int* maxl;           // per world
@@ -62,7 +60,7 @@ struct WArgs {
     unsigned* surv;              // [entries_cap] box-box pairs the quick test could not separate (listed from the bucket's start)
     unsigned* surv_cnt;          // per level
     WorldStats* stats;
-    unsigned* tmp;               // per world x 6: tested, hits, contacts, overflow, ref_exc, (pad) of THIS step's wide pass
+    unsigned* tmp;               // per world x 6: tested, hits, contacts, overflow, ref_exc, bodies that left their margin; THIS step's wide pass
     unsigned long long* tmp_pen; // per world: max |penetration| bits of this step
     RecPair* rec_pairs; RecContact* rec_contacts; int* rec_counts; int rec_pair_cap, rec_contact_cap;
     StepParams sp;
@@ -107,9 +105,9 @@ __global__ void __launch_bounds__(128) wide_predict(WArgs a)
     st_dyn(a.cur, 0, g, cur);
     integrate(cur, p, a.sp, pr);
     st_dyn(a.pred, 0, g, pr);
-    a.pvalid[g] = 1; a.nhit[g] = 0; a.last[g] = 0;
+    a.pvalid[g] = 1; a.nhit[g] = 0;
     if (p.is_static && !pose_fixed(cur, pr)) atomicOr(&a.wflags[w], (unsigned)WF_STATIC);
-    double* cu = a.cull + (size_t)o * 6;
+    double* cu = a.cull + (size_t)o * kCullF;
     cu[b] = pr.x.x; cu[N + b] = pr.x.y; cu[2 * N + b] = pr.x.z;
     double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
     double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
@@ -124,6 +122,7 @@ __global__ void __launch_bounds__(128) wide_predict(WArgs a)
     cu[3 * N + b] = rs * slack + 1e-9 + m;
     cu[4 * N + b] = rb * slack + 1e-9 + m;
     cu[5 * N + b] = m * m;
+    cu[6 * N + b] = 0.0;
 }
 
 // ---- B: near list ---------------------------------------------------------------------------------------
@@ -142,7 +141,7 @@ __global__ void __launch_bounds__(128) wide_near_count(WArgs a)
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= a.n_bodies) return;
     const int w = a.body_world[g], o = a.off[w], N = a.off[w + 1] - o, i = g - o;
-    const double* cu = a.cull + (size_t)o * 6;
+    const double* cu = a.cull + (size_t)o * kCullF;
     int cn = 0;
     for (int j = i + 1; j < N; j++) cn += wide_near_test(a, cu, o, N, i, j) ? 1 : 0;
     a.row[o + w + i] = cn;
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(128) wide_near_fill(WArgs a)
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= a.n_bodies) return;
     const int w = a.body_world[g], o = a.off[w], N = a.off[w + 1] - o, i = g - o;
-    const double* cu = a.cull + (size_t)o * 6;
+    const double* cu = a.cull + (size_t)o * kCullF;
     unsigned* near = w_near(a, w);
     unsigned char* hit = w_hit(a, w);
     int q = a.row[o + w + i];
@@ -175,46 +174,102 @@ __global__ void __launch_bounds__(128) wide_near_fill(WArgs a)
         }
 }
 
-// ---- C: levels + buckets (thread per world) ----------------------------------------------------------------
+// ---- C: levels + buckets ---------------------------------------------------------------------------------
 PSD int pair_kind(const WArgs& a, int o, int i, int j)  // 0 sphere-sphere, 1 sphere/box mixed, 2 box-box
 {
     return (int)a.isbox[o + i] + (int)a.isbox[o + j];
 }
-// Buckets are counted per CTA in shared memory first (64 worlds per CTA): 6 M pairs hammering ~150 global counters
-// took 2 ms per pass.
-constexpr int kLvlThreads = 64;
-__global__ void __launch_bounds__(kLvlThreads) wide_levels(WArgs a)
+// A CTA owns kLvlWorlds consecutive worlds.  The level of a near pair depends on the previous near pair of either
+// body, so one thread walks a world's list in order — with the per-body "last level" table in shared memory, so
+// that the dependent chain never waits on global memory (with the table in global memory this kernel took 2 ms per
+// C3 step).  Everything that is not a chain — the (level, kind) histogram here, the scatter below — is done by
+// the whole CTA with coalesced reads of the lists and warp-aggregated shared-memory counters.
+constexpr int kLvlWorlds = 32;
+constexpr int kLvlThreads = 128;
+__host__ __device__ inline int lvl_stride(int max_n) { return 2 * ((((max_n + 1) / 2)) | 1); }  // unsigned shorts per world; odd word count
+__host__ __device__ inline size_t lvl_smem_bytes(int max_n) { return (size_t)kLvlWorlds * lvl_stride(max_n) * sizeof(unsigned short); }
+
+// one pass of the CTA over the near lists of its worlds: f(bucket) per pair, all lanes of a warp call f together
+template <class F>
+__device__ __forceinline__ void for_cta_pairs(const WArgs& a, int w0, int wend, F f)
 {
-    __shared__ unsigned hist[kBuckets];
-    for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads) hist[b] = 0;
-    __syncthreads();
-    int w = blockIdx.x * kLvlThreads + threadIdx.x;
-    if (w < a.n_worlds && !a.wflags[w]) {
+    for (int w = w0; w < wend; w++) {
+        if (__ldcg(&a.wflags[w])) continue;  // CTA-uniform (read past L1: a thread of this CTA may just have set it)
         const int o = a.off[w], K = a.K[w];
         const unsigned* near = w_near(a, w);
-        unsigned short* level = w_level(a, w);
-        int maxl = 0;
-        for (int k = 0; k < K; k++) {
-            unsigned ij = near[k];
-            int i = ij & 0xffff, j = ij >> 16;
-            int li = a.isstat[o + i] ? 0 : a.last[o + i];
-            int lj = a.isstat[o + j] ? 0 : a.last[o + j];
-            int l = (li > lj ? li : lj) + 1;
-            level[k] = (unsigned short)l;
-            if (!a.isstat[o + i]) a.last[o + i] = (unsigned short)l;
-            if (!a.isstat[o + j]) a.last[o + j] = (unsigned short)l;
-            if (l > maxl) maxl = l;
-        }
-        if (maxl > kWideMaxLevels) {
-            atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY);
-        } else {
-            a.maxl[w] = maxl;
-            for (int k = 0; k < K; k++) {
-                unsigned ij = near[k];
-                atomicAdd(&hist[level[k] * 4 + pair_kind(a, o, ij & 0xffff, ij >> 16)], 1u);
+        const unsigned short* level = w_level(a, w);
+        for (int k0 = 0; k0 < K; k0 += kLvlThreads) {  // warp-uniform trip count
+            const int k = k0 + (int)threadIdx.x;
+            const bool valid = k < K;
+            unsigned ij = 0; int b = -1;
+            if (valid) {
+                ij = near[k];
+                b = (int)level[k] * 4 + pair_kind(a, o, ij & 0xffff, ij >> 16);
             }
+            f(w, k, ij, b, valid);
         }
     }
+}
+// add 1 to counter[b] for every valid lane; returns the lane's slot (old value + rank among the lanes of the same b)
+__device__ __forceinline__ unsigned warp_agg_inc(unsigned* counter, int b, bool valid)
+{
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? b : -1 - (int)(threadIdx.x & 31));
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (valid && lane == leader) base = atomicAdd(&counter[b], (unsigned)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (unsigned)__popc(peers & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(kLvlThreads) wide_levels(WArgs a)
+{
+    extern __shared__ __align__(16) unsigned char lv_raw[];
+    __shared__ unsigned hist[kBuckets];
+    unsigned short* lastS = reinterpret_cast<unsigned short*>(lv_raw);  // per body: bit15 static | last level
+    const int stride = lvl_stride(a.max_n);
+    const int w0 = blockIdx.x * kLvlWorlds, wend = min(w0 + kLvlWorlds, a.n_worlds);
+    for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads) hist[b] = 0;
+    for (int g = a.off[w0] + (int)threadIdx.x; g < a.off[wend]; g += kLvlThreads) {
+        const int w = a.body_world[g];
+        lastS[(w - w0) * stride + (g - a.off[w])] = a.isstat[g] ? 0x8000 : 0;
+    }
+    __syncthreads();
+    const int w = w0 + (int)threadIdx.x;
+    if (threadIdx.x < kLvlWorlds && w < wend && !a.wflags[w]) {
+        const int K = a.K[w];
+        const unsigned* __restrict__ near = w_near(a, w);
+        unsigned short* __restrict__ level = w_level(a, w);
+        unsigned short* L = lastS + threadIdx.x * stride;
+        int maxl = 0;
+        bool over = false;
+        for (int k0 = 0; k0 < K && !over; k0 += 4) {
+            unsigned q[4];
+            if (k0 + 4 <= K) {
+                uint4 t = *reinterpret_cast<const uint4*>(near + k0);  // the list starts 16-byte aligned
+                q[0] = t.x; q[1] = t.y; q[2] = t.z; q[3] = t.w;
+            } else {
+                for (int u = 0; u < 4; u++) q[u] = (k0 + u < K) ? near[k0 + u] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (k0 + u >= K) break;
+                const int i = q[u] & 0xffff, j = q[u] >> 16;
+                const unsigned vi = L[i], vj = L[j];
+                const int li = (vi & 0x8000u) ? 0 : (int)vi, lj = (vj & 0x8000u) ? 0 : (int)vj;
+                const int l = (li > lj ? li : lj) + 1;
+                if (l > kWideMaxLevels) { over = true; break; }
+                level[k0 + u] = (unsigned short)l;
+                if (!(vi & 0x8000u)) L[i] = (unsigned short)l;
+                if (!(vj & 0x8000u)) L[j] = (unsigned short)l;
+                if (l > maxl) maxl = l;
+            }
+        }
+        if (over) atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY);
+        else a.maxl[w] = maxl;
+    }
+    __syncthreads();  // level[] of the CTA's worlds is complete (and wflags settled for them)
+    __threadfence_block();
+    for_cta_pairs(a, w0, wend, [&](int, int, unsigned, int b, bool valid) { warp_agg_inc(hist, b, valid); });
     __syncthreads();
     for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads)
         if (hist[b]) atomicAdd(&a.bucket[b], hist[b]);
@@ -232,34 +287,26 @@ __global__ void wide_bucket_scan(WArgs a)  // one warp: kBuckets is ~4 K
     for (int b = lane * per; b < (lane + 1) * per; b++) { unsigned t = a.bucket[b]; a.bucket[b] = base; base += t; }
     if (lane == 31) a.bucket[kBuckets] = base;
 }
-__global__ void __launch_bounds__(kLvlThreads) wide_scatter(WArgs a)  // thread per world, CTA-local reservation of ranges
+__global__ void __launch_bounds__(kLvlThreads) wide_scatter(WArgs a)  // same CTA -> worlds map as wide_levels
 {
     __shared__ unsigned cnt[kBuckets];   // pairs of this CTA per bucket, then the CTA's base inside the bucket
     __shared__ unsigned cur[kBuckets];
     for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads) { cnt[b] = 0; cur[b] = 0; }
-    __syncthreads();
-    const int w = blockIdx.x * kLvlThreads + threadIdx.x;
-    const bool over = a.bucket[kBuckets] > a.entries_cap;
-    bool live = w < a.n_worlds && !a.wflags[w];
-    if (live && over) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); live = false; }
-    const int o = live ? a.off[w] : 0, K = live ? a.K[w] : 0;
-    const unsigned* near = live ? w_near(a, w) : nullptr;
-    const unsigned short* level = live ? w_level(a, w) : nullptr;
-    for (int k = 0; k < K; k++) {
-        unsigned ij = near[k];
-        atomicAdd(&cnt[level[k] * 4 + pair_kind(a, o, ij & 0xffff, ij >> 16)], 1u);
+    const int w0 = blockIdx.x * kLvlWorlds, wend = min(w0 + kLvlWorlds, a.n_worlds);
+    if (a.bucket[kBuckets] > a.entries_cap) {  // the sorted list does not fit: the fused kernel takes the step
+        for (int w = w0 + (int)threadIdx.x; w < wend; w += kLvlThreads) atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY);
+        return;
     }
+    __syncthreads();
+    for_cta_pairs(a, w0, wend, [&](int, int, unsigned, int b, bool valid) { warp_agg_inc(cnt, b, valid); });
     __syncthreads();
     for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads)
         if (cnt[b]) cnt[b] = a.bucket[b] + atomicAdd(&a.bucket_cur[b], cnt[b]);
     __syncthreads();
-    for (int k = 0; k < K; k++) {
-        unsigned ij = near[k];
-        int b = level[k] * 4 + pair_kind(a, o, ij & 0xffff, ij >> 16);
-        unsigned pos = cnt[b] + atomicAdd(&cur[b], 1u);
-        Entry e; e.w = w; e.ij = ij; e.k = (unsigned)k; e.nc = 0; e.cfirst = 0;
-        a.entries[pos] = e;
-    }
+    for_cta_pairs(a, w0, wend, [&](int w, int k, unsigned ij, int b, bool valid) {
+        const unsigned slot = warp_agg_inc(cur, b, valid);
+        if (valid) *reinterpret_cast<uint4*>(&a.entries[cnt[b] + slot]) = make_uint4((unsigned)w, ij, (unsigned)k, 0u);
+    });
 }
 
 // ---- rounds ---------------------------------------------------------------------------------------------
@@ -328,7 +375,7 @@ __device__ __forceinline__ void wide_detect_body(const WArgs& a, unsigned first,
     unsigned cf = atomicAdd(&a.cpool_cur[level], (unsigned)nc);
     if (cf + (unsigned)nc > a.cpool_cap) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); return; }
     for (int k = 0; k < nc; k++) a.cpool[cf + k] = sc.cs[k];
-    e.nc = (unsigned)nc; e.cfirst = cf;
+    e.knc |= (unsigned)nc << 24; e.cfirst = cf;
     unsigned slot = atomicAdd(&a.hit_cnt[level * 4 + KIND], 1u);
     a.hitlist[first + slot] = ei;
     atomicAdd(&tm[1], 1u);
@@ -376,7 +423,7 @@ __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first
     if (si) di.L = mk(0.0, 0.0, 0.0);
     if (sj) dj.L = mk(0.0, 0.0, 0.0);
     if (KIND == 2) {
-        const int nc = (int)e.nc;
+        const int nc = (int)(e.knc >> 24);
         Contact cs[PS_MAX_CONTACTS];
         CPData cp[PS_MAX_CONTACTS];
         for (int k = 0; k < nc; k++) cs[k] = a.cpool[e.cfirst + k];
@@ -387,9 +434,9 @@ __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first
         cs[0] = a.cpool[e.cfirst];
         resolve_t<1>(di, pi, dj, pj, cs, 1, cp, a.sp);
     }
-    w_hit(a, w)[e.k] = 1;
+    w_hit(a, w)[e.knc & 0xffffffu] = 1;
     double* Sw = a.S + (size_t)o * 3 * kMaxStatics;
-    const double* cu = a.cull + (size_t)o * 6;
+    double* cu = a.cull + (size_t)o * kCullF;
 #pragma unroll 1
     for (int side = 0; side < 2; side++) {
         const int b = side ? j : i, other = side ? i : j;
@@ -406,11 +453,11 @@ __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first
         Dyn pr;
         integrate(d, p, a.sp, pr);
         st_dyn(a.pred, 0, o + b, pr);  // pvalid stays 1: the predicted copy is current again
-        if ((int)a.last[o + b] > level) {  // a later near pair will test this body at pr.x
-            d3 dd = pr.x - mk(cu[b], cu[N + b], cu[2 * N + b]);
-            double q = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
-            if (!(q <= cu[5 * N + b])) atomicOr(&a.wflags[w], (unsigned)WF_MARGIN);
-        }
+        // pr.x is where the reference tests the body in every pair that comes up before its next write-back, culled
+        // pairs included: outside the margin the largest deviation is kept for wide_verify (this thread owns the body)
+        d3 dd = pr.x - mk(cu[b], cu[N + b], cu[2 * N + b]);
+        double q = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
+        if (!(q <= cu[5 * N + b]) && !(q <= cu[6 * N + b])) cu[6 * N + b] = q;  // a NaN sticks
     }
 }
 
@@ -438,6 +485,35 @@ __global__ void __launch_bounds__(128) wide_round_resolve(WArgs a, unsigned firs
     if (blk < b0) wide_resolve_body<0>(a, first, level, blk * 128 + threadIdx.x);
     else if (blk < b0 + b1) wide_resolve_body<1>(a, first + c0, level, (blk - b0) * 128 + threadIdx.x);
     else wide_resolve_body<2>(a, first + c0 + c1, level, (blk - b0 - b1) * 128 + threadIdx.x);
+}
+
+// ---- V: bodies that left their margin (thread per body).  A culled pair (b, x) stays impossible if the spheres grown
+// to the largest deviations still do not touch; only a pair that was culled and now touches sends the world to the
+// fused kernel's wider-margin retry.
+__global__ void __launch_bounds__(128) wide_verify(WArgs a)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n_bodies) return;
+    const int w = a.body_world[g];
+    const int o = a.off[w], N = a.off[w + 1] - o, b = g - o;
+    const double* cu = a.cull + (size_t)o * kCullF;
+    const double d2 = cu[6 * N + b], m2 = cu[5 * N + b];
+    if (d2 <= m2) return;
+    if (a.wflags[w]) return;
+    atomicAdd(&a.tmp[6 * (size_t)w + 5], 1u);
+    if (!(d2 == d2)) { atomicOr(&a.wflags[w], (unsigned)WF_MARGIN); return; }
+    const double gb = cull_growth(d2, m2);
+    for (int x = 0; x < N; x++) {
+        if (x == b) continue;
+        if (wide_near_test(a, cu, o, N, b, x)) continue;  // on the near list: tested where it stood
+        const double gx = cull_growth(cu[6 * N + x], cu[5 * N + x]);
+        double dx = cu[b] - cu[x], dy = cu[N + b] - cu[N + x], dz = cu[2 * N + b] - cu[2 * N + x];
+        double dd = dx * dx + dy * dy + dz * dz;
+        double rb = (a.isbox[o + x] ? cu[4 * N + b] : cu[3 * N + b]) + gb;
+        double rx = (a.isbox[o + b] ? cu[4 * N + x] : cu[3 * N + x]) + gx;
+        double r = rb + rx;
+        if (!(dd > r * r)) { atomicOr(&a.wflags[w], (unsigned)WF_MARGIN); return; }
+    }
 }
 
 // ---- E: static bodies: L = fold over their colliding pairs in pair order (thread per body, statics only) -----
@@ -505,6 +581,7 @@ __global__ void wide_account(WArgs a)
     if (!f) {  // the wide pass stands: commit its counters
         const unsigned* tm = a.tmp + 6 * (size_t)w;
         st.steps++; st.tested += tm[0]; st.hits += tm[1]; st.contacts += tm[2]; st.overflow += tm[3]; st.ref_exc += tm[4];
+        if (tm[5]) st.verified++;
         st.max_pen = fmax(st.max_pen, __longlong_as_double((long long)a.tmp_pen[w]));
         return;
     }

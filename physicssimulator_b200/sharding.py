@@ -8,7 +8,7 @@ from typing import Dict, Tuple
 
 SUM_KEYS = ("steps", "body_steps", "pairs_tested", "pairs_colliding", "contacts", "fallback_steps", "nan_worlds",
             "contact_overflow", "reference_exceptions", "fallback_margin_steps", "fallback_capacity_steps",
-            "fallback_static_steps")
+            "fallback_static_steps", "margin_verified_steps")
 MAX_KEYS = ("max_penetration",)
 
 

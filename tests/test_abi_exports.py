@@ -39,7 +39,7 @@ def test_config_struct_layout_matches_ctypes():
     from physicssimulator_b200.configuration import ps_step_config
     assert ctypes.sizeof(ps_step_config) == 5 * 8 + 8 * 4
     from physicssimulator_b200._native import ps_stats
-    assert ctypes.sizeof(ps_stats) == 13 * 8
+    assert ctypes.sizeof(ps_stats) == 14 * 8
 
 
 def test_product_never_touches_the_oracle():

@@ -296,3 +296,26 @@ def test_joints_in_chunks_of_the_tile_width(monkeypatch):
         worlds.append(p)
         joints.append(j)
     _run(worlds, cfg, [1, 5, 12], "C4 chains, 4 lanes per world", joints=joints)
+
+
+@pytest.mark.parametrize("path,tile", [("fused", "4"), ("fused", "16"), ("fused", "32"), ("wide", "8")])
+def test_tight_margins_exercise_the_verification_and_the_retry(monkeypatch, path, tile):
+    """a motion margin far too small: bodies leave their cull spheres all the time, so the culled pairs are re-examined
+    (phase V / wide_verify) and some world-steps restart with the wider margin — the result is still the oracle's"""
+    from physicssimulator_b200.simulator import BatchSimulator
+    monkeypatch.setenv("PS_B200_PATH", path)
+    monkeypatch.setenv("PS_B200_TILE", tile)
+    monkeypatch.setenv("PS_B200_MSCALE", "0.02")
+    monkeypatch.setenv("PS_B200_NCAP", "0")
+    worlds = [scenes.c3_mixed128(w, n_boxes=24, n_spheres=24)[0] for w in range(7)]
+    cfg = scenes.c3_mixed128(0)[1]
+    sim = BatchSimulator(worlds, cfg, device=0)
+    oracles = _oracle_worlds(worlds, cfg)
+    for n in (1, 30, 90):
+        sim.Step(n)
+        for o in oracles:
+            o.step(n)
+        _compare(sim, oracles, f"tight margins {path}/{tile} +{n}", False)
+    st = sim.Stats()
+    assert st["margin_verified_steps"] > 0, st
+    sim.close()
