@@ -531,6 +531,16 @@ int ps_batch_destroy(void* handle)
         fprintf(stderr, "[ps_b200 wide profile] steps %lld rounds/step %.1f | ms/step: setup %.3f (-) %.3f detect_stage1 %.3f (-) %.3f bb_full %.3f resolve %.3f tail %.3f fused %.3f\n",
                 B->prof_steps, (double)B->prof_rounds / B->prof_steps, B->prof_ms[0] / B->prof_steps, B->prof_ms[1] / B->prof_steps, B->prof_ms[2] / B->prof_steps,
                 B->prof_ms[3] / B->prof_steps, B->prof_ms[4] / B->prof_steps, B->prof_ms[5] / B->prof_steps, B->prof_ms[6] / B->prof_steps, B->prof_ms[7] / B->prof_steps);
+#ifdef PS_PROF_CLK
+    {
+        unsigned long long sm[32], mx[32], cn[32];
+        cudaMemcpyFromSymbol(sm, psp::g_clk_sum, sizeof(sm)); cudaMemcpyFromSymbol(mx, psp::g_clk_max, sizeof(mx)); cudaMemcpyFromSymbol(cn, psp::g_clk_cnt, sizeof(cn));
+        const char* nm[32] = {"bb: boxes+face axes", "bb: edge axes", "bb: face setup", "bb: clipping", "bb: contacts", "bb: edge contact", "", "", "bbkernel: loads", "bbkernel: detect_bb total", "", "",
+                              "resolve: loads", "resolve: contact loads", "resolve: solve", "resolve: write-back + 2 integrations"};
+        for (int i = 0; i < 16; i++)
+            if (cn[i]) fprintf(stderr, "[clk] %-38s n=%9llu mean %8.0f max %8llu cycles\n", nm[i], cn[i], (double)sm[i] / cn[i], mx[i]);
+    }
+#endif
     if (getenv("PS_B200_WIDE_PROF") && !B->prof_round.empty()) {
         std::vector<unsigned> hc(psw::kBuckets), sc(psw::kWideMaxLevels + 2);
         cudaMemcpy(hc.data(), B->d_hit_cnt, hc.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
@@ -558,7 +568,7 @@ static void fill_kargs(Batch* B, KArgs& a, int n_steps)
     a.exact_all_pairs = B->cfg.exact_all_pairs;
     a.restore_joints = B->cfg.restore_joints;
     a.margin_ncap = 16;
-    a.margin_scale = 2.0;  // measured on C2: 1.0 -> 3.26 ms (0.8 % of world-steps restart), 2.0 -> 3.11 ms, 3.0 -> 3.42 ms (more near pairs)
+    a.margin_scale = 1.0;  // with margins verified after the fact (phase V): C2 2.0 -> 2.25 ms, 1.0 -> 2.11 ms, 0.7 -> 3.36 ms (10 % of world-steps restart); C3 20.1, 18.8, 29.7 (0.5)
     if (const char* e = getenv("PS_B200_MSCALE")) a.margin_scale = atof(e);  // tuning knob
     if (const char* e = getenv("PS_B200_NCAP")) a.margin_ncap = std::max(0, std::min(255, atoi(e)));  // tuning knob
     a.joff = B->d_joff; a.ja = B->d_ja; a.jb = B->d_jb; a.jla = B->d_jla; a.jlb = B->d_jlb; a.jlast = B->d_jlast;

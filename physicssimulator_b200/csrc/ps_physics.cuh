@@ -14,6 +14,18 @@
 namespace psp {
 using namespace psm;
 
+// -DPS_PROF_CLK: SM-cycle laps inside the pair routines of the batch-wide kernels (tools only; off in the product)
+#if defined(PS_PROF_CLK) && defined(__CUDACC__)
+__device__ unsigned long long g_clk_sum[32], g_clk_max[32], g_clk_cnt[32];
+#endif
+#if defined(PS_PROF_CLK) && defined(__CUDA_ARCH__)
+#define PS_CLK_BEGIN(on) long long clk_t0_ = clock64(); const bool clk_on_ = (on);
+#define PS_CLK(i) { if (clk_on_) { long long t_ = clock64(); unsigned long long d_ = (unsigned long long)(t_ - clk_t0_); atomicAdd(&g_clk_sum[i], d_); atomicMax(&g_clk_max[i], d_); atomicAdd(&g_clk_cnt[i], 1ull); clk_t0_ = clock64(); } }
+#else
+#define PS_CLK_BEGIN(on)
+#define PS_CLK(i)
+#endif
+
 // step parameters in kernel-argument form
 struct StepParams {
     double eps, baumgarte, slop, max_corr, dt;
@@ -104,7 +116,7 @@ struct OBox {
     d3 A, B, C, x;
     d3 n[6];  // world face normals (Box.fs:42-49 order)
 };
-PSN void make_obox(const Dyn& b, const Par& p, OBox& ob)
+PSD void make_obox_i(const Dyn& b, const Par& p, OBox& ob)
 {
     double hx = p.dims[0] / 2.0, hy = p.dims[1] / 2.0, hz = p.dims[2] / 2.0;
     ob.A = mk(b.R.a[0] * hx, b.R.a[3] * hx, b.R.a[6] * hx);
@@ -119,6 +131,7 @@ PSN void make_obox(const Dyn& b, const Par& p, OBox& ob)
         ob.n[f] = mulMV(b.R, local) + mk(0.0, 0.0, 0.0);  // toWorldCoordinates orientation zero (OrientedBox.fs:18-21)
     }
 }
+PSN void make_obox(const Dyn& b, const Par& p, OBox& ob) { make_obox_i(b, p, ob); }
 // world vertex k of Box.fs:23-32 (PointwiseMultiply by the half sizes, then toWorldCoordinates)
 PSD d3 box_vertex(const OBox& ob, int k)
 {
@@ -145,7 +158,7 @@ struct PairScratch {
 
 // min/max of the 8 vertex projections (OrientedBox.Vertices order is irrelevant: only the two values are used).
 // The partial sums of the vertex formula are shared down the sign tree: 2 + 4 + 8 additions per component.
-PSN void project_box(const OBox& ob, d3 axis, double& mn, double& mx)
+PSD void project_box_i(const OBox& ob, d3 axis, double& mn, double& mx)
 {
     const d3 A = ob.A, B = ob.B, C = ob.C, x = ob.x;
     bool first = true;
@@ -172,6 +185,13 @@ PSN void project_box(const OBox& ob, d3 axis, double& mn, double& mx)
     mx = hi;
 }
 
+PSN void project_box(const OBox& ob, d3 axis, double& mn, double& mx) { project_box_i(ob, axis, mn, mx); }
+template <bool F> PSD void pbox(const OBox& ob, d3 axis, double& mn, double& mx)
+{
+    if (F) project_box_i(ob, axis, mn, mx);
+    else project_box(ob, axis, mn, mx);
+}
+
 // ----------------------------------------------------------------------------------------
 // GraphicsUtils (Utilities/GraphicsUtils.fs)
 // ----------------------------------------------------------------------------------------
@@ -182,7 +202,7 @@ PSD d3 closest_on_edge(d3 a, d3 b, d3 pos)  // :9-24
     t = fmax_net(0.0, fmin_net(1.0, t));
     return a + scale(t, ab);
 }
-PSN d3 closest_on_quad(d3 pos, const d3 q[4])  // :26-37, edges (last,first),(0,1),(1,2),(2,3); first min
+PSD d3 closest_on_quad_i(d3 pos, const d3 q[4])  // :26-37, edges (last,first),(0,1),(1,2),(2,3); first min
 {
     d3 best = closest_on_edge(q[3], q[0], pos);
     d3 d = pos - best;
@@ -199,7 +219,8 @@ PSN d3 closest_on_quad(d3 pos, const d3 q[4])  // :26-37, edges (last,first),(0,
     }
     return best;
 }
-PSN bool plane_edge_hit(double eps, d3 pn, double pd, d3 s, d3 e, d3& out)  // :41-63
+PSN d3 closest_on_quad(d3 pos, const d3 q[4]) { return closest_on_quad_i(pos, q); }
+PSD bool plane_edge_hit_i(double eps, d3 pn, double pd, d3 s, d3 e, d3& out)  // :41-63
 {
     d3 ab = e - s;
     double ab_p = dot(pn, ab);
@@ -212,6 +233,12 @@ PSN bool plane_edge_hit(double eps, d3 pn, double pd, d3 s, d3 e, d3& out)  // :
     }
     return false;
 }
+PSN bool plane_edge_hit(double eps, d3 pn, double pd, d3 s, d3 e, d3& out) { return plane_edge_hit_i(eps, pn, pd, s, e, out); }
+template <bool F> PSD bool pehit(double eps, d3 pn, double pd, d3 s, d3 e, d3& out)
+{
+    return F ? plane_edge_hit_i(eps, pn, pd, s, e, out) : plane_edge_hit(eps, pn, pd, s, e, out);
+}
+template <bool F> PSD d3 cquad(d3 pos, const d3 q[4]) { return F ? closest_on_quad_i(pos, q) : closest_on_quad(pos, q); }
 PSD bool in_plane(d3 pn, double pd, d3 p) { return (dot(pn, p) - pd) >= 0.0; }  // :65-66
 PSD void tangents(d3 n, d3& t1, d3& t2)  // :112-123
 {
@@ -225,42 +252,51 @@ PSD void tangents(d3 n, d3& t1, d3& t2)  // :112-123
 // Narrow phase
 // ----------------------------------------------------------------------------------------
 // detectSphereSphereCollision (CollisionDetection.fs:186-205)
-PSN int detect_ss(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, Contact* out)
+template <bool F>
+PSD int detect_ss_t(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, Contact* out)
 {
     d3 d = b1.x - b2.x;
-    double dist = norm(d);
+    double dist = norm_t<F>(d);
     double r1 = p1.dims[0], r2 = p2.dims[0];
     if (dist > r1 + r2) return 0;
-    d3 n = normalize(d);
+    // normalize(d) = Normalize(2.0): same norm as `dist` (same routine, same input): reuse it
+    d3 n = (dist == 0.0) ? d : scale(1.0 / dist, d);
     d3 cp1 = b1.x + scale(r1, -n);
     d3 cp2 = b2.x + scale(r2, n);
     d3 cp = cp1 + scale(1.0 / 2.0, cp2 - cp1);
     out[0].n = n;
     out[0].p = cp;
-    out[0].pen = norm(cp1 - cp2);
+    out[0].pen = norm_t<F>(cp1 - cp2);
     out[0].feat = 0u;
     return 1;
+}
+PSN int detect_ss(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, Contact* out)
+{
+    return detect_ss_t<false>(b1, p1, b2, p2, out);
 }
 
 // SAT.SphereBox.tryFindSeparatingAxis (SAT.fs:108-151) + detectedSphereBoxCollision
 // (CollisionDetection.fs:166-184). Normal returned "from box". err set where the reference throws.
-PSN int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Par& bp, double eps, Contact* out,
-                          int& face, int& err, OBox& ob)
+template <bool F>
+PSD int detect_sphere_box_t(const Dyn& sb, const Par& sp_, const Dyn& bb, const Par& bp, double eps, Contact* out,
+                            int& face, int& err, OBox& ob)
 {
-    make_obox(bb, bp, ob);
+    if (F) make_obox_i(bb, bp, ob);
+    else make_obox(bb, bp, ob);
     double r = sp_.dims[0];
     double best_pen = 0.0;
     int best = -1;
+    d3 nb = mk(0.0, 0.0, 0.0);
     // The six face normals come in +- pairs (f, f+1) and n[f+1] == 0.0 - n[f] bit for bit (Box.fs:42-49, both are
     // R*(+-e_k) + 0).  A dot product against the negated axis is 0.0 - (the dot product): every product flips
     // sign and a zero-started sum is never -0.0.  So one projection pass serves both axes of a pair.
-#pragma unroll 1
+#pragma unroll (F ? 3 : 1)
     for (int fp = 0; fp < 6; fp += 2) {
         d3 axis = ob.n[fp];
         double a0, b0;
-        project_box(ob, axis, a0, b0);
+        pbox<F>(ob, axis, a0, b0);
         double c0 = dot(axis, sb.x);
-#pragma unroll 1
+#pragma unroll (F ? 2 : 1)
         for (int h = 0; h < 2; h++) {
             double a = h ? 0.0 - b0 : a0, b = h ? 0.0 - a0 : b0, c = h ? 0.0 - c0 : c0;
             double cp = c + r, cm = c - r;
@@ -276,14 +312,14 @@ PSN int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Pa
             if (best < 0 || pen < best_pen) {
                 best = fp + h;
                 best_pen = pen;
+                nb = ob.n[fp + h];
             }
         }
     }
-    d3 nb = ob.n[best];
     d3 endP = sb.x - scale(r, nb);
     double pd = dot(nb, face_vertex(ob, best, 0));  // Face.toPlane (Entities/Base.fs:27-29)
     d3 pos;
-    if (!plane_edge_hit(eps, nb, pd, sb.x, endP, pos)) {
+    if (!pehit<F>(eps, nb, pd, sb.x, endP, pos)) {
         err = 1;  // Option.get of None
         return 0;
     }
@@ -292,6 +328,11 @@ PSN int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Pa
     out[0].pen = best_pen;
     face = best;
     return 1;
+}
+PSN int detect_sphere_box(const Dyn& sb, const Par& sp_, const Dyn& bb, const Par& bp, double eps, Contact* out,
+                          int& face, int& err, OBox& ob)
+{
+    return detect_sphere_box_t<false>(sb, sp_, bb, bp, eps, out, face, err, ob);
 }
 
 // SAT.tryGetCollisionDataForAxis (SAT.fs:155-183) on precomputed projection ranges
@@ -315,40 +356,52 @@ PSD bool sat_ranges(double a, double b, double c, double d, double& pen, bool& f
 // (SAT.fs:185-198 `sequence`), whichever it is.  Tries the face axis of each box that looks most along the centre
 // offset, with the reference's own arithmetic for that axis.  true = proven separated (exactly what the full walk
 // would conclude); false = undecided.
-PSN bool bb_quick_separated(const Dyn& b1, const Dyn& b2, const OBox& o1, const OBox& o2)
+template <bool F>
+PSD bool bb_quick_separated_t(const Dyn& b1, const Dyn& b2, const OBox& o1, const OBox& o2)
 {
     d3 fromFirst = b2.x - b1.x;
-#pragma unroll 1
+#pragma unroll (F ? 2 : 1)
     for (int side = 0; side < 2; side++) {
         const Dyn& bb = side == 0 ? b1 : b2;
         int k = 0;
         double bestd = -1.0;
-#pragma unroll 1
+#pragma unroll (F ? 3 : 1)
         for (int q = 0; q < 3; q++) {
             double dq = fabs(bb.R.a[q] * fromFirst.x + bb.R.a[3 + q] * fromFirst.y + bb.R.a[6 + q] * fromFirst.z);
             if (dq > bestd) { bestd = dq; k = q; }
         }
-        const int f = (k == 0) ? 4 : (k == 1 ? 2 : 1);  // the +e_k face (Box.fs:42-49)
         const OBox& T = side == 0 ? o1 : o2;
         const OBox& O = side == 0 ? o2 : o1;
+        const d3 axis = (k == 0) ? T.n[4] : (k == 1 ? T.n[2] : T.n[1]);  // the +e_k face (Box.fs:42-49)
         double ta, tb, oc, od, pen;
         bool flip;
-        project_box(T, T.n[f], ta, tb);
-        project_box(O, T.n[f], oc, od);
+        pbox<F>(T, axis, ta, tb);
+        pbox<F>(O, axis, oc, od);
         if (!sat_ranges(ta, tb, oc, od, pen, flip)) return true;
     }
     return false;
+}
+PSN bool bb_quick_separated(const Dyn& b1, const Dyn& b2, const OBox& o1, const OBox& o2)
+{
+    return bb_quick_separated_t<false>(b1, b2, o1, o2);
 }
 
 // detectBoxBoxCollision (CollisionDetection.fs:29-164) over SAT.tryFindSeparatingAxis (SAT.fs:206-240)
 // returns #contacts (0 = none); overflow set when the manifold would exceed PS_MAX_CONTACTS
 // boxes_ready: sc.o1/sc.o2 are already built and the quick test has already failed to separate them
-PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
-                  int& overflow, PairScratch& sc, bool boxes_ready = false)
+template <bool F>
+PSD int detect_bb_t(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+                    int& overflow, PairScratch& sc, bool boxes_ready, bool prof = false)
 {
-    OBox& o1 = sc.o1;
-    OBox& o2 = sc.o2;
-    if (!boxes_ready) {
+    PS_CLK_BEGIN(prof)
+    // F: the boxes are values of this frame (registers once everything below is unrolled to static indices)
+    OBox l1, l2;
+    OBox& o1 = F ? l1 : sc.o1;
+    OBox& o2 = F ? l2 : sc.o2;
+    if (F) {
+        make_obox_i(b1, p1, o1);
+        make_obox_i(b2, p2, o2);
+    } else if (!boxes_ready) {
         make_obox(b1, p1, o1);
         make_obox(b2, p2, o2);
     }
@@ -358,21 +411,21 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
     d3 best_n = mk(0, 0, 0);
     d3 fromFirst = b2.x - b1.x;
 
-    if (!boxes_ready && bb_quick_separated(b1, b2, o1, o2)) return 0;
+    if (!boxes_ready && bb_quick_separated_t<F>(b1, b2, o1, o2)) return 0;
 
     // Face1 then Face2 (SAT.fs:230-234).  Normals come in +- pairs (f, f+1) with n[f+1] == 0.0 - n[f] bit for
     // bit, and a projection onto the negated axis is 0.0 - projection (see detect_sphere_box): one pass per pair.
-#pragma unroll 1
+#pragma unroll (F ? 2 : 1)
     for (int origin = 0; origin < 2; origin++) {
         const OBox& T = origin == 0 ? o1 : o2;  // Face2: boxes flipped
         const OBox& O = origin == 0 ? o2 : o1;
-#pragma unroll 1
+#pragma unroll (F ? 3 : 1)
         for (int fp = 0; fp < 6; fp += 2) {
             d3 axis0 = T.n[fp];
             double a0, b0, c0, d0;
-            project_box(T, axis0, a0, b0);
-            project_box(O, axis0, c0, d0);
-#pragma unroll 1
+            pbox<F>(T, axis0, a0, b0);
+            pbox<F>(O, axis0, c0, d0);
+#pragma unroll (F ? 2 : 1)
             for (int h = 0; h < 2; h++) {
                 double a = h ? 0.0 - b0 : a0, b = h ? 0.0 - a0 : b0;
                 double c = h ? 0.0 - d0 : c0, d = h ? 0.0 - c0 : d0;
@@ -388,29 +441,30 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
             }
         }
     }
+    PS_CLK(0)
     // Edge axes (:218-226): RigidBody.Axes = normalize(R e_k + 0) (RigidBody.fs:34-41)
     d3 ax1[3], ax2[3];
-#pragma unroll 1
+#pragma unroll (F ? 3 : 1)
     for (int k = 0; k < 3; k++) {
-        ax1[k] = normalize(mk(b1.R.a[k], b1.R.a[3 + k], b1.R.a[6 + k]) + mk(0.0, 0.0, 0.0));
-        ax2[k] = normalize(mk(b2.R.a[k], b2.R.a[3 + k], b2.R.a[6 + k]) + mk(0.0, 0.0, 0.0));
+        ax1[k] = normalize_t<F>(mk(b1.R.a[k], b1.R.a[3 + k], b1.R.a[6 + k]) + mk(0.0, 0.0, 0.0));
+        ax2[k] = normalize_t<F>(mk(b2.R.a[k], b2.R.a[3 + k], b2.R.a[6 + k]) + mk(0.0, 0.0, 0.0));
     }
-#pragma unroll 1
+#pragma unroll (F ? 3 : 1)
     for (int i = 0; i < 3; i++)
-#pragma unroll 1
+#pragma unroll (F ? 3 : 1)
         for (int j = 0; j < 3; j++) {
             // normalized(second x first), dropped iff isZero 0.01 of the NORMALISED vector (:223-225): that norm is
             // ~1 unless the cross product is exactly zero (then Normalize returns the zero vector), so the test is
             // `norm(cross) == 0` (finite inputs)
             d3 cr = cross(ax2[j], ax1[i]);
-            double cn = norm(cr);
+            double cn = norm_t<F>(cr);
             if (cn == 0.0) continue;
             d3 e = scale(1.0 / cn, cr);
             if (dot(e, fromFirst) < 0.0) e = -e;
             double a, b, c, d, pen;
             bool flip;
-            project_box(o1, e, a, b);
-            project_box(o2, e, c, d);
+            pbox<F>(o1, e, a, b);
+            pbox<F>(o2, e, c, d);
             if (!sat_ranges(a, b, c, d, pen, flip)) return 0;
             if (pen < best_pen) {
                 best_origin = 2;
@@ -421,26 +475,32 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
             }
         }
 
+    PS_CLK(1)
     if (best_origin < 2) {
         // generateFaceContactPoints (CollisionDetection.fs:30-73)
-        const OBox& ref = (best_origin == 0) ? o1 : o2;
-        const OBox& oth = (best_origin == 0) ? o2 : o1;
+        OBox rv, ov;  // F: reference / other box by value (a select per field instead of a pointer into memory)
+        if (F) {
+            rv = o1; ov = o2;
+            if (best_origin != 0) { rv = o2; ov = o1; }
+        }
+        const OBox& ref = F ? rv : ((best_origin == 0) ? o1 : o2);
+        const OBox& oth = F ? ov : ((best_origin == 0) ? o2 : o1);
         d3 normal = best_n;
         int rf = -1;
-#pragma unroll 1
+        d3 rn = mk(0.0, 0.0, 0.0);
+#pragma unroll (F ? 6 : 1)
         for (int f = 0; f < 6; f++)
-            if (veq(ref.n[f], normal)) {  // Box.findFaceByNormal (Box.fs:113-114)
+            if (rf < 0 && veq(ref.n[f], normal)) {  // Box.findFaceByNormal (Box.fs:113-114): the first match
                 rf = f;
-                break;
+                rn = ref.n[f];
             }
         if (rf < 0) {
             err = 1;
             return 0;
         }
-        d3 rn = ref.n[rf];
         int inc = 0;
         double incv = dot(rn, oth.n[0]);
-#pragma unroll 1
+#pragma unroll (F ? 5 : 1)
         for (int f = 1; f < 6; f++) {  // findIncidentFace: first min (:35-37)
             double d = dot(rn, oth.n[f]);
             if (d < incv) {
@@ -452,13 +512,14 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
         PolyV* cur = sc.bufA;
         PolyV* nxt = sc.bufB;
         int n = 4;
-#pragma unroll 1
+#pragma unroll (F ? 4 : 1)
         for (int k = 0; k < 4; k++) {
             cur[k].p = face_vertex(oth, inc, k);
             cur[k].tag = (unsigned)k;
         }
         int pi = 0;
-#pragma unroll 1
+        PS_CLK(2)
+#pragma unroll (F ? 6 : 1)
         for (int f = 0; f < 6; f++) {
             double ad = fabs(dot(rn, ref.n[f]));
             if (near_eq(eps, 1.0, ad)) continue;  // not adjacent
@@ -476,12 +537,12 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
                 if (sin_ && ein) {
                     if (m < PS_MAX_CONTACTS + 4) nxt[m++] = e; else overflow = 1;
                 } else if (sin_ && !ein) {
-                    if (plane_edge_hit(eps, pn, pd, s.p, e.p, x)) {
+                    if (pehit<F>(eps, pn, pd, s.p, e.p, x)) {
                         if (m < PS_MAX_CONTACTS + 4) { nxt[m].p = x; nxt[m].tag = xtag; m++; } else overflow = 1;
                     }
                 } else if (!sin_ && ein) {
                     if (m < PS_MAX_CONTACTS + 4) nxt[m++] = e; else overflow = 1;
-                    if (plane_edge_hit(eps, pn, pd, s.p, e.p, x)) {
+                    if (pehit<F>(eps, pn, pd, s.p, e.p, x)) {
                         if (m < PS_MAX_CONTACTS + 4) { nxt[m].p = x; nxt[m].tag = xtag; m++; } else overflow = 1;
                     }
                 }
@@ -490,9 +551,10 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
             n = m;
             pi++;
         }
+        PS_CLK(3)
         // List.distinct, then keep points on/below the reference plane (:52-54), then contacts (:63-67)
         d3 refq[4];
-#pragma unroll 1
+#pragma unroll (F ? 4 : 1)
         for (int k = 0; k < 4; k++) refq[k] = face_vertex(ref, rf, k);
         d3 rpn = -rn;
         double rpd = -dot(rn, refq[0]);
@@ -512,7 +574,7 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
                 overflow = 1;
                 break;
             }
-            d3 cl = closest_on_quad(cur[k].p, refq);
+            d3 cl = cquad<F>(cur[k].p, refq);
             out[nc].pen = dot(normal, cur[k].p - cl);
             out[nc].n = (best_origin == 1) ? -normal : normal;  // WithInvertedNormals (:157)
             out[nc].p = cur[k].p;
@@ -520,6 +582,7 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
                            ((unsigned)(nc & 31) << 10) | (cur[k].tag << 15);
             nc++;
         }
+        PS_CLK(4)
         return nc;
     }
 
@@ -527,14 +590,17 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
     d3 normal = best_n;
     d3 ea[2], eb[2];
     int eidx[2];
-#pragma unroll 1
+    const d3 sel1 = best_i == 0 ? ax1[0] : (best_i == 1 ? ax1[1] : ax1[2]);
+    const d3 sel2 = best_j == 0 ? ax2[0] : (best_j == 1 ? ax2[1] : ax2[2]);
+#pragma unroll (F ? 2 : 1)
     for (int side = 0; side < 2; side++) {
         const OBox& ob = side == 0 ? o1 : o2;
-        d3 axis = side == 0 ? ax1[best_i] : ax2[best_j];
+        d3 axis = side == 0 ? sel1 : sel2;
         d3 nrm = side == 0 ? normal : -normal;
         bool have = false;
         double bestv = 0.0;
         int idx = 0;
+        d3 bea = mk(0.0, 0.0, 0.0), beb = mk(0.0, 0.0, 0.0);
         // OrientedBox.getEdges: faces 0..5, per face (v3,v0),(v0,v1),(v1,v2),(v2,v3); List.distinct on
         // ordered pairs — every directed edge of a non-degenerate box appears once, so index = 4*f+k.
 #pragma unroll 1
@@ -543,15 +609,20 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
             for (int k = 0; k < 4; k++) {
                 d3 a = face_vertex(ob, f, (k + 3) & 3), b = face_vertex(ob, f, k);
                 d3 dd = b - a;
-                if (!near_eq(eps, 0.0, norm(cross(dd, axis)))) continue;  // areParallel: axis |> crossProduct d = d x axis
+                d3 cr = cross(dd, axis);  // areParallel: axis |> crossProduct d = d x axis, isZero eps of its norm
+                // Exact shortcut: Hypotenuse never returns less than its larger argument (|x| * sqrt(1 + r*r) >= |x|), so
+                // the norm is >= every |component|; one component above eps decides "not parallel" without the two
+                // divisions and square roots (20 of the 24 edges end here; a NaN norm compares false either way).
+                if (fabs(cr.x) > eps || fabs(cr.y) > eps || fabs(cr.z) > eps) continue;
+                if (!near_eq(eps, 0.0, norm_t<F>(cr))) continue;
                 double pa = dot(nrm, a), pb = dot(nrm, b);
                 double key = (pb > pa) ? pb : pa;
                 if (!have || key > bestv) {
                     have = true;
                     bestv = key;
                     idx = 4 * f + k;
-                    ea[side] = a;
-                    eb[side] = b;
+                    bea = a;
+                    beb = b;
                 }
             }
         if (!have) {
@@ -559,6 +630,8 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
             return 0;
         }
         eidx[side] = idx;
+        ea[side] = bea;
+        eb[side] = beb;
     }
     d3 DA = eb[0] - ea[0], DB = eb[1] - ea[1];
     d3 r = ea[0] - ea[1];
@@ -573,46 +646,56 @@ PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, do
     out[0].pen = -best_pen;
     out[0].feat = 3u | (2u << 2) | ((unsigned)best_i << 4) | ((unsigned)best_j << 7) | ((unsigned)eidx[0] << 10) |
                   ((unsigned)eidx[1] << 15);
+    PS_CLK(5)
     return 1;
 }
-
-// CollisionDetection.areColliding (CollisionDetection.fs:208-220)
-PSD int detect(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
-               int& overflow, PairScratch& sc)
+PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+                  int& overflow, PairScratch& sc, bool boxes_ready = false)
 {
-    if (p1.shape == 0 && p2.shape == 0) return detect_ss(b1, p1, b2, p2, out);
-    if (p1.shape == 1 && p2.shape == 1) return detect_bb(b1, p1, b2, p2, eps, out, err, overflow, sc);
-    int face = 0;
-    if (p1.shape == 0) {
-        int n = detect_sphere_box(b1, p1, b2, p2, eps, out, face, err, sc.o1);
-        if (n) {
-            out[0].n = -out[0].n;  // WithInvertedNormals (:217-219)
-            out[0].feat = 1u | ((unsigned)face << 4);
-        }
-        return n;
-    }
-    int n = detect_sphere_box(b2, p2, b1, p1, eps, out, face, err, sc.o1);
-    if (n) out[0].feat = 2u | ((unsigned)face << 4);
-    return n;
+    return detect_bb_t<false>(b1, p1, b2, p2, eps, out, err, overflow, sc, boxes_ready);
 }
 
 // areColliding for a pair with at least one sphere: exactly one contact, no clip buffers needed
-PSD int detect_sphere_pair(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
-                           OBox& ob)
+template <bool F>
+PSD int detect_sphere_pair_t(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+                             OBox& ob)
 {
-    if (p1.shape == 0 && p2.shape == 0) return detect_ss(b1, p1, b2, p2, out);
+    if (p1.shape == 0 && p2.shape == 0) return F ? detect_ss_t<true>(b1, p1, b2, p2, out) : detect_ss(b1, p1, b2, p2, out);
     int face = 0;
     if (p1.shape == 0) {
-        int n = detect_sphere_box(b1, p1, b2, p2, eps, out, face, err, ob);
+        int n = F ? detect_sphere_box_t<true>(b1, p1, b2, p2, eps, out, face, err, ob)
+                  : detect_sphere_box(b1, p1, b2, p2, eps, out, face, err, ob);
         if (n) {
             out[0].n = -out[0].n;  // WithInvertedNormals (CollisionDetection.fs:217-219)
             out[0].feat = 1u | ((unsigned)face << 4);
         }
         return n;
     }
-    int n = detect_sphere_box(b2, p2, b1, p1, eps, out, face, err, ob);
+    int n = F ? detect_sphere_box_t<true>(b2, p2, b1, p1, eps, out, face, err, ob)
+              : detect_sphere_box(b2, p2, b1, p1, eps, out, face, err, ob);
     if (n) out[0].feat = 2u | ((unsigned)face << 4);
     return n;
+}
+PSD int detect_sphere_pair(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+                           OBox& ob)
+{
+    return detect_sphere_pair_t<false>(b1, p1, b2, p2, eps, out, err, ob);
+}
+
+// CollisionDetection.areColliding (CollisionDetection.fs:208-220)
+template <bool F>
+PSD int detect_t(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+                 int& overflow, PairScratch& sc)
+{
+    if (p1.shape == 1 && p2.shape == 1)
+        return F ? detect_bb_t<true>(b1, p1, b2, p2, eps, out, err, overflow, sc, false)
+                 : detect_bb(b1, p1, b2, p2, eps, out, err, overflow, sc);
+    return detect_sphere_pair_t<F>(b1, p1, b2, p2, eps, out, err, sc.o1);
+}
+PSD int detect(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
+               int& overflow, PairScratch& sc)
+{
+    return detect_t<false>(b1, p1, b2, p2, eps, out, err, overflow, sc);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -48,6 +48,7 @@ constexpr int kParF = 16;       // doubles of parameters per body
 constexpr int kMaxLevels = 1022;
 constexpr int kMaxStatics = 4;  // static bodies per world whose pairs run in parallel (more -> serial walk)
 constexpr int kMaxThreads = 128;
+constexpr int kBoostSteps = 8;  // steps of doubled margins after a world had to verify (a restart costs a whole world-step)
 constexpr int kCullF = 7;       // doubles of cull-sphere data per body: centre 3, radius vs sphere, radius vs box, margin^2, max deviation^2
 
 struct WorldStats {  // per world, accumulated over steps
@@ -55,7 +56,8 @@ struct WorldStats {  // per world, accumulated over steps
     unsigned long long fb_margin, fb_capacity, fb_static;
     unsigned long long verified;  // world-steps in which a body left its margin and the culled pairs were re-examined
     double max_pen;
-    int nan_flag, pad;
+    int nan_flag;
+    int boost;  // > 0: a body of this world left its margin recently -> margins doubled for that many more steps
     // SM cycles of thread 0 per phase, summed over steps: predict+cull spheres, near list, levels+sort,
     // wavefronts (or serial walk), static fold + joints + final sweep + publish; and the slowest single step
     unsigned long long cyc[5], cyc_max_step;
@@ -462,6 +464,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
     unsigned long long t_fbm = 0, t_fbc = 0, t_fbs = 0, t_ver = 0;
     double t_maxpen = 0.0;
     unsigned long long cyc[5] = {0, 0, 0, 0, 0}, cyc_max = 0, sumK = 0, sumL = 0;
+    int boost = live ? a.stats[w].boost : 0;  // per lane, kept equal across the tile
 
     for (int step = 0; step < a.n_steps; step++) {
         long long tk0 = clock64(), tk = tk0;
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
             // dt * (its new velocity): the margin covers n such moves, n estimated from the number of
             // colliding pairs the body was in during the previous step.
             {
-                const double mscale = (attempt == 0 ? 1.0 : 8.0) * a.margin_scale;
+                const double mscale = (attempt == 0 ? (boost > 0 ? 2.0 : 1.0) : 8.0) * a.margin_scale;
                 for (int b = tid; b < Nw; b += T) {
                     const bool on = fast && b < N;
                     Par p;
@@ -731,6 +734,11 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
             //  it goes round again with attempt == 2)
             __syncwarp();
         }
+        {   // a world that had to verify (or restart) keeps doubled margins for a while; otherwise the boost runs out
+            const unsigned tm_ = (T == 32) ? FULL : (((1u << T) - 1u) << (tile * T));
+            const bool hot = (__ballot_sync(FULL, live && (bs.violate || fb_reason == 1)) & tm_) != 0u;
+            boost = hot ? kBoostSteps : (boost > 0 ? boost - 1 : 0);
+        }
         if (tid == 0 && live && fb_reason != 0 && !a.exact_all_pairs && !a.only_flagged) {
             t_fallback++;
             if (fb_reason == 1) t_fbm++; else if (fb_reason == 2) t_fbc++; else t_fbs++;
@@ -837,6 +845,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
         st.fb_margin += t_fbm; st.fb_capacity += t_fbc; st.fb_static += t_fbs; st.verified += t_ver;
         st.max_pen = fmax(st.max_pen, t_maxpen);
         st.nan_flag = bad ? 1 : 0;
+        st.boost = boost;
         for (int k = 0; k < 5; k++) st.cyc[k] += cyc[k];
         if (cyc_max > st.cyc_max_step) st.cyc_max_step = cyc_max;
         st.sum_K += sumK; st.sum_levels += sumL;

@@ -25,6 +25,8 @@
 // whose static bodies do not sit at a fixed point of integrate(), or that overflows a table is flagged and redone
 // from the published state by the fused kernel (which owns the 8x-margin and exact-serial fallbacks).
 #pragma once
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
 #include "ps_step_kernel.cuh"
 
 namespace psw {
@@ -60,7 +62,7 @@ struct WArgs {
     unsigned* surv;              // [entries_cap] box-box pairs the quick test could not separate (listed from the bucket's start)
     unsigned* surv_cnt;          // per level
     WorldStats* stats;
-    unsigned* tmp;               // per world x 6: tested, hits, contacts, overflow, ref_exc, bodies that left their margin; THIS step's wide pass
+    unsigned* tmp;               // per world x 6 words of THIS step's wide pass: [0-1] tested | colliding | contacts packed in 64 bits (count_pair), [3] overflow, [4] ref_exc, [5] bodies that left their margin
     unsigned long long* tmp_pen; // per world: max |penetration| bits of this step
     RecPair* rec_pairs; RecContact* rec_contacts; int* rec_counts; int rec_pair_cap, rec_contact_cap;
     StepParams sp;
@@ -69,6 +71,27 @@ struct WArgs {
 };
 
 enum { WF_MARGIN = 1, WF_STATIC = 2, WF_CAPACITY = 4 };
+
+// Every pair of a round reserves its slot in the round's lists from the SAME counter.  One atomic per thread on one
+// address serialises in L2 (a round of 25 K box pairs spent most of its 140 us there, round 1 with 10^6 pairs
+// milliseconds); the lanes of a warp that arrive together reserve together and share one atomic.
+__device__ __forceinline__ unsigned agg_reserve(unsigned* counter, unsigned n)
+{
+    namespace cg = cooperative_groups;
+    cg::coalesced_group g = cg::coalesced_threads();
+    const unsigned pre = cg::exclusive_scan(g, n);
+    const unsigned total = g.shfl(pre + n, g.size() - 1);
+    unsigned base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, total);
+    return g.shfl(base, 0) + pre;
+}
+// per-world counters of this step's wide pass: tested (20 bits) | colliding (20 bits) | contacts (24 bits) in one
+// 64-bit add per pair (a world has at most 2^19 pairs)
+__device__ __forceinline__ void count_pair(const WArgs& a, int w, unsigned hit, unsigned contacts)
+{
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.tmp + 6 * (size_t)w),
+              1ull | ((unsigned long long)hit << 20) | ((unsigned long long)contacts << 40));
+}
 
 PSD unsigned* w_near(const WArgs& a, int w) { return reinterpret_cast<unsigned*>(a.lists + a.lists_off[w]); }
 PSD size_t w_np(const WArgs& a, int w) { size_t N = (size_t)(a.off[w + 1] - a.off[w]); return N * (N > 0 ? N - 1 : 0) / 2; }
@@ -113,7 +136,8 @@ __global__ void __launch_bounds__(128) wide_predict(WArgs a)
     double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
     int np_ = a.nprev[g];
     double n = (double)(np_ < a.margin_ncap ? np_ : a.margin_ncap) + 2.0;
-    double m = p.is_static ? 0.0 : a.margin_scale * (0.01 + n * a.sp.dt * (speed + n * acc * a.sp.dt + 0.5));
+    const double mscale = a.margin_scale * (a.stats[w].boost > 0 ? 2.0 : 1.0);
+    double m = p.is_static ? 0.0 : mscale * (0.01 + n * a.sp.dt * (speed + n * acc * a.sp.dt + 0.5));
     if (!(m == m)) m = 0.0;
     double rs, rb;
     if (p.shape == 0) { rs = p.dims[0]; rb = 1.7320508075688774 * p.dims[0]; }
@@ -327,13 +351,13 @@ __device__ __forceinline__ void wide_bb_quick_body(const WArgs& a, unsigned firs
     ld_dyn(a.pred, 0, o + i, di);
     ld_dyn(a.pred, 0, o + j, dj);
     OBox o1, o2;
-    make_obox(di, pi, o1);
-    make_obox(dj, pj, o2);
-    if (bb_quick_separated(di, dj, o1, o2)) {
-        atomicAdd(&a.tmp[6 * (size_t)w], 1u);  // tested, no collision
+    make_obox_i(di, pi, o1);
+    make_obox_i(dj, pj, o2);
+    if (bb_quick_separated_t<true>(di, dj, o1, o2)) {
+        count_pair(a, w, 0u, 0u);  // tested, no collision
         return;
     }
-    unsigned slot = atomicAdd(&a.surv_cnt[level], 1u);
+    unsigned slot = agg_reserve(&a.surv_cnt[level], 1u);
     a.surv[first + slot] = first + t;
 }
 
@@ -341,6 +365,7 @@ __device__ __forceinline__ void wide_bb_quick_body(const WArgs& a, unsigned firs
 template <int KIND>
 __device__ __forceinline__ void wide_detect_body(const WArgs& a, unsigned first, unsigned count, int level, unsigned t)
 {
+    PS_CLK_BEGIN(KIND == 2 && level >= 3)
     unsigned ei = first + t;
     if (KIND == 2) {  // box-box: only the pairs stage 1 could not separate
         if (t >= a.surv_cnt[level]) return;
@@ -356,33 +381,37 @@ __device__ __forceinline__ void wide_detect_body(const WArgs& a, unsigned first,
     ld_par(a.par, 0, o + j, pj);
     ld_dyn(a.pred, 0, o + i, di);
     ld_dyn(a.pred, 0, o + j, dj);
-    PairScratch sc;
+    // the inlined, unrolled forms of the narrow phase (ps_physics.cuh, F = true): a round lasts as long as its slowest
+    // pair, so the dependent chain of ONE pair is what counts here
+    PairScratch scb;   // box-box only: clip buffers, manifold
+    Contact cs1[1];    // a pair with a sphere has one contact
+    Contact* const cs = (KIND == 2) ? scb.cs : cs1;
     int err = 0, ovf = 0, nc;
     if (KIND == 0) {
-        nc = detect_ss(di, pi, dj, pj, sc.cs);
+        nc = detect_ss_t<true>(di, pi, dj, pj, cs);
     } else if (KIND == 2) {
-        make_obox(di, pi, sc.o1);
-        make_obox(dj, pj, sc.o2);
-        nc = detect_bb(di, pi, dj, pj, a.sp.eps, sc.cs, err, ovf, sc, true);
+        PS_CLK(8)
+        nc = detect_bb_t<true>(di, pi, dj, pj, a.sp.eps, cs, err, ovf, scb, true, level >= 3);  // the quick test has already failed to separate
+        PS_CLK(9)
     } else {
-        nc = detect(di, pi, dj, pj, a.sp.eps, sc.cs, err, ovf, sc);
+        OBox ob;
+        nc = detect_sphere_pair_t<true>(di, pi, dj, pj, a.sp.eps, cs, err, ob);
     }
     unsigned* tm = a.tmp + 6 * (size_t)w;
-    atomicAdd(&tm[0], 1u);
     if (err) atomicAdd(&tm[4], 1u);
     if (ovf) atomicAdd(&tm[3], 1u);
+    count_pair(a, w, nc > 0 ? 1u : 0u, nc > 0 ? (unsigned)nc : 0u);
     if (nc <= 0) return;
-    unsigned cf = atomicAdd(&a.cpool_cur[level], (unsigned)nc);
+    unsigned cf = agg_reserve(&a.cpool_cur[level], (unsigned)nc);
     if (cf + (unsigned)nc > a.cpool_cap) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); return; }
-    for (int k = 0; k < nc; k++) a.cpool[cf + k] = sc.cs[k];
+    for (int k = 0; k < nc; k++) a.cpool[cf + k] = cs[k];
     e.knc |= (unsigned)nc << 24; e.cfirst = cf;
-    unsigned slot = atomicAdd(&a.hit_cnt[level * 4 + KIND], 1u);
+    unsigned slot = agg_reserve(&a.hit_cnt[level * 4 + KIND], 1u);
     a.hitlist[first + slot] = ei;
-    atomicAdd(&tm[1], 1u);
-    atomicAdd(&tm[2], (unsigned)nc);
     double mp = 0.0;
-    for (int k = 0; k < nc; k++) mp = fmax(mp, fabs(sc.cs[k].pen));
-    atomicMax(&a.tmp_pen[w], (unsigned long long)__double_as_longlong(mp));
+    for (int k = 0; k < nc; k++) mp = fmax(mp, fabs(cs[k].pen));
+    const unsigned long long mpb = (unsigned long long)__double_as_longlong(mp);
+    if (mpb > __ldcg(&a.tmp_pen[w])) atomicMax(&a.tmp_pen[w], mpb);  // the maximum rarely moves
     if (a.rec_pairs) {
         int* cnt = a.rec_counts + 2 * w;
         int slot2 = atomicAdd(&cnt[0], 1);
@@ -393,9 +422,9 @@ __device__ __forceinline__ void wide_detect_body(const WArgs& a, unsigned first,
             RecContact* out = a.rec_contacts + (size_t)w * a.rec_contact_cap + f2;
             for (int k = 0; k < nc; k++) {
                 RecContact r;
-                r.n[0] = sc.cs[k].n.x; r.n[1] = sc.cs[k].n.y; r.n[2] = sc.cs[k].n.z;
-                r.p[0] = sc.cs[k].p.x; r.p[1] = sc.cs[k].p.y; r.p[2] = sc.cs[k].p.z;
-                r.pen = sc.cs[k].pen; r.feat = sc.cs[k].feat; r.pad = 0;
+                r.n[0] = cs[k].n.x; r.n[1] = cs[k].n.y; r.n[2] = cs[k].n.z;
+                r.p[0] = cs[k].p.x; r.p[1] = cs[k].p.y; r.p[2] = cs[k].p.z;
+                r.pen = cs[k].pen; r.feat = cs[k].feat; r.pad = 0;
                 out[k] = r;
             }
         }
@@ -408,6 +437,7 @@ __device__ __forceinline__ void wide_detect_body(const WArgs& a, unsigned first,
 template <int KIND>
 __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first, int level, unsigned t)
 {
+    PS_CLK_BEGIN(KIND == 2 && level >= 3)
     if (t >= a.hit_cnt[level * 4 + KIND]) return;
     const Entry& e = a.entries[a.hitlist[first + t]];
     const int w = e.w;
@@ -422,12 +452,13 @@ __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first
     const bool si = pi.is_static, sj = pj.is_static;
     if (si) di.L = mk(0.0, 0.0, 0.0);
     if (sj) dj.L = mk(0.0, 0.0, 0.0);
+    PS_CLK(12)
     if (KIND == 2) {
         const int nc = (int)(e.knc >> 24);
-        Contact cs[PS_MAX_CONTACTS];
         CPData cp[PS_MAX_CONTACTS];
-        for (int k = 0; k < nc; k++) cs[k] = a.cpool[e.cfirst + k];
-        resolve_t<0>(di, pi, dj, pj, cs, nc, cp, a.sp);
+        PS_CLK(13)
+        resolve_t<0>(di, pi, dj, pj, a.cpool + e.cfirst, nc, cp, a.sp);  // the manifold is read where the narrow phase left it
+        PS_CLK(14)
     } else {  // sphere pairs always carry exactly one contact
         Contact cs[1];
         CPData cp[1];
@@ -459,6 +490,7 @@ __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first
         double q = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
         if (!(q <= cu[5 * N + b]) && !(q <= cu[6 * N + b])) cu[6 * N + b] = q;  // a NaN sticks
     }
+    PS_CLK(15)
 }
 
 // One launch per stage and round: the CTA index selects the kind (CTA-uniform branch), so a round costs three
@@ -578,9 +610,15 @@ __global__ void wide_account(WArgs a)
     if (w >= a.n_worlds) return;
     unsigned f = a.wflags[w];
     WorldStats& st = a.stats[w];
+    const unsigned* tm = a.tmp + 6 * (size_t)w;
+    if (!a.always_fused[w]) {  // doubled margins for a while after a body left its margin (the fused kernel keeps its own count)
+        if (tm[5] || (f & WF_MARGIN)) st.boost = kBoostSteps;
+        else if (!f && st.boost > 0) st.boost--;
+    }
     if (!f) {  // the wide pass stands: commit its counters
-        const unsigned* tm = a.tmp + 6 * (size_t)w;
-        st.steps++; st.tested += tm[0]; st.hits += tm[1]; st.contacts += tm[2]; st.overflow += tm[3]; st.ref_exc += tm[4];
+        const unsigned long long pk = *reinterpret_cast<const unsigned long long*>(tm);
+        st.steps++; st.tested += pk & 0xfffffull; st.hits += (pk >> 20) & 0xfffffull; st.contacts += pk >> 40;
+        st.overflow += tm[3]; st.ref_exc += tm[4];
         if (tm[5]) st.verified++;
         st.max_pen = fmax(st.max_pen, __longlong_as_double((long long)a.tmp_pen[w]));
         return;

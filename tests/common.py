@@ -79,11 +79,11 @@ def host_harness():
         if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-x", "c++", src, "-o", so])
         _HH = ctypes.CDLL(so)
-        _HH.hh_world_step.restype = None
+        _HH.hh_world_step_v.restype = None
     return _HH
 
 
-def harness_step(bodies: dict, cfg_native, nsteps: int, cap_pairs=4096, cap_contacts=32768):
+def harness_step(bodies: dict, cfg_native, nsteps: int, cap_pairs=4096, cap_contacts=32768, fast=False):
     hh = host_harness()
     par, dyn = to_planar(bodies)
     n = len(bodies["mass"])
@@ -93,11 +93,11 @@ def harness_step(bodies: dict, cfg_native, nsteps: int, cap_pairs=4096, cap_cont
     cont = np.zeros((cap_contacts, 7))
     counts = np.zeros(2, dtype=np.int32)
     P_ = ctypes.POINTER
-    hh.hh_world_step(ctypes.c_int(n), par.ctypes.data_as(P_(ctypes.c_double)), dyn.ctypes.data_as(P_(ctypes.c_double)),
-                     ctypes.byref(cfg_native), ctypes.c_int(nsteps), counters.ctypes.data_as(P_(ctypes.c_int64)),
-                     pairs.ctypes.data_as(P_(ctypes.c_int32)), feats.ctypes.data_as(P_(ctypes.c_uint32)),
-                     cont.ctypes.data_as(P_(ctypes.c_double)), counts.ctypes.data_as(P_(ctypes.c_int32)),
-                     ctypes.c_int(cap_pairs), ctypes.c_int(cap_contacts))
+    hh.hh_world_step_v(ctypes.c_int(n), par.ctypes.data_as(P_(ctypes.c_double)), dyn.ctypes.data_as(P_(ctypes.c_double)),
+                       ctypes.byref(cfg_native), ctypes.c_int(nsteps), counters.ctypes.data_as(P_(ctypes.c_int64)),
+                       pairs.ctypes.data_as(P_(ctypes.c_int32)), feats.ctypes.data_as(P_(ctypes.c_uint32)),
+                       cont.ctypes.data_as(P_(ctypes.c_double)), counts.ctypes.data_as(P_(ctypes.c_int32)),
+                       ctypes.c_int(cap_pairs), ctypes.c_int(cap_contacts), ctypes.c_int(1 if fast else 0))
     st = from_planar_dyn(dyn)
     npairs, nc = int(counts[0]), int(counts[1])
     first = np.concatenate([[0], np.cumsum(pairs[:npairs, 2])]).astype(np.int32)

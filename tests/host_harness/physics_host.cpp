@@ -44,8 +44,10 @@ void ld_par(const double* a, int N, int b, Par& p)
 extern "C" {
 
 // planar layouts as in ps_step_kernel.cuh: dyn[f*N+b] (18 planes), par[f*N+b] (16 planes, plane 0 = 1/mass)
-void hh_world_step(int N, const double* par, double* dyn, const ps_step_config* cfg, int nsteps, int64_t* counters /*tested,hits,contacts,exc,overflow*/,
-                   int32_t* last_pairs, uint32_t* last_feats, double* last_contacts /*7 per contact*/, int32_t* last_counts /*pairs,contacts*/, int cap_pairs, int cap_contacts)
+// fast = 1: the inlined/unrolled forms of the narrow phase (the ones the batch-wide kernels call)
+void hh_world_step_v(int N, const double* par, double* dyn, const ps_step_config* cfg, int nsteps, int64_t* counters /*tested,hits,contacts,exc,overflow*/,
+                     int32_t* last_pairs, uint32_t* last_feats, double* last_contacts /*7 per contact*/, int32_t* last_counts /*pairs,contacts*/, int cap_pairs, int cap_contacts,
+                     int fast)
 {
     StepParams sp;
     sp.eps = cfg->epsilon; sp.baumgarte = cfg->baumgarte; sp.slop = cfg->allowed_penetration; sp.max_corr = cfg->max_correction_velocity;
@@ -71,7 +73,7 @@ void hh_world_step(int N, const double* par, double* dyn, const ps_step_config* 
                 Contact* cs = sc.cs;
                 int err = 0, ovf = 0;
                 counters[0]++;
-                int nc = detect(di, pi, dj, pj, sp.eps, cs, err, ovf, sc);
+                int nc = fast ? detect_t<true>(di, pi, dj, pj, sp.eps, cs, err, ovf, sc) : detect(di, pi, dj, pj, sp.eps, cs, err, ovf, sc);
                 counters[3] += err; counters[4] += ovf;
                 if (nc <= 0) continue;
                 counters[1]++; counters[2] += nc;
@@ -99,5 +101,10 @@ void hh_world_step(int N, const double* par, double* dyn, const ps_step_config* 
         }
         if (last_counts) { last_counts[0] = np; last_counts[1] = ncs; }
     }
+}
+void hh_world_step(int N, const double* par, double* dyn, const ps_step_config* cfg, int nsteps, int64_t* counters,
+                   int32_t* last_pairs, uint32_t* last_feats, double* last_contacts, int32_t* last_counts, int cap_pairs, int cap_contacts)
+{
+    hh_world_step_v(N, par, dyn, cfg, nsteps, counters, last_pairs, last_feats, last_contacts, last_counts, cap_pairs, cap_contacts, 0);
 }
 }

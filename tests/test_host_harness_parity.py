@@ -19,11 +19,14 @@ def _run(protos, cfg, chunks, what):
     done = 0
     for n in chunks:
         o.step(n)
+        # both forms of the narrow phase: the compact one of the fused kernel and the inlined one of the wide kernels
         st, rec, cnt = harness_step(cur, nc, n)
+        st_f, rec_f, cnt_f = harness_step(cur, nc, n, fast=True)
         done += n
-        assert_state_bits(o.get_state(), st, f"{what} @ {done}")
-        assert_contacts_equal(o.contacts(), rec, f"{what} @ {done}")
-        assert cnt["overflow"] == 0
+        for s_, r_, c_, form in ((st, rec, cnt, "compact"), (st_f, rec_f, cnt_f, "inlined")):
+            assert_state_bits(o.get_state(), s_, f"{what}/{form} @ {done}")
+            assert_contacts_equal(o.contacts(), r_, f"{what}/{form} @ {done}")
+            assert c_["overflow"] == 0
         cur.update(st)
 
 
