@@ -56,11 +56,22 @@ typedef struct {
     int32_t solver_iterations;      /* CollisionSolverIterationCount = 10 */
     int32_t enable_friction;        /* EnableFriction = true */
     int32_t integrator_kind;        /* 0 FirstOrder, 1 AugmentedSecondOrder (Configuration.fs:5-7) */
-    int32_t broadphase_kind;        /* 0 Dummy order (BroadPhase.fs:33-39) — the only GPU mode this round */
+    int32_t broadphase_kind;        /* 0 Dummy: all (i<j), lexicographic (BroadPhase.fs:33-39).
+                                     * 1 SpatialTree (BroadPhase.fs:100-127): the persistent 2^3-tree of
+                                     *   Utilities/SpatialTree.fs decides the candidates and their ORDER; it lives on
+                                     *   the host (one per world, csrc/ps_octree.hpp), is fed with the bodies' extents
+                                     *   from the device before every step and hands the ordered list back — one
+                                     *   host round trip per step, meant for the Gui-scene sized worlds that select
+                                     *   this mode; the device work per pair is the same as in mode 0 */
     int32_t restore_joints;         /* 0 = reference default (Simulator.fs:55 is commented out) */
     int32_t record_contacts;        /* 1: keep the last step's Collisions map for ps_batch_get_contacts */
     int32_t exact_all_pairs;        /* 1: parity/debug — disable the conservative cull, walk all pairs serially */
+    /* SpatialTreeConfiguration (Configuration.fs:13-23), read when broadphase_kind == 1 */
+    int32_t tree_leaf_capacity;     /* LeafCapacity = 4 */
+    int32_t tree_max_depth;         /* MaxDepth = 10 */
     int32_t reserved;
+    double tree_min[3];             /* SpaceBoundaries.Min = (-15,-15,-15) */
+    double tree_max[3];             /* SpaceBoundaries.Max = ( 15, 15, 15) */
 } ps_step_config;
 
 /* gravity is NOT in the config: the F# side folds it into per-body force

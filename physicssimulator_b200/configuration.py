@@ -85,12 +85,18 @@ class ps_step_config(ctypes.Structure):
         ("restore_joints", ctypes.c_int32),
         ("record_contacts", ctypes.c_int32),
         ("exact_all_pairs", ctypes.c_int32),
+        ("tree_leaf_capacity", ctypes.c_int32),
+        ("tree_max_depth", ctypes.c_int32),
         ("reserved", ctypes.c_int32),
+        ("tree_min", ctypes.c_double * 3),
+        ("tree_max", ctypes.c_double * 3),
     ]
 
 
 def to_native_config(cfg: Configuration, record_contacts: bool = False, exact_all_pairs: bool = False) -> ps_step_config:
     s = cfg.StepConfig
+    t = cfg.BroadPhaseCollisionDetectionKind.SpatialTree
+    tree = t or SpatialTreeConfiguration()
     return ps_step_config(
         epsilon=s.Epsilon,
         baumgarte=s.BaumgarteTerm,
@@ -100,7 +106,11 @@ def to_native_config(cfg: Configuration, record_contacts: bool = False, exact_al
         solver_iterations=s.CollisionSolverIterationCount,
         enable_friction=1 if s.EnableFriction else 0,
         integrator_kind=int(s.RigidBodyIntegratorKind),
-        broadphase_kind=0,
+        broadphase_kind=0 if t is None else 1,
+        tree_leaf_capacity=int(tree.LeafCapacity),
+        tree_max_depth=int(tree.MaxDepth),
+        tree_min=(ctypes.c_double * 3)(*[float(v) for v in tree.SpaceBoundariesMin]),
+        tree_max=(ctypes.c_double * 3)(*[float(v) for v in tree.SpaceBoundariesMax]),
         restore_joints=1 if cfg.RestoreJoints else 0,
         record_contacts=1 if record_contacts else 0,
         exact_all_pairs=1 if exact_all_pairs else 0,

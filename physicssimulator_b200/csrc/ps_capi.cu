@@ -16,6 +16,7 @@
 #include "../../include/ps_b200.h"
 #include "ps_step_kernel.cuh"
 #include "ps_wide.cuh"
+#include "ps_octree.hpp"
 
 using namespace psk;
 
@@ -101,6 +102,16 @@ struct Batch {
     ps_stats* d_stats_sum = nullptr;
     cudaStream_t stream = nullptr;
     long long launches = 0;
+    // SpatialTree candidate order (broadphase_kind 1): one persistent tree per world on the host (the reference keeps it
+    // in SimulatorState, BroadPhase.fs:100-127), extents come from the device, the ordered list goes back
+    bool tree_mode = false;
+    std::vector<pst::Tree<3>> trees;
+    double* d_ext = nullptr;     // 6 doubles per body: AABB size xyz, min corner xyz
+    double* h_ext = nullptr;     // pinned
+    unsigned* d_cand = nullptr;  // candidate lists of all worlds for the coming step
+    int* d_cand_off = nullptr;
+    std::vector<uint32_t> h_cand;
+    std::vector<int> h_cand_off;
 };
 
 // ---- layout kernels ------------------------------------------------------------------------------
@@ -197,6 +208,36 @@ __global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const 
     atomicMax((unsigned long long*)&out->max_penetration, (unsigned long long)__double_as_longlong(mp));
 }
 
+// SimulatorObject.getAABoundingBox (SimulatorObject.fs:58-71: a sphere's box has side = radius, quirk Q5;
+// Box.worldAxisAlignedSize, Box.fs:69-85) as objExtentProvider hands it to the tree (BroadPhase.fs:21-31: size and
+// MIN corner = centre - size / 2), from the body-major records
+__global__ void extent_kernel(int n, const double* __restrict__ dyn, const double* __restrict__ par, double* __restrict__ ext)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const double* d = dyn + (size_t)g * kDynF;
+    const double* p = par + (size_t)g * kParF;
+    double sx, sy, sz;
+    if (p[15] == 0.0) {
+        sx = sy = sz = p[12];  // Box.createCube radius
+    } else {
+        m33 R;
+#pragma unroll
+        for (int k = 0; k < 9; k++) R.a[k] = d[6 + k];
+        double hx = p[12] / 2.0, hy = p[13] / 2.0, hz = p[14] / 2.0;
+        d3 z = mk(0.0, 0.0, 0.0);
+        d3 ex = mulMV(R, mk(hx, 0.0, 0.0)) + z;  // toWorldCoordinates with the orientation only
+        d3 ey = mulMV(R, mk(0.0, hy, 0.0)) + z;
+        d3 ez = mulMV(R, mk(0.0, 0.0, hz)) + z;
+        sx = (fabs(ex.x) + fabs(ey.x) + fabs(ez.x)) * 2.0;
+        sy = (fabs(ex.y) + fabs(ey.y) + fabs(ez.y)) * 2.0;
+        sz = (fabs(ex.z) + fabs(ey.z) + fabs(ez.z)) * 2.0;
+    }
+    d3 mn = mk(d[0], d[1], d[2]) - scale(1.0 / 2.0, mk(sx, sy, sz));
+    double* o = ext + (size_t)g * 6;
+    o[0] = sx; o[1] = sy; o[2] = sz; o[3] = mn.x; o[4] = mn.y; o[5] = mn.z;
+}
+
 // ---- helpers ---------------------------------------------------------------------------------------
 template <class T>
 void dfree(T*& p)
@@ -213,6 +254,8 @@ void free_device(Batch* B)
     if (B->h_bucket) { cudaFreeHost(B->h_bucket); B->h_bucket = nullptr; }
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
+    dfree(B->d_ext); dfree(B->d_cand); dfree(B->d_cand_off);
+    if (B->h_ext) { cudaFreeHost(B->h_ext); B->h_ext = nullptr; }
 }
 
 int validate_bodies(const HostBodies& h)
@@ -411,10 +454,94 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_rec_counts, nw * 2 * sizeof(int)));
         CK(cudaMemset(B->d_rec_counts, 0, nw * 2 * sizeof(int)));
     }
+    B->tree_mode = B->cfg.broadphase_kind == 1;
+    if (B->tree_mode) {
+        B->wide = false;  // the batch-wide path builds its lists from the Dummy order
+        size_t np = 0;
+        for (int w = 0; w < B->n_worlds; w++) { size_t N = (size_t)(h.off[w + 1] - h.off[w]); np += N * (N > 0 ? N - 1 : 0) / 2; }
+        CK(cudaMalloc(&B->d_ext, nb * 6 * sizeof(double)));
+        CK(cudaMallocHost(&B->h_ext, nb * 6 * sizeof(double)));
+        CK(cudaMalloc(&B->d_cand, std::max<size_t>(np, 1) * sizeof(unsigned)));
+        CK(cudaMalloc(&B->d_cand_off, (size_t)(B->n_worlds + 1) * sizeof(int)));
+    }
     if (with_state && B->n_bodies > 0) {
         int rc = ps_batch_set_state(B, 0, B->n_worlds, h.pos.data(), h.vel.data(), h.rot.data(), h.L.data());
         if (rc) return rc;
     }
+    return PS_OK;
+}
+
+// ---- SpatialTree candidate order ------------------------------------------------------------------------------------
+// extents of every body at the state the device holds now -> B->h_ext
+int tree_pull_extents(Batch* B, cudaStream_t st)
+{
+    if (B->n_bodies == 0) return PS_OK;
+    extent_kernel<<<(B->n_bodies + 127) / 128, 128, 0, st>>>(B->n_bodies, B->d_dyn, B->d_par, B->d_ext);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(B->h_ext, B->d_ext, (size_t)B->n_bodies * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PS_OK;
+}
+static pst::Ext<3> ext_of(const Batch* B, int g)
+{
+    pst::Ext<3> e;
+    const double* q = B->h_ext + (size_t)g * 6;
+    for (int k = 0; k < 3; k++) { e.size[k] = q[k]; e.pos[k] = q[3 + k]; }
+    return e;
+}
+// BroadPhase.init (BroadPhase.fs:72-81, 41-60): every id of the world, ascending; an object outside the tree's space
+// makes the reference throw ArgumentException (SpatialTree.fs:171-172)
+int tree_init_world(Batch* B, int w)
+{
+    const int o = B->cur.off[w], N = B->cur.off[w + 1] - o;
+    pst::Tree<3>& t = B->trees[w];
+    if (!t.init(B->cfg.tree_leaf_capacity, B->cfg.tree_max_depth, B->cfg.tree_min, B->cfg.tree_max))
+        return fail(PS_ERR_INVALID_ARGUMENT, "SpatialTree: must be positive (maxLeafObjects / maxDepth)");
+    for (int id = 0; id < N; id++)
+        if (!t.insert(id, [&](int x) { return ext_of(B, o + x); }))
+            return fail(PS_ERR_INVALID_ARGUMENT, "world %d: object %d out of space bounds", w, id);
+    return PS_OK;
+}
+int tree_init_all(Batch* B)
+{
+    int rc = tree_pull_extents(B, B->stream);
+    if (rc) return rc;
+    B->trees.assign((size_t)B->n_worlds, pst::Tree<3>());
+    for (int w = 0; w < B->n_worlds; w++) {
+        rc = tree_init_world(B, w);
+        if (rc) return rc;
+    }
+    B->h_cand.clear();
+    B->h_cand_off.assign((size_t)B->n_worlds + 1, 0);
+    return PS_OK;
+}
+// BroadPhase.update (BroadPhase.fs:100-127) for every world at the step-start state: dynamic ids leave every leaf and
+// come back in ascending order (tryInsert: an object outside the space is silently absent this step), then the
+// candidate list in leaf order; uploaded for the step kernel
+int tree_update_and_upload(Batch* B, cudaStream_t st)
+{
+    int rc = tree_pull_extents(B, st);
+    if (rc) return rc;
+    B->h_cand.clear();
+    B->h_cand_off.assign((size_t)B->n_worlds + 1, 0);
+    std::vector<uint32_t> one;
+    std::vector<unsigned char> stat;
+    for (int w = 0; w < B->n_worlds; w++) {
+        const int o = B->cur.off[w], N = B->cur.off[w + 1] - o;
+        stat.assign((size_t)N, 0);
+        for (int b = 0; b < N; b++) stat[b] = std::isinf(B->cur.mass[o + b]) ? 1 : 0;
+        pst::Tree<3>& t = B->trees[w];
+        t.remove_if([&](int id) { return !stat[id]; });
+        for (int id = 0; id < N; id++)
+            if (!stat[id]) t.insert(id, [&](int x) { return ext_of(B, o + x); });
+        pst::candidates(t, stat.data(), one);
+        B->h_cand.insert(B->h_cand.end(), one.begin(), one.end());
+        B->h_cand_off[w + 1] = (int)B->h_cand.size();
+    }
+    if (!B->h_cand.empty())
+        CK(cudaMemcpyAsync(B->d_cand, B->h_cand.data(), B->h_cand.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B->d_cand_off, B->h_cand_off.data(), B->h_cand_off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // the host vectors are reused by the next step
     return PS_OK;
 }
 
@@ -475,7 +602,7 @@ int ps_batch_create(void** handle, const ps_bodies_view* bodies, const ps_joints
     int rc = check_view(bodies);
     if (rc) return rc;
     if (config->solver_iterations < 0) return fail(PS_ERR_INVALID_ARGUMENT, "solver_iterations must be >= 0");
-    if (config->broadphase_kind != 0) return fail(PS_ERR_INVALID_ARGUMENT, "only the Dummy candidate order (broadphase_kind 0) runs on the device");
+    if (config->broadphase_kind != 0 && config->broadphase_kind != 1) return fail(PS_ERR_INVALID_ARGUMENT, "broadphase_kind must be 0 (Dummy) or 1 (SpatialTree)");
     if (!(config->dt == config->dt)) return fail(PS_ERR_INVALID_ARGUMENT, "dt is NaN");
     if (g_device < 0) {
         rc = ps_init(-1);
@@ -511,6 +638,7 @@ int ps_batch_create(void** handle, const ps_bodies_view* bodies, const ps_joints
         return fail(PS_ERR_CUDA, "cannot create a stream on device %d", g_device);
     }
     rc = upload(B, true);
+    if (!rc && B->tree_mode) rc = tree_init_all(B);
     if (rc) {
         free_device(B);
         cudaStreamDestroy(B->stream);
@@ -578,6 +706,8 @@ static void fill_kargs(Batch* B, KArgs& a, int n_steps)
     a.hitcnt = B->d_hitcnt; a.cur = B->d_cur; a.pred = B->d_pred; a.S = B->d_S;
     a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.scratch = B->d_scratch; a.lvl = B->d_lvl; a.last = B->d_last;
     a.only_flagged = nullptr;
+    a.cand = B->tree_mode ? B->d_cand : nullptr;
+    a.cand_off = B->tree_mode ? B->d_cand_off : nullptr;
 }
 
 static void launch_fused(Batch* B, const KArgs& a, cudaStream_t st)
@@ -684,6 +814,16 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
         for (int s = 0; s < n_steps; s++) {
             int rc = launch_wide_step(B, a, st);
             if (rc) return rc;
+        }
+        return PS_OK;
+    }
+    if (B->tree_mode) {  // the candidate list of a step depends on the state the previous step left: one launch per step
+        a.n_steps = 1;
+        for (int s = 0; s < n_steps; s++) {
+            int rc = tree_update_and_upload(B, st);
+            if (rc) return rc;
+            launch_fused(B, a, st);
+            CK(cudaGetLastError());
         }
         return PS_OK;
     }
@@ -831,6 +971,14 @@ int ps_batch_get_candidates(void* handle, int32_t world, int32_t* n_pairs, int32
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
     if (world < 0 || world >= B->n_worlds) return fail(PS_ERR_OUT_OF_RANGE, "world %d outside [0,%d)", world, B->n_worlds);
+    if (B->tree_mode) {  // the list the last step walked (empty before the first step)
+        const int c0 = B->h_cand_off[world], c1 = B->h_cand_off[world + 1];
+        for (int k = c0; k < c1; k++)
+            if (pair_ids && k - c0 < pair_capacity) { pair_ids[2 * (k - c0)] = (int32_t)(B->h_cand[k] & 0xffff); pair_ids[2 * (k - c0) + 1] = (int32_t)(B->h_cand[k] >> 16); }
+        if (n_pairs) *n_pairs = c1 - c0;
+        if (pair_ids && c1 - c0 > pair_capacity) return fail(PS_ERR_CAPACITY, "need room for %d pairs", c1 - c0);
+        return PS_OK;
+    }
     // Dummy order (BroadPhase.fs:33-39) filtered by canIntersect (CollisionResolver.fs:58-60): a function of
     // the body set only, so it is produced here from the static flags.
     int o = B->cur.off[world], N = B->cur.off[world + 1] - o;
@@ -890,6 +1038,15 @@ int ps_batch_add_body(void* handle, int32_t world, const ps_bodies_view* one)
     rc = upload(B, true);
     if (rc) return rc;
     CK(cudaMemcpy(B->d_stats, keep.data(), keep.size() * sizeof(WorldStats), cudaMemcpyHostToDevice));
+    if (B->tree_mode) {  // BroadPhase.onNewObjectAdded (BroadPhase.fs:83-98): the new id joins the existing tree
+        rc = tree_pull_extents(B, B->stream);
+        if (rc) return rc;
+        const int o = h.off[world], id = h.off[world + 1] - o - 1;
+        if (!B->trees[world].insert(id, [&](int x) { return ext_of(B, o + x); }))
+            return fail(PS_ERR_INVALID_ARGUMENT, "world %d: object %d out of space bounds", world, id);  // the reference throws after its state update too
+        B->h_cand_off.assign((size_t)B->n_worlds + 1, 0);
+        B->h_cand.clear();
+    }
     return PS_OK;
 }
 
@@ -898,7 +1055,9 @@ int ps_batch_reset(void* handle)
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
     B->cur = B->init;  // bodies added later are dropped (Simulator.fs:36-40,113-121)
-    return upload(B, true);
+    int rc = upload(B, true);
+    if (!rc && B->tree_mode) rc = tree_init_all(B);  // initSimulationState builds the tree anew
+    return rc;
 }
 
 int ps_batch_stats(void* handle, ps_stats* out)

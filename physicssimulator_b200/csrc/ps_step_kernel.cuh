@@ -111,6 +111,11 @@ struct KArgs {
     // when set: only worlds with a non-zero flag are stepped (the batch-wide path hands its failed worlds over);
     // bit0 margin violated -> start at the 8x margin, bit1 static pose / too many statics -> exact serial walk
     const unsigned* only_flagged;
+    // SpatialTree candidate order (ps_step_config.broadphase_kind 1): the ordered candidate list of every world for THIS
+    // step, i | j << 16 with i < j, static-static pairs already dropped (csrc/ps_octree.hpp builds it on the host);
+    // nullptr = Dummy order, all (i<j) lexicographic
+    const unsigned* cand;
+    const int* cand_off;      // n_worlds+1
 };
 
 // ---- per-world working set: pointers into global scratch + a small shared-memory block -------------
@@ -442,6 +447,8 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
     s.par = a.par + (size_t)off * kParF;
     s.S = a.S + (size_t)off * 3 * kMaxStatics;
     const StepParams sp = a.sp;
+    const unsigned* cl = a.cand ? a.cand + a.cand_off[w] : nullptr;
+    const int ncand = (a.cand && live) ? a.cand_off[w + 1] - a.cand_off[w] : 0;
     const int Nw = warp_max(N);  // loop bound of the per-body phases (warp-uniform)
 
     // working copy of the world (coalesced, contiguous per world)
@@ -539,8 +546,34 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                 attempt = 2; fb_reason = 3;
             }
             if (tid == 0 && live) { long long t = clock64(); cyc[0] += t - tk; tk = t; }
-            // ---- B: near list, lexicographic order kept by a row scan ---------------------------------------
-            if (fast) {
+            // ---- B: near list ---------------------------------------------------------------------------------
+            // SpatialTree order: the near list is the candidate list minus the pairs the cull rules out, order kept by
+            // a ballot scan over chunks of T candidates (warp-uniform trip count)
+            if (a.cand) {
+                const unsigned tmask_ = (T == 32) ? FULL : (((1u << T) - 1u) << (tile * T));
+                const int nc_ = fast ? ncand : 0;
+                const int ncw = warp_max(nc_);
+                int kacc = 0;
+                for (int base = 0; base < ncw; base += T) {
+                    const int q = base + tid;
+                    unsigned ij = 0;
+                    bool pred = false;
+                    if (q < nc_) {
+                        ij = cl[q];
+                        pred = near_test(s, N, (int)(ij & 0xffff), (int)(ij >> 16));
+                    }
+                    const unsigned mine = (__ballot_sync(FULL, pred) & tmask_) >> (tile * T);
+                    if (pred) {
+                        const int pos = kacc + __popc(mine & ((1u << tid) - 1u));
+                        s.near[pos] = ij;
+                        s.hit[pos] = 0;
+                    }
+                    kacc += __popc(mine);
+                }
+                if (fast && tid == 0) bs.K = kacc;
+            }
+            // Dummy order: lexicographic order kept by a row scan
+            if (fast && !a.cand) {
                 for (int i = tid; i < N; i += T) {
                     int cn = 0;
                     for (int j = i + 1; j < N; j++) cn += near_test(s, N, i, j) ? 1 : 0;
@@ -548,7 +581,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                 }
             }
             __syncwarp();
-            if (fast && tid == 0) {
+            if (fast && !a.cand && tid == 0) {
                 int acc = 0;
                 for (int i = 0; i < N; i++) { int t = s.row[i]; s.row[i] = acc; acc += t; }
                 s.row[N] = acc;
@@ -556,7 +589,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
             }
             __syncwarp();
             const int K = fast ? bs.K : 0;
-            if (fast) {
+            if (fast && !a.cand) {
                 for (int i = tid; i < N; i += T) {
                     int o = s.row[i];
                     for (int j = i + 1; j < N; j++)
@@ -643,17 +676,23 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                     }
                 }
             }
-            // ---- exact serial walk over ALL pairs in Dummy order (BroadPhase.fs:33-39), one lane per world ------
+            // ---- exact serial walk over ALL candidates in order, one lane per world: Dummy order (BroadPhase.fs:33-39)
+            // or the SpatialTree list ---------------------------------------------------------------------------------
             {
-                int si = 0, sj = 1;
-                bool sact = serial && tid == 0 && N >= 2;
+                int si = 0, sj = 1, sk = 0;
+                bool sact = serial && tid == 0 && (a.cand ? ncand > 0 : N >= 2);
                 for (;;) {
                     if (!__any_sync(FULL, sact)) break;
+                    if (sact && a.cand) { const unsigned ij = cl[sk]; si = (int)(ij & 0xffff); sj = (int)(ij >> 16); }
                     bool valid = sact && !(s.isstat[si] && s.isstat[sj]);
                     if (valid) process_pair(c, si, sj, 0, false);
                     if (sact) {
-                        sj++;
-                        if (sj >= N) { si++; sj = si + 1; if (sj >= N) sact = false; }
+                        if (a.cand) {
+                            if (++sk >= ncand) sact = false;
+                        } else {
+                            sj++;
+                            if (sj >= N) { si++; sj = si + 1; if (sj >= N) sact = false; }
+                        }
                     }
                 }
             }

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
+import sys
 from dataclasses import dataclass, field
 from typing import Sequence, Tuple, Union
 
@@ -237,3 +238,49 @@ def ball_socket_local_anchors(world: dict, a: int, b: int, anchor_world: Sequenc
             loc.append(s)
         out.append(tuple(loc))
     return out[0], out[1]
+
+
+def getAABoundingBox(proto: RigidBodyPrototype):
+    """RigidBodyPrototype.getAABoundingBox (RigidBodyPrototype.fs:92-95) = SimulatorObject.getAABoundingBox of the built
+    body (SimulatorObject.fs:58-71): (centre, size).  A sphere's box has side = RADIUS (quirk Q5); a box takes
+    Box.worldAxisAlignedSize (Box.fs:69-85), evaluated like MathNet's dense M*v (zero-started sums)."""
+    arr = empty_bodies(1)
+    build_into(arr, 0, proto)
+    c = tuple(float(v) for v in arr["pos"][0])
+    if int(arr["shape"][0]) == SPHERE:
+        r = float(arr["dims"][0, 0])
+        return c, (r, r, r)
+    R = arr["rot"][0].reshape(3, 3)
+    h = [float(arr["dims"][0, k]) / 2.0 for k in range(3)]
+
+    def to_world(local):  # R * local + 0, dense M*v summed from 0.0 in index order
+        out = []
+        for i in range(3):
+            acc = 0.0
+            for q in range(3):
+                acc = acc + float(R[i, q]) * local[q]
+            out.append(acc + 0.0)
+        return out
+
+    ex, ey, ez = to_world([h[0], 0.0, 0.0]), to_world([0.0, h[1], 0.0]), to_world([0.0, 0.0, h[2]])
+    size = tuple((abs(ex[i]) + abs(ey[i]) + abs(ez[i])) * 2.0 for i in range(3))
+    return c, size
+
+
+class SpatialTreeBoundaries:
+    """SpatialTreeBoundaries module (RigidBodyPrototype.fs:97-132)."""
+
+    @staticmethod
+    def fromPrototypeAABBs(prototypes: Sequence[RigidBodyPrototype], padding: float, motionMargin: Sequence[float]):
+        """Union of the prototype AABBs grown by `padding` (static geometry) and `motionMargin` (dynamic travel):
+        returns (Min, Max) of the SpaceBoundaries record (Configuration.fs:9-11)."""
+        expand = [padding + float(m) for m in motionMargin]
+        big = sys.float_info.max
+        mn, mx = [big, big, big], [-big, -big, -big]
+        for p in prototypes:
+            c, s = getAABoundingBox(p)
+            for k in range(3):
+                half = s[k] * (1.0 / 2.0)  # Vector3D `/`: multiply by 1/s (Vector3D.fs:34)
+                mn[k] = min(c[k] - half, mn[k])
+                mx[k] = max(c[k] + half, mx[k])
+        return tuple(mn[k] - expand[k] for k in range(3)), tuple(mx[k] + expand[k] for k in range(3))

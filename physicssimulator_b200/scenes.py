@@ -65,8 +65,8 @@ def stack_scene() -> Tuple[List[P.RigidBodyPrototype], Configuration]:
 
 
 def domino_scene() -> Tuple[List[P.RigidBodyPrototype], Configuration]:
-    """DominoSceneData (Gui/Scenes/DominoScene.fs:13-67); the SpatialTree bounds there come from
-    SpatialTreeBoundaries.fromPrototypeAABBs — here the Dummy order is used (canonical GPU order)."""
+    """DominoSceneData (Gui/Scenes/DominoScene.fs:13-67), SpatialTree bounds from SpatialTreeBoundaries.fromPrototypeAABBs
+    as there (:41-55)."""
     count, thick, width, height, mass = 15, 0.08, 0.35, 1.2, 100.0
     spacing = thick + 0.4
     origin_y = -(float(count - 1) * spacing) / 2.0
@@ -75,7 +75,13 @@ def domino_scene() -> Tuple[List[P.RigidBodyPrototype], Configuration]:
         protos.append(P.createDefaultBox(width, thick, height).With(
             Mass=mass, ElasticityCoeff=0.05, StaticFrictionCoeff=0.7, KineticFrictionCoeff=0.55,
             Position=(0.0, origin_y + float(i) * spacing, height / 2.0)))
-    return protos, Configuration()
+    impulse_strength = 120.0
+    tip_reach = height + width  # "AABB grows to ~height when a domino tips over"
+    margin = tip_reach + impulse_strength / mass * 2.0
+    mn, mx = P.SpatialTreeBoundaries.fromPrototypeAABBs(protos, 2.0, (margin, margin, margin))
+    cfg = Configuration(BroadPhaseCollisionDetectionKind=BroadPhaseCollisionDetectionKind(
+        SpatialTreeConfiguration(LeafCapacity=4, SpaceBoundariesMin=mn, SpaceBoundariesMax=mx, MaxDepth=12)))
+    return protos, cfg
 
 
 # ---------------------------------------------------------------------------------------------

@@ -61,10 +61,8 @@ class BatchSimulator:
                  joints: Optional[Sequence[Sequence[Tuple[int, int, Sequence[float]]]]] = None, device: int = -1,
                  record_contacts: bool = False, exact_all_pairs: bool = False, _prebuilt=None):
         self.configuration = configuration or Configuration()
-        if not self.configuration.BroadPhaseCollisionDetectionKind.IsDummy:
-            # the SpatialTree candidate ORDER is history dependent (Q16); the device walks the canonical Dummy
-            # order, which yields the same colliding set whenever the octree does not drop a touching pair (Q5)
-            pass
+        # BroadPhaseCollisionDetectionKind.SpatialTree: the candidate ORDER is the persistent tree's (history dependent,
+        # Q16); the library keeps one tree per world on the host and feeds the device the ordered list every step
         sc = self.configuration.StepConfig
         if _prebuilt is not None:
             self._worlds = _prebuilt

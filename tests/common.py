@@ -75,12 +75,74 @@ def host_harness():
         d = os.path.join(ROOT, "tests", "host_harness")
         so = os.path.join(d, "libps_host_harness.so")
         src = os.path.join(d, "physics_host.cpp")
-        deps = [src] + [os.path.join(ROOT, "physicssimulator_b200", "csrc", f) for f in ("ps_physics.cuh", "ps_math.cuh", "ps_sincos.h")]
+        deps = [src] + [os.path.join(ROOT, "physicssimulator_b200", "csrc", f) for f in ("ps_physics.cuh", "ps_math.cuh", "ps_sincos.h", "ps_octree.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-x", "c++", src, "-o", so])
         _HH = ctypes.CDLL(so)
         _HH.hh_world_step_v.restype = None
+        _HH.hh_tree_create.restype = ctypes.c_void_p
+        for f in ("hh_tree_destroy", "hh_tree_set_extent", "hh_tree_set_root_leaf", "hh_tree_set_root_children", "hh_tree_remove"):
+            getattr(_HH, f).restype = None
     return _HH
+
+
+class ProductTree:
+    """the product's host-side SpatialTree (physicssimulator_b200/csrc/ps_octree.hpp, compiled into the host harness)
+    behind the interface of oracle.OracleTree"""
+
+    def __init__(self, max_leaf, max_depth, bounds):
+        bb = np.ascontiguousarray(np.array(bounds, dtype=np.float64).reshape(-1))
+        self.ndim = len(bb) // 2
+        h = host_harness().hh_tree_create(ctypes.c_int(max_leaf), ctypes.c_int(max_depth), ctypes.c_int(self.ndim),
+                                          bb.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        if not h:
+            raise ValueError("SpatialTree.init: invalid argument")
+        self.h = ctypes.c_void_p(h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                host_harness().hh_tree_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_extent(self, oid, extents):
+        e = np.ascontiguousarray(np.array(extents, dtype=np.float64).reshape(-1))
+        host_harness().hh_tree_set_extent(self.h, ctypes.c_int(oid), e.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+
+    def set_root_leaf(self, ids):
+        a = np.array(list(ids), dtype=np.int32)
+        host_harness().hh_tree_set_root_leaf(self.h, ctypes.c_int(len(a)), a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+
+    def set_root_children(self, children):
+        counts = np.array([len(c) for c in children], dtype=np.int32)
+        ids = np.array([i for c in children for i in c], dtype=np.int32)
+        host_harness().hh_tree_set_root_children(self.h, ctypes.c_int(len(children)), counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                                 ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+
+    def insert(self, oid) -> int:
+        return host_harness().hh_tree_insert(self.h, ctypes.c_int(oid))
+
+    def remove(self, oid):
+        host_harness().hh_tree_remove(self.h, ctypes.c_int(oid))
+
+    def dump(self) -> str:
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = host_harness().hh_tree_dump(self.h, buf, ctypes.c_int(len(buf)))
+        assert n >= 0
+        return buf.value.decode()
+
+    def num_buckets(self) -> int:
+        return host_harness().hh_tree_num_buckets(self.h)
+
+    def candidates(self, is_static):
+        st = np.ascontiguousarray(np.array(is_static, dtype=np.uint8))
+        out = np.zeros(1 << 20, dtype=np.uint32)
+        n = host_harness().hh_tree_candidates(self.h, st.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
+                                              out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.c_int(len(out)))
+        assert 0 <= n <= len(out)
+        return [(int(k) & 0xffff, int(k) >> 16) for k in out[:n]]
 
 
 def harness_step(bodies: dict, cfg_native, nsteps: int, cap_pairs=4096, cap_contacts=32768, fast=False):

@@ -9,6 +9,10 @@
 #include <vector>
 
 #include "../../physicssimulator_b200/csrc/ps_physics.cuh"
+#include "../../physicssimulator_b200/csrc/ps_octree.hpp"
+
+#include <cstring>
+#include <map>
 
 using namespace psp;
 
@@ -106,5 +110,89 @@ void hh_world_step(int N, const double* par, double* dyn, const ps_step_config* 
                    int32_t* last_pairs, uint32_t* last_feats, double* last_contacts, int32_t* last_counts, int cap_pairs, int cap_contacts)
 {
     hh_world_step_v(N, par, dyn, cfg, nsteps, counters, last_pairs, last_feats, last_contacts, last_counts, cap_pairs, cap_contacts, 0);
+}
+
+// ---- the product's host-side SpatialTree (ps_octree.hpp) behind the same hooks as the oracle's tree, so that the
+// reference's known-answer facts (PhysicsSimulator.Tests/UtilitiesTests.fs) run against it too ------------------
+}  // extern "C"
+struct HHTree {
+    int ndim;
+    pst::Tree<1> t1; pst::Tree<2> t2; pst::Tree<3> t3;
+    std::map<int, std::vector<double>> ext;  // id -> (size, pos) per dimension
+};
+template <int D> static pst::Ext<D> hh_ext(const HHTree* h, int id)
+{
+    pst::Ext<D> e{};
+    auto it = h->ext.find(id);
+    for (int k = 0; k < D; k++) { e.size[k] = it->second[2 * k]; e.pos[k] = it->second[2 * k + 1]; }
+    return e;
+}
+extern "C" {
+void* hh_tree_create(int max_leaf, int max_depth, int ndim, const double* bounds /* (lo, hi) per dimension */)
+{
+    if (ndim < 1 || ndim > 3) return nullptr;
+    HHTree* h = new HHTree();
+    h->ndim = ndim;
+    double lo[3], hi[3];
+    for (int k = 0; k < ndim; k++) { lo[k] = bounds[2 * k]; hi[k] = bounds[2 * k + 1]; }
+    bool ok = ndim == 1 ? h->t1.init(max_leaf, max_depth, lo, hi) : ndim == 2 ? h->t2.init(max_leaf, max_depth, lo, hi) : h->t3.init(max_leaf, max_depth, lo, hi);
+    if (!ok) { delete h; return nullptr; }
+    return h;
+}
+void hh_tree_destroy(void* p) { delete (HHTree*)p; }
+void hh_tree_set_extent(void* p, int id, const double* e) { HHTree* h = (HHTree*)p; h->ext[id].assign(e, e + 2 * h->ndim); }
+void hh_tree_set_root_leaf(void* p, int n, const int32_t* ids)
+{
+    HHTree* h = (HHTree*)p;
+    std::vector<int> v(ids, ids + n);
+    if (h->ndim == 1) h->t1.set_root_leaf(v); else if (h->ndim == 2) h->t2.set_root_leaf(v); else h->t3.set_root_leaf(v);
+}
+void hh_tree_set_root_children(void* p, int nkids, const int32_t* counts, const int32_t* ids)
+{
+    HHTree* h = (HHTree*)p;
+    std::vector<std::vector<int>> kids;
+    for (int c = 0, o = 0; c < nkids; o += counts[c], c++) kids.emplace_back(ids + o, ids + o + counts[c]);
+    if (h->ndim == 1) h->t1.set_root_children(kids); else if (h->ndim == 2) h->t2.set_root_children(kids); else h->t3.set_root_children(kids);
+}
+int hh_tree_insert(void* p, int id)
+{
+    HHTree* h = (HHTree*)p;
+    if (!h->ext.count(id)) return -2;
+    bool ok = h->ndim == 1 ? h->t1.insert(id, [&](int o) { return hh_ext<1>(h, o); })
+            : h->ndim == 2 ? h->t2.insert(id, [&](int o) { return hh_ext<2>(h, o); })
+                           : h->t3.insert(id, [&](int o) { return hh_ext<3>(h, o); });
+    return ok ? 0 : -1;
+}
+void hh_tree_remove(void* p, int id)
+{
+    HHTree* h = (HHTree*)p;
+    auto gone = [&](int o) { return o == id; };
+    if (h->ndim == 1) h->t1.remove_if(gone); else if (h->ndim == 2) h->t2.remove_if(gone); else h->t3.remove_if(gone);
+}
+int hh_tree_dump(void* p, char* buf, int cap)
+{
+    HHTree* h = (HHTree*)p;
+    std::string s = h->ndim == 1 ? h->t1.dump() : h->ndim == 2 ? h->t2.dump() : h->t3.dump();
+    if ((int)s.size() + 1 > cap) return -1;
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+int hh_tree_num_buckets(void* p)
+{
+    HHTree* h = (HHTree*)p;
+    int n = 0;
+    auto f = [&](const std::vector<int>&) { n++; };
+    if (h->ndim == 1) h->t1.for_each_bucket(f); else if (h->ndim == 2) h->t2.for_each_bucket(f); else h->t3.for_each_bucket(f);
+    return n;
+}
+// candidate list of a 3-D tree (BroadPhase.getCollisionCandidates + canIntersect), ids i | j << 16
+int hh_tree_candidates(void* p, const unsigned char* is_static, uint32_t* out, int cap)
+{
+    HHTree* h = (HHTree*)p;
+    if (h->ndim != 3) return -1;
+    std::vector<uint32_t> v;
+    pst::candidates(h->t3, is_static, v);
+    for (int k = 0; k < (int)v.size() && k < cap; k++) out[k] = v[k];
+    return (int)v.size();
 }
 }

@@ -37,7 +37,7 @@ def test_no_signature_mentions_torch():
 
 def test_config_struct_layout_matches_ctypes():
     from physicssimulator_b200.configuration import ps_step_config
-    assert ctypes.sizeof(ps_step_config) == 5 * 8 + 8 * 4
+    assert ctypes.sizeof(ps_step_config) == 5 * 8 + 10 * 4 + 6 * 8
     from physicssimulator_b200._native import ps_stats
     assert ctypes.sizeof(ps_stats) == 14 * 8
 

@@ -25,7 +25,11 @@ def _oracle_worlds(worlds, cfg, joints=None):
             for (a, bb, anchor) in joints[w]:
                 la, lb = P.ball_socket_local_anchors(b, a, bb, anchor)
                 jl.append((a, bb, la, lb))
-        out.append(OracleWorld(b, to_native_config(cfg), joints=jl))
+        o = OracleWorld(b, to_native_config(cfg), joints=jl)
+        tc = cfg.BroadPhaseCollisionDetectionKind.SpatialTree
+        if tc is not None:  # the oracle's persistent tree (pinned by the reference's known-answer facts)
+            assert o.use_spatial_tree(tc.LeafCapacity, tc.MaxDepth, tc.SpaceBoundariesMin, tc.SpaceBoundariesMax) == 0
+        out.append(o)
     return out
 
 
@@ -319,3 +323,64 @@ def test_tight_margins_exercise_the_verification_and_the_retry(monkeypatch, path
     st = sim.Stats()
     assert st["margin_verified_steps"] > 0, st
     sim.close()
+
+
+# ---- BroadPhaseCollisionDetectionKind.SpatialTree: the candidate ORDER of the persistent tree ---------------------
+def _tree_cfg(**kw):
+    from physicssimulator_b200.configuration import BroadPhaseCollisionDetectionKind, SpatialTreeConfiguration
+    return Configuration(BroadPhaseCollisionDetectionKind=BroadPhaseCollisionDetectionKind(SpatialTreeConfiguration(**kw)))
+
+
+@pytest.mark.parametrize("tile", ["", "4", "16"])
+def test_spatial_tree_mode_gui_scenes(monkeypatch, tile):
+    """the Gui scenes in the configuration they ship with (Gui/Scenes/StackScene.fs:36-42, DominoScene.fs:45-55): states,
+    colliding sets, contacts, feature ids AND the ordered candidate list of every step chunk equal the oracle's"""
+    if tile:
+        monkeypatch.setenv("PS_B200_TILE", tile)
+    s, cfg_s = scenes.stack_scene()
+    _run([s], cfg_s, [1, 4, 45, 150], f"stack/tree/{tile}")
+    d, cfg_d = scenes.domino_scene()
+    _run([d], cfg_d, [1, 4, 45, 100], f"domino/tree/{tile}")
+
+
+def test_spatial_tree_mode_batch_of_worlds_and_exact_walk():
+    """one tree per world; several worlds per launch; the exact serial walk follows the tree's list too"""
+    cfg = _tree_cfg(LeafCapacity=2, MaxDepth=10)
+    c1, _ = scenes.c1_stack20()
+    s, _ = scenes.stack_scene()
+    _run([c1, s, c1], cfg, [1, 9, 60, 130], "c1+stack/tree")
+    _run([s, c1], cfg, [1, 9, 60], "tree/serial", exact=True)
+    cfg3 = scenes.c3_mixed128(0)[1].With(BroadPhaseCollisionDetectionKind=_tree_cfg(
+        LeafCapacity=3, MaxDepth=6, SpaceBoundariesMin=(-30.0, -30.0, -3.0), SpaceBoundariesMax=(30.0, 30.0, 30.0)).BroadPhaseCollisionDetectionKind)
+    w3 = [scenes.c3_mixed128(w, n_boxes=14, n_spheres=14)[0] for w in range(5)]
+    _run(w3, cfg3, [1, 19, 60], "c3 slices/tree")
+
+
+def test_spatial_tree_mode_mutations_and_errors():
+    """AddObject joins the existing tree (BroadPhase.onNewObjectAdded), Reset rebuilds it; a body outside the space at
+    construction is an ArgumentException in the reference (SpatialTree.fs:171-172)"""
+    from physicssimulator_b200.simulator import Simulator, BatchSimulator
+    from oracle.oracle import OracleWorld
+    protos, cfg = scenes.stack_scene()
+    tc = cfg.BroadPhaseCollisionDetectionKind.SpatialTree
+    sim = Simulator(protos, cfg, device=0)
+    o = OracleWorld(P.build_world(protos), to_native_config(cfg))
+    assert o.use_spatial_tree(tc.LeafCapacity, tc.MaxDepth, tc.SpaceBoundariesMin, tc.SpaceBoundariesMax) == 0
+    sim.Step(25); o.step(25)
+    new = P.createDefaultCube(0.5).With(Mass=50.0, Position=(0.0, -3.0, 3.0))
+    sim.AddObject(new)
+    one = P.empty_bodies(1); P.build_into(one, 0, new)
+    assert o.add_body(one) == 5
+    sim.Step(70); o.step(70)
+    got, ref = sim._b.WorldState(0), o.get_state()
+    for k in ("pos", "vel", "rot"):
+        assert same_bits(got[k], ref[k]), k
+    sim.Reset()
+    o2 = OracleWorld(P.build_world(protos), to_native_config(cfg))
+    assert o2.use_spatial_tree(tc.LeafCapacity, tc.MaxDepth, tc.SpaceBoundariesMin, tc.SpaceBoundariesMax) == 0
+    sim.Step(40); o2.step(40)
+    assert same_bits(sim._b.WorldState(0)["pos"], o2.get_state()["pos"])
+    sim.Dispose()
+    far = protos + [P.createDefaultCube(1.0).With(Position=(100.0, 0.0, 0.0))]
+    with pytest.raises(ValueError):
+        BatchSimulator([far], cfg, device=0)

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-CMD="python tools/sweep.py --workload c3 --worlds 16384 --steps 2 --settle 203 --variants wide:1:16"
-ncu --set full --clock-control none --import-source on -k regex:wide_round_bb -s 8600 -c 1 -o gpurun_out/prof_c3_bb -f $CMD > gpurun_out/ncu_bb.log 2>&1; echo "ncu bb rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:wide_round_resolve -s 8600 -c 1 -o gpurun_out/prof_c3_res -f $CMD > gpurun_out/ncu_res.log 2>&1; echo "ncu res rc=$?"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
+timeout 300 python tools/sweep.py --workload c2 --worlds 4096 --steps 20 --variants "fused:1:16" 2>&1 | grep -v "^\["
+timeout 300 python tools/sweep.py --workload c3 --worlds 16384 --steps 6 --settle 203 --variants "wide:1:16" 2>&1 | grep -v "^\["
