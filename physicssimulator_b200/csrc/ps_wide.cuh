@@ -71,6 +71,9 @@ struct WArgs {
 };
 
 enum { WF_MARGIN = 1, WF_STATIC = 2, WF_CAPACITY = 4 };
+#ifndef PS_WIDE_MINB
+#define PS_WIDE_MINB 2  // resident 128-thread CTAs per SM the box-box and resolve kernels are compiled for (2 -> up to 255 registers)
+#endif
 
 // Every pair of a round reserves its slot in the round's lists from the SAME counter.  One atomic per thread on one
 // address serialises in L2 (a round of 25 K box pairs spent most of its 140 us there, round 1 with 10^6 pairs
@@ -505,12 +508,12 @@ __global__ void __launch_bounds__(128) wide_round_detect(WArgs a, unsigned first
     else wide_bb_quick_body(a, first + c0 + c1, c2, level, (blk - b0 - b1) * 128 + threadIdx.x);
 }
 // stage 2: full box-box SAT + contact generation on the survivors of the quick test
-__global__ void __launch_bounds__(128) wide_round_bb(WArgs a, unsigned first_bb, unsigned c2, int level)
+__global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_bb(WArgs a, unsigned first_bb, unsigned c2, int level)
 {
     wide_detect_body<2>(a, first_bb, c2, level, blockIdx.x * 128 + threadIdx.x);
 }
 // stage 3: solve + write-back of every colliding pair of the round
-__global__ void __launch_bounds__(128) wide_round_resolve(WArgs a, unsigned first, unsigned c0, unsigned c1, unsigned c2, int level)
+__global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_resolve(WArgs a, unsigned first, unsigned c0, unsigned c1, unsigned c2, int level)
 {
     const unsigned b0 = (c0 + 127) / 128, b1 = (c1 + 127) / 128;
     const unsigned blk = blockIdx.x;
