@@ -64,10 +64,11 @@ def lib():
     """Load libps_b200.so; raises if it was not built (run __graft_entry__.build())."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing: the CUDA extension was not built and there is no CPU path. "
+        path = os.environ.get("PS_B200_LIB", LIB_PATH)  # tuning: another BUILD of the same CUDA library (tools/variants)
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: the CUDA extension was not built and there is no CPU path. "
                                "Run `python -c 'import __graft_entry__ as g; g.build()'`.")
-        L = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(path)
         L.ps_last_error.restype = c_char_p
         _lib = L
     return _lib

@@ -60,6 +60,7 @@ struct Batch {
     HostJoints joints;
     int n_worlds = 0, n_bodies = 0, n_dynamic = 0, max_n = 0;
     int threads = 8;  // lanes per world
+    int minb = 16;    // register build of the step kernel: one-warp CTAs per SM it allows (16 -> 128 regs, 8 -> 255)
     size_t smem = 0;
     // device
     double* d_dyn = nullptr;
@@ -291,10 +292,22 @@ int upload(Batch* B, bool with_state)
     // lanes per world (tile): a wavefront level of a 128-body pile holds ~10 pairs, so 8 lanes per world and 4
     // worlds per warp keep the lanes busy; with few worlds wider tiles give the SMs more warps to overlap
     B->threads = 8;
+    B->minb = PS_MINB32;
     if ((long long)B->n_worlds * 4 / 32 >= 148 * 12) B->threads = 4;
-    if ((long long)B->n_worlds * 8 / 32 < 148 * 8) B->threads = 16;
-    if ((long long)B->n_worlds * 16 / 32 < 148 * 8) B->threads = 32;
+    {   // Latency regime: every one-warp CTA of the batch is resident at 8 per SM -> the 255-register build, and the
+        // widest tile (up to 16 lanes per world) that still keeps the batch in that single wave.  Measured (B200, ms per
+        // step, 255 registers): C2 4096 worlds T=4 2.38, T=8 1.62, T=16 (two waves) 1.78; C4 8192 worlds T=4 2.32, T=8
+        // (two waves) 2.65; C2 1024 worlds T=16 0.77, T=32 0.80.
+        const long long wave = 148LL * 8;
+        int t = 0;
+        if ((long long)B->n_worlds * 16 / 32 <= wave) t = 16;
+        else if ((long long)B->n_worlds * 8 / 32 <= wave) t = 8;
+        else if ((long long)B->n_worlds * 4 / 32 <= wave) t = 4;
+        if (t) { B->threads = t; B->minb = 8; }
+        if ((long long)B->n_worlds * 16 / 32 < 148) B->threads = 32;  // a handful of worlds: all lanes to each of them
+    }
     if (const char* e = getenv("PS_B200_TILE")) { int t = atoi(e); if (t == 4 || t == 8 || t == 16 || t == 32) B->threads = t; }  // tuning knob
+    if (const char* e = getenv("PS_B200_MINB")) { int m = atoi(e); if (m == 8 || m == PS_MINB32) B->minb = m; }              // tuning knob
     B->smem = smem_bytes(B->max_n) * (size_t)(32 / B->threads);
     int dev_max = 0;
     CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, B->device));
@@ -302,20 +315,19 @@ int upload(Batch* B, bool with_state)
         return fail(PS_ERR_INVALID_ARGUMENT, "largest world (%d bodies) needs %zu B of shared memory; device allows %d", B->max_n, B->smem, dev_max);
     {   // the kernel needs little shared memory: reserve what PS_RESIDENT CTAs per SM need and leave the rest of the
         // unified array to L1 (local stack of the per-pair routines)
-        int resident = 12;
+        int resident = B->minb == 8 ? 8 : 12;
         if (const char* e = getenv("PS_B200_RESIDENT")) resident = std::max(1, atoi(e));
         size_t need = (size_t)resident * (B->smem + 1024 + 256);
         int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 1);
         if (const char* e = getenv("PS_B200_CARVEOUT")) pct = atoi(e);
-        CK(cudaFuncSetAttribute(step_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        CK(cudaFuncSetAttribute(step_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        CK(cudaFuncSetAttribute(step_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        CK(cudaFuncSetAttribute(step_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        const int dyn = (int)std::max<size_t>(B->smem, 1024);
+#define PS_SET_ATTRS(T_, M_)                                                                                  \
+        CK(cudaFuncSetAttribute(step_kernel<T_, M_>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)); \
+        CK(cudaFuncSetAttribute(step_kernel<T_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        PS_SET_ATTRS(4, PS_MINB32) PS_SET_ATTRS(8, PS_MINB32) PS_SET_ATTRS(16, PS_MINB32) PS_SET_ATTRS(32, PS_MINB32)
+        PS_SET_ATTRS(4, 8) PS_SET_ATTRS(8, 8) PS_SET_ATTRS(16, 8) PS_SET_ATTRS(32, 8)
+#undef PS_SET_ATTRS
     }
-    CK(cudaFuncSetAttribute(step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
-    CK(cudaFuncSetAttribute(step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
-    CK(cudaFuncSetAttribute(step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
-    CK(cudaFuncSetAttribute(step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(B->smem, 1024)));
 
     size_t nb = (size_t)std::max(1, B->n_bodies);
     CK(cudaMalloc(&B->d_dyn, nb * kDynF * sizeof(double)));
@@ -714,10 +726,17 @@ static void launch_fused(Batch* B, const KArgs& a, cudaStream_t st)
 {
     const int wpc = 32 / B->threads;  // worlds per one-warp CTA
     const int grid = (B->n_worlds + wpc - 1) / wpc;
-    if (B->threads == 4) step_kernel<4><<<grid, 32, B->smem, st>>>(a);
-    else if (B->threads == 8) step_kernel<8><<<grid, 32, B->smem, st>>>(a);
-    else if (B->threads == 16) step_kernel<16><<<grid, 32, B->smem, st>>>(a);
-    else step_kernel<32><<<grid, 32, B->smem, st>>>(a);
+    if (B->minb == 8) {
+        if (B->threads == 4) step_kernel<4, 8><<<grid, 32, B->smem, st>>>(a);
+        else if (B->threads == 8) step_kernel<8, 8><<<grid, 32, B->smem, st>>>(a);
+        else if (B->threads == 16) step_kernel<16, 8><<<grid, 32, B->smem, st>>>(a);
+        else step_kernel<32, 8><<<grid, 32, B->smem, st>>>(a);
+    } else {
+        if (B->threads == 4) step_kernel<4, PS_MINB32><<<grid, 32, B->smem, st>>>(a);
+        else if (B->threads == 8) step_kernel<8, PS_MINB32><<<grid, 32, B->smem, st>>>(a);
+        else if (B->threads == 16) step_kernel<16, PS_MINB32><<<grid, 32, B->smem, st>>>(a);
+        else step_kernel<32, PS_MINB32><<<grid, 32, B->smem, st>>>(a);
+    }
     B->launches++;
 }
 

@@ -46,6 +46,9 @@ using namespace psp;
 constexpr int kDynF = 18;       // doubles of dynamic state per body
 constexpr int kParF = 16;       // doubles of parameters per body
 constexpr int kMaxLevels = 1022;
+#ifndef PS_PREFETCH
+#define PS_PREFETCH 0  // 1: process_pair requests both body records before it consumes either (experiment)
+#endif
 constexpr int kMaxStatics = 4;  // static bodies per world whose pairs run in parallel (more -> serial walk)
 constexpr int kMaxThreads = 128;
 constexpr int kBoostSteps = 8;  // steps of doubled margins after a world had to verify (a restart costs a whole world-step)
@@ -297,8 +300,30 @@ PSD void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
     ld_par(c.s.par, c.N, i, pi);
     ld_par(c.s.par, c.N, j, pj);
     Dyn di, dj;
+#if PS_PREFETCH
+    {   // both records are requested before either is consumed (the two L2 round trips overlap)
+        const bool vi = c.s.pvalid[i] != 0, vj = c.s.pvalid[j] != 0;
+        ld_dyn(vi ? c.s.pred : c.s.dyn, c.N, i, di);
+        ld_dyn(vj ? c.s.pred : c.s.dyn, c.N, j, dj);
+        if (!vi) {
+            Dyn cur = di;
+            integrate(cur, pi, c.a->sp, di);
+            st_dyn(c.s.pred, c.N, i, di);
+            c.s.pvalid[i] = 1;
+            if (fast) track_margin(c, i, di.x);
+        }
+        if (!vj) {
+            Dyn cur = dj;
+            integrate(cur, pj, c.a->sp, dj);
+            st_dyn(c.s.pred, c.N, j, dj);
+            c.s.pvalid[j] = 1;
+            if (fast) track_margin(c, j, dj.x);
+        }
+    }
+#else
     get_pred(c, i, pi, di, fast);
     get_pred(c, j, pj, dj, fast);
+#endif
     const bool bb = (pi.shape == 1) && (pj.shape == 1);
     int err = 0, ovf = 0, nc;
     c.tested++;
@@ -407,8 +432,14 @@ PSD int warp_max(int v)
 // the maximum over the warp's tiles, lanes past their tile's bound are predicated off), so that the heavy routines
 // (integrate, process_pair) are entered by lanes of different worlds at the same program counter and share the
 // warp's instruction issue.  No lane returns early; a tile without a world has N = 0.
-template <int T>
-__global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
+//
+// MINB = one-warp CTAs per SM the register allocation has to allow: 16 -> 128 registers (batches that need several
+// waves are throughput bound and want the residency), 8 -> 255 registers (a batch whose CTAs are all resident at 8 per
+// SM is bound by the latency of each warp, and the 128-register build spills the two body records of a pair: measured
+// C2 4096 worlds 1.82 -> 1.62 ms, C4 8192 worlds 3.23 -> 2.32 ms, C2 1024 worlds 1.00 -> 0.77 ms per step; C3 on the
+// fused kernel alone, 16384 worlds, 57.6 -> 64.7 ms: many waves, there the residency wins).
+template <int T, int MINB>
+__global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BlockShared bs_all[32 / T];
@@ -485,6 +516,7 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
         for (int pass = 0; pass < 3; pass++) {  // a tile needs at most three attempts
             if (!__any_sync(FULL, !finished)) break;
             const bool run = !finished;
+            bool folding = false;  // this pass ends with the static fold (phase E)
             bool fast = run && attempt < 2;
             const bool serial = run && attempt == 2;
             if (run) {
@@ -741,7 +773,39 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                     fb_reason = 1;
                     attempt++;
                 } else {
-                    // ---- E: static bodies: L = fold over their colliding pairs in pair order -------------------
+                    finished = true;
+                    folding = true;
+                }
+            } else if (serial) {
+                finished = true;
+            }
+            // ---- E: static bodies: L = fold over their colliding pairs in pair order.  The tile first compacts, in
+            // order, the partners of the colliding pairs that involve a static body (ballot scan over chunks of T
+            // near pairs, warp-uniform trip count; the level-order table is free by now and takes the list), then one
+            // lane per static body folds its entries: the dependent additions of a ~20-entry list instead of a
+            // latency-bound walk over the whole near list by that one lane.
+            {
+                const unsigned tmask_ = (T == 32) ? FULL : (((1u << T) - 1u) << (tile * T));
+                const int Kf = folding ? K : 0;
+                const int Kw = warp_max(Kf);
+                int cnt = 0;
+                for (int base = 0; base < Kw; base += T) {
+                    const int k = base + tid;
+                    bool pred = false;
+                    unsigned short ent = 0;
+                    if (k < Kf && s.hit[k]) {
+                        const unsigned ij = s.near[k];
+                        const int i = ij & 0xffff, j = ij >> 16;
+                        // at most one body of a near pair is static (canIntersect); entry = partner | ordinal << 12
+                        if (s.isstat[i]) { pred = true; ent = (unsigned short)(j | ((s.isstat[i] - 1) << 12)); }
+                        else if (s.isstat[j]) { pred = true; ent = (unsigned short)(i | ((s.isstat[j] - 1) << 12)); }
+                    }
+                    const unsigned mine = (__ballot_sync(FULL, pred) & tmask_) >> (tile * T);
+                    if (pred) s.order[cnt + __popc(mine & ((1u << tid) - 1u))] = ent;
+                    cnt += __popc(mine);
+                }
+                __syncwarp();
+                if (folding)
                     for (int b = tid; b < N; b += T) {
                         if (!s.isstat[b]) continue;
                         Par p; ld_par(s.par, N, b, p);
@@ -749,13 +813,12 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                         double* pb = s.pred + (size_t)b * kDynF;
                         d3 L = mk(cb[15], cb[16], cb[17]);
                         d3 dL = scale(sp.dt, p.T);
-                        const double* Sb = s.S + 3 * (s.isstat[b] - 1) * N;
-                        for (int k = 0; k < K; k++) {
-                            if (!s.hit[k]) continue;
-                            unsigned ij = s.near[k];
-                            int i = ij & 0xffff, j = ij >> 16;
-                            int other;
-                            if (i == b) other = j; else if (j == b) other = i; else continue;
+                        const unsigned ord = (unsigned)(s.isstat[b] - 1);
+                        const double* Sb = s.S + 3 * ord * N;
+                        for (int q = 0; q < cnt; q++) {
+                            const unsigned ent = s.order[q];
+                            if ((ent >> 12) != ord) continue;
+                            const int other = ent & 0xfff;
                             L = L + dL;  // the predicted copy's integration
                             L = L + mk(Sb[3 * other], Sb[3 * other + 1], Sb[3 * other + 2]);
                         }
@@ -764,10 +827,6 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
                         d3 Lf = L + dL;
                         pb[15] = Lf.x; pb[16] = Lf.y; pb[17] = Lf.z;
                     }
-                    finished = true;
-                }
-            } else if (serial) {
-                finished = true;
             }
             // (a tile that switched to the serial walk above has run == true, fast == false, serial == false:
             //  it goes round again with attempt == 2)
@@ -846,12 +905,11 @@ __global__ void __launch_bounds__(32, PS_MINB32) step_kernel(KArgs a)
             if (on) {
                 if (!need) ld_dyn(s.pred, N, b, out);
                 st_dyn(s.dyn, N, b, out);
+                st_dyn(gdyn, N, b, out);  // publish the step (also the restart point of the next step's fallback)
                 s.nprev[b] = s.nhit[b];
             }
         }
         __syncwarp();
-        // publish the step (also the restart point of the next step's fallback)
-        for (int k = tid; k < kDynF * N; k += T) gdyn[k] = s.dyn[k];
         if (tid == 0 && live) { long long t = clock64(); cyc[4] += t - tk; if ((unsigned long long)(t - tk0) > cyc_max) cyc_max = t - tk0; }
 
         // fold per-lane counters into the tile's block
