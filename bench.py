@@ -231,14 +231,22 @@ def main():
     host = {k: v.numpy() for k, v in pinned.items()}
     e2e_steps = max(3, min(args.steps, 10))
     sim.batch.set_state(host); sim.batch.step(1); sim.batch.get_state(out=host)  # warm
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):  # informational: the three calls one after the other
+        sim.batch.set_state(host)
+        sim.batch.step(1)
+        sim.batch.get_state(out=host)
+    e2e_seq_s = time.perf_counter() - t1
+    sim.batch.step_host(host, 1, out=host)  # warm (creates the chunk streams)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     for _ in range(e2e_steps):
-        sim.batch.set_state(host)
-        sim.batch.step(1)
-        sim.batch.get_state(out=host)
+        # the reference-facing call: state in host memory -> one step -> state in host memory (ps_batch_step_host:
+        # H2D, step kernel and D2H pipelined over chunks of worlds)
+        sim.batch.step_host(host, 1, out=host)
     e2e_s = time.perf_counter() - t1
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -274,7 +282,9 @@ def main():
                        "l2": "256 MiB buffer written between timed iterations (outside the CUDA-event pairs)",
                        "parallelism": f"worlds sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": bytes_state, "d2h_bytes_per_step": bytes_state,
-                    "steps": e2e_steps, "what": "ps_batch_set_state(host pinned) + ps_batch_step(1) + ps_batch_get_state(host) per step"},
+                    "steps": e2e_steps, "what": "ps_batch_step_host(pinned host state in, 1 step, pinned host state out) per step: H2D + step + D2H inside the timed region, pipelined over world chunks",
+                    "sequential_calls_value_this_rank": n_dyn * per_gpu * e2e_steps / e2e_seq_s,
+                    "sequential_calls_what": "ps_batch_set_state + ps_batch_step(1) + ps_batch_get_state, one after the other (informational)"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "psk::step_kernel" if sched["path"] == "fused" else "psw::wide_* stages + psk::step_kernel (one step)", "algorithmic_bytes_per_body_step": B_ALG, "kernel_ms": kernel_ms,

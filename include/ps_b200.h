@@ -164,6 +164,14 @@ int ps_batch_get_state(void* handle, int32_t w0, int32_t w1, double* pos, double
                        double* ang_mom);
 int ps_batch_set_state(void* handle, int32_t w0, int32_t w1, const double* pos, const double* vel,
                        const double* rot, const double* ang_mom);
+/* marshal -> n x Simulator.updateSimulation -> unmarshal in ONE call (Simulator.fs:47-62 seen from a caller whose
+ * SimulatorState lives in managed memory): equivalent to ps_batch_set_state(all) + ps_batch_step(n) +
+ * ps_batch_get_state(all), but pipelined over chunks of worlds on separate streams so that the host<->device copies
+ * of one chunk hide behind the step of the others.  Pinned host buffers make the copies asynchronous; pageable ones
+ * work, unpipelined.  in and out may be the same arrays. */
+int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, const double* vel_in,
+                       const double* rot_in, const double* ang_mom_in, double* pos_out, double* vel_out,
+                       double* rot_out, double* ang_mom_out);
 /* same read-back into caller-owned DEVICE buffers (plain device pointers): no host round trip */
 int ps_batch_get_state_device(void* handle, int32_t w0, int32_t w1, double* d_pos, double* d_vel,
                               double* d_rot, double* d_ang_mom, void* cuda_stream);

@@ -26,7 +26,7 @@ EXPORTS = (
     "ps_batch_step_async", "ps_batch_synchronize", "ps_batch_get_state", "ps_batch_set_state",
     "ps_batch_get_state_device", "ps_batch_get_contacts", "ps_batch_get_candidates", "ps_batch_apply_impulse",
     "ps_batch_add_body", "ps_batch_reset", "ps_batch_stats", "ps_batch_num_bodies", "ps_broadphase_pairs",
-    "ps_batch_debug_cycles", "ps_batch_schedule",
+    "ps_batch_debug_cycles", "ps_batch_schedule", "ps_batch_step_host",
 )
 
 
@@ -166,6 +166,18 @@ class Batch:
         w1 = self.n_worlds if w1 is None else w1
         a = [np.ascontiguousarray(st[k], dtype=np.float64) for k in ("pos", "vel", "rot", "ang_mom")]
         check(lib().ps_batch_set_state(self.h, c_int32(w0), c_int32(w1), dptr(a[0]), dptr(a[1]), dptr(a[2]), dptr(a[3])))
+
+    def step_host(self, st: dict, n=1, out=None):
+        """set_state(all) + step(n) + get_state(all) in one call, copies pipelined against the step over chunks of
+        worlds (ps_batch_step_host).  `st`/`out`: dicts of C-contiguous float64 arrays (pinned memory makes the copies
+        asynchronous); out may be st."""
+        a = [np.ascontiguousarray(st[k], dtype=np.float64) for k in ("pos", "vel", "rot", "ang_mom")]
+        if out is None:
+            n_b = int(self.world_offset[-1])
+            out = {"pos": np.empty((n_b, 3)), "vel": np.empty((n_b, 3)), "rot": np.empty((n_b, 9)), "ang_mom": np.empty((n_b, 3))}
+        check(lib().ps_batch_step_host(self.h, c_int32(n), dptr(a[0]), dptr(a[1]), dptr(a[2]), dptr(a[3]),
+                                       dptr(out["pos"]), dptr(out["vel"]), dptr(out["rot"]), dptr(out["ang_mom"])))
+        return out
 
     def get_state_device(self, d_pos, d_vel, d_rot, d_L, w0=0, w1=None, stream=0):
         """raw device pointers (ints), e.g. torch tensors' data_ptr()"""

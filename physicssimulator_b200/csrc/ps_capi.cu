@@ -102,6 +102,9 @@ struct Batch {
     int rec_pair_cap = 0, rec_contact_cap = 0;
     ps_stats* d_stats_sum = nullptr;
     cudaStream_t stream = nullptr;
+    std::vector<cudaStream_t> chunk_streams;  // ps_batch_step_host: one stream per world chunk
+    std::vector<cudaEvent_t> chunk_done;
+    cudaEvent_t chunk_start = nullptr;
     long long launches = 0;
     // SpatialTree candidate order (broadphase_kind 1): one persistent tree per world on the host (the reference keeps it
     // in SimulatorState, BroadPhase.fs:100-127), extents come from the device, the ordered list goes back
@@ -693,6 +696,9 @@ int ps_batch_destroy(void* handle)
         }
     }
     free_device(B);
+    for (cudaStream_t s : B->chunk_streams) cudaStreamDestroy(s);
+    for (cudaEvent_t e : B->chunk_done) cudaEventDestroy(e);
+    if (B->chunk_start) cudaEventDestroy(B->chunk_start);
     cudaStreamDestroy(B->stream);
     delete B;
     return PS_OK;
@@ -718,6 +724,7 @@ static void fill_kargs(Batch* B, KArgs& a, int n_steps)
     a.hitcnt = B->d_hitcnt; a.cur = B->d_cur; a.pred = B->d_pred; a.S = B->d_S;
     a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.scratch = B->d_scratch; a.lvl = B->d_lvl; a.last = B->d_last;
     a.only_flagged = nullptr;
+    a.world_base = 0;
     a.cand = B->tree_mode ? B->d_cand : nullptr;
     a.cand_off = B->tree_mode ? B->d_cand_off : nullptr;
 }
@@ -725,7 +732,7 @@ static void fill_kargs(Batch* B, KArgs& a, int n_steps)
 static void launch_fused(Batch* B, const KArgs& a, cudaStream_t st)
 {
     const int wpc = 32 / B->threads;  // worlds per one-warp CTA
-    const int grid = (B->n_worlds + wpc - 1) / wpc;
+    const int grid = (a.n_worlds - a.world_base + wpc - 1) / wpc;  // (a.n_worlds is the end of the launched range)
     if (B->minb == 8) {
         if (B->threads == 4) step_kernel<4, 8><<<grid, 32, B->smem, st>>>(a);
         else if (B->threads == 8) step_kernel<8, 8><<<grid, 32, B->smem, st>>>(a);
@@ -940,6 +947,72 @@ int ps_batch_set_state(void* handle, int32_t w0, int32_t w1, const double* pos, 
     CK(cudaMemcpyAsync(dl, ang_mom, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, B->stream));
     pack_dyn_kernel<<<(n + 255) / 256, 256, 0, B->stream>>>(B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn, b0);
     CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(B->stream));
+    return PS_OK;
+}
+
+// marshal -> step -> unmarshal in one call (what Simulator.updateSimulation does around the native step, Simulator.fs:47-62),
+// pipelined over chunks of worlds: chunk k's host->device copy, its step kernel and its device->host copy run on their own
+// stream, so the copies of one chunk hide behind the step of the others (worlds are independent, the step kernel takes a
+// world range).  The batch-wide and SpatialTree paths step the whole batch at once: there the three stages run in sequence.
+int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, const double* vel_in, const double* rot_in,
+                       const double* ang_mom_in, double* pos_out, double* vel_out, double* rot_out, double* ang_mom_out)
+{
+    if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
+    Batch* B = (Batch*)handle;
+    if (n_steps < 0) return fail(PS_ERR_INVALID_ARGUMENT, "n_steps must be >= 0");
+    if (!pos_in || !vel_in || !rot_in || !ang_mom_in || !pos_out || !vel_out || !rot_out || !ang_mom_out)
+        return fail(PS_ERR_INVALID_ARGUMENT, "state array is null");
+    if (B->n_worlds == 0) return PS_OK;
+    int chunks = 8;  // measured, C2 4096 worlds, e2e body-steps/s: 1 chunk 0.875e8, 2 1.00e8, 4 1.04e8, 8 1.08e8
+    if (const char* e = getenv("PS_B200_HOST_CHUNKS")) chunks = std::max(1, std::min(64, atoi(e)));  // tuning knob
+    if (B->wide || B->tree_mode || chunks == 1 || n_steps == 0) {
+        int rc = ps_batch_set_state(handle, 0, B->n_worlds, pos_in, vel_in, rot_in, ang_mom_in);
+        if (!rc) rc = ps_batch_step(handle, n_steps);
+        if (!rc) rc = ps_batch_get_state(handle, 0, B->n_worlds, pos_out, vel_out, rot_out, ang_mom_out);
+        return rc;
+    }
+    CK(cudaSetDevice(B->device));
+    const int wpc = 32 / B->threads;
+    int per = (B->n_worlds + chunks - 1) / chunks;
+    per = (per + wpc - 1) / wpc * wpc;  // chunk borders on CTA borders
+    chunks = (B->n_worlds + per - 1) / per;
+    while ((int)B->chunk_streams.size() < chunks) {
+        cudaStream_t s; cudaEvent_t e;
+        CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        B->chunk_streams.push_back(s); B->chunk_done.push_back(e);
+    }
+    if (!B->chunk_start) CK(cudaEventCreateWithFlags(&B->chunk_start, cudaEventDisableTiming));
+    CK(cudaEventRecord(B->chunk_start, B->stream));  // after whatever the handle's own stream still holds
+    KArgs a{};
+    fill_kargs(B, a, n_steps);
+    for (int k = 0; k < chunks; k++) {
+        const int w0 = k * per, w1 = std::min(B->n_worlds, w0 + per);
+        const int b0 = B->cur.off[w0], n = B->cur.off[w1] - b0;
+        cudaStream_t st = B->chunk_streams[k];
+        CK(cudaStreamWaitEvent(st, B->chunk_start, 0));
+        if (n > 0) {
+            double* sp = B->d_stage + (size_t)b0 * kDynF;
+            double *dp = sp, *dv = sp + 3 * (size_t)n, *dr = sp + 6 * (size_t)n, *dl = sp + 15 * (size_t)n;
+            CK(cudaMemcpyAsync(dp, pos_in + 3 * (size_t)b0, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(dv, vel_in + 3 * (size_t)b0, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(dr, rot_in + 9 * (size_t)b0, 9 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(dl, ang_mom_in + 3 * (size_t)b0, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+            pack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn, b0);
+            KArgs ak = a;
+            ak.world_base = w0; ak.n_worlds = w1;
+            launch_fused(B, ak, st);
+            unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn, b0);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(pos_out + 3 * (size_t)b0, dp, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(vel_out + 3 * (size_t)b0, dv, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(rot_out + 9 * (size_t)b0, dr, 9 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ang_mom_out + 3 * (size_t)b0, dl, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaEventRecord(B->chunk_done[k], st));
+        CK(cudaStreamWaitEvent(B->stream, B->chunk_done[k], 0));
+    }
     CK(cudaStreamSynchronize(B->stream));
     return PS_OK;
 }

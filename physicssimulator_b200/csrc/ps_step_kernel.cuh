@@ -85,6 +85,7 @@ struct KArgs {
     double* pred;         // [total_bodies*18] predicted copies
     double* S;            // [total_bodies*3*kMaxStatics] angular-momentum sums of static-body pairs
     int n_worlds, n_steps;
+    int world_base;           // first world of this launch (n_worlds is the END of the range); a multiple of 32 / T
     StepParams sp;
     int exact_all_pairs;
     int restore_joints;
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
 
     const int tile = threadIdx.x / T;
     const int tid = threadIdx.x % T;
-    const int wraw = blockIdx.x * (32 / T) + tile;
+    const int wraw = a.world_base + blockIdx.x * (32 / T) + tile;  // world_base: a launch over a sub-range of the batch
     const unsigned wflag = (wraw < a.n_worlds && a.only_flagged) ? a.only_flagged[wraw] : 0u;
     const bool live = wraw < a.n_worlds && (!a.only_flagged || wflag != 0u);
     const int w = live ? wraw : 0;
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
     const int N = live ? a.off[w + 1] - off : 0;
     Ctx c;
     c.N = N; c.w = w; c.a = &a; c.bs = &bs;
-    c.scratch = a.scratch + ((size_t)blockIdx.x * 32 + threadIdx.x);
+    c.scratch = a.scratch + ((size_t)(a.world_base / (32 / T) + blockIdx.x) * 32 + threadIdx.x);
     carve(smem_raw + (size_t)tile * smem_bytes(a.max_n), N, c.s);
     Smem& s = c.s;
     {

@@ -100,6 +100,11 @@ class BatchSimulator:
         self.batch.step(n)
 
     # -- read-back --------------------------------------------------------------------------------------
+    def StepHost(self, state: dict, n: int = 1, out: Optional[dict] = None) -> dict:
+        """marshal -> n steps -> unmarshal in one native call (the shape of Simulator.updateSimulation, Simulator.fs:47-62,
+        for a caller that keeps the state in host memory): copies overlap the step, chunk of worlds by chunk of worlds."""
+        return self.batch.step_host(state, n, out)
+
     def State(self, w0: int = 0, w1: Optional[int] = None) -> dict:
         return self.batch.get_state(w0, w1)
 

@@ -278,9 +278,12 @@ def compare(a: Trajectory, b: Trajectory, static_ang_mom: bool = False) -> List[
             ce = all(np.array_equal(p, q) for p, q in zip(fa.candidates, fbb.candidates))
         if fa.contacts is not None and fbb.contacts is not None:
             pe = all(np.array_equal(p["pairs"], q["pairs"]) for p, q in zip(fa.contacts, fbb.contacts))
-            fe = pe and all(np.array_equal(p["first"], q["first"]) and np.array_equal(p["feature"], q["feature"])
-                            for p, q in zip(fa.contacts, fbb.contacts))
-            if fe:
+            counts = pe and all(np.array_equal(p["first"], q["first"]) for p, q in zip(fa.contacts, fbb.contacts))
+            if PRODUCER_REFERENCE_DOTNET in (a.producer, b.producer):
+                fe = None if counts else False  # the reference stores no feature ids: contact counts only
+            else:
+                fe = counts and all(np.array_equal(p["feature"], q["feature"]) for p, q in zip(fa.contacts, fbb.contacts))
+            if counts:
                 cm = 0.0
                 for p, q in zip(fa.contacts, fbb.contacts):
                     for k in ("normal", "position", "penetration"):

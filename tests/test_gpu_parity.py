@@ -9,6 +9,8 @@ import pytest
 from common import (P, scenes, Configuration, StepConfiguration, to_native_config, same_bits, assert_state_bits,
                     assert_contacts_equal, bits)
 
+from physicssimulator_b200.simulator import BatchSimulator
+
 pytestmark = pytest.mark.gpu
 
 STATIC_L_RTOL = 1e-9
@@ -384,3 +386,45 @@ def test_spatial_tree_mode_mutations_and_errors():
     far = protos + [P.createDefaultCube(1.0).With(Position=(100.0, 0.0, 0.0))]
     with pytest.raises(ValueError):
         BatchSimulator([far], cfg, device=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", ["1", "3", "4", "64"])
+def test_step_host_equals_set_step_get(monkeypatch, chunks):
+    """ps_batch_step_host (copies pipelined against the step over chunks of worlds) == the three calls in sequence"""
+    monkeypatch.setenv("PS_B200_HOST_CHUNKS", chunks)
+    worlds = [scenes.c2_spheres64(w)[0] for w in range(37)]  # not a multiple of anything
+    cfg = scenes.c2_spheres64(0)[1]
+    a = BatchSimulator(worlds, cfg, device=0)
+    b = BatchSimulator(worlds, cfg, device=0)
+    try:
+        a.Step(30); b.Step(30)
+        st = a.State()
+        for _ in range(3):
+            a.batch.set_state(st); a.batch.step(2); ref = a.batch.get_state()
+            got = b.StepHost(st, 2)
+            assert_state_bits(ref, got, f"step_host chunks={chunks}")
+            st = {k: v.copy() for k, v in got.items()}
+        sa, sb = a.Stats(), b.Stats()
+        assert sa["pairs_colliding"] == sb["pairs_colliding"] and sa["contacts"] == sb["contacts"] and sa["steps"] == sb["steps"]
+        inplace = {k: v.copy() for k, v in st.items()}
+        b.StepHost(inplace, 1, out=inplace)   # in == out
+        a.batch.set_state(st); a.batch.step(1)
+        assert_state_bits(a.batch.get_state(), inplace, "step_host in place")
+    finally:
+        a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_step_host_on_the_spatial_tree_path_and_errors():
+    protos, cfg = scenes.stack_scene()
+    a = BatchSimulator([protos, protos], cfg, device=0)
+    b = BatchSimulator([protos, protos], cfg, device=0)
+    try:
+        st = a.State()
+        a.batch.set_state(st); a.batch.step(5)
+        assert_state_bits(a.batch.get_state(), b.StepHost(st, 5), "step_host, tree mode")
+        with pytest.raises(ValueError):  # PS_ERR_INVALID_ARGUMENT -> ArgumentException class
+            b.batch.step_host(st, -1)
+    finally:
+        a.close(); b.close()
