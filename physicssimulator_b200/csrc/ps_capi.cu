@@ -69,6 +69,11 @@ struct Batch {
     int* d_off = nullptr;
     WorldStats* d_stats = nullptr;
     unsigned char* d_hitcnt = nullptr;
+    unsigned short* d_cost = nullptr;  // per world: passes of its last step (step kernel)
+    int* d_perm = nullptr;             // slot -> world, sorted by cost inside each segment
+    int seg = 0;                       // worlds per segment (= chunk of ps_batch_step_host); 0: no re-ordering
+    bool cost_valid = false, perm_valid = false;
+    int steps_since_sort = 1 << 20;
     double *d_cur = nullptr, *d_pred = nullptr, *d_S = nullptr;  // per-world scratch of the step kernel
     double* d_cull = nullptr;         // cull spheres, 6 doubles per body
     int* d_row = nullptr;             // near-list row offsets
@@ -251,7 +256,7 @@ void dfree(T*& p)
 }
 void free_device(Batch* B)
 {
-    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_scratch); dfree(B->d_lvl); dfree(B->d_last);
+    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cost); dfree(B->d_perm); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_scratch); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
     dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt);
@@ -399,6 +404,18 @@ int upload(Batch* B, bool with_state)
     }
     CK(cudaMalloc(&B->d_hitcnt, nb));
     CK(cudaMemsetAsync(B->d_hitcnt, 0, nb, B->stream));
+    {   // segments of worlds: the chunks ps_batch_step_host pipelines, and the unit inside which worlds are re-ordered
+        int chunks = 8;  // measured, C2 4096 worlds, e2e body-steps/s: 1 chunk 0.875e8, 2 1.00e8, 4 1.04e8, 8 1.08e8
+        if (const char* e = getenv("PS_B200_HOST_CHUNKS")) chunks = std::max(1, std::min(64, atoi(e)));  // tuning knob
+        const int wpc = 32 / B->threads;
+        int per = (std::max(1, B->n_worlds) + chunks - 1) / chunks;
+        B->seg = (per + wpc - 1) / wpc * wpc;
+        CK(cudaMalloc(&B->d_cost, (size_t)std::max(1, B->n_worlds) * sizeof(unsigned short)));
+        CK(cudaMalloc(&B->d_perm, (size_t)std::max(1, B->n_worlds) * sizeof(int)));
+        CK(cudaMemsetAsync(B->d_cost, 0, (size_t)std::max(1, B->n_worlds) * sizeof(unsigned short), B->stream));
+        B->cost_valid = B->perm_valid = false;
+        B->steps_since_sort = 1 << 20;
+    }
     CK(cudaMemsetAsync(B->d_stats, 0, (size_t)std::max(1, B->n_worlds) * sizeof(WorldStats), B->stream));
     CK(cudaMemcpyAsync(B->d_off, h.off.data(), (size_t)(B->n_worlds + 1) * sizeof(int), cudaMemcpyHostToDevice, B->stream));
 
@@ -725,8 +742,56 @@ static void fill_kargs(Batch* B, KArgs& a, int n_steps)
     a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.scratch = B->d_scratch; a.lvl = B->d_lvl; a.last = B->d_last;
     a.only_flagged = nullptr;
     a.world_base = 0;
+    a.perm = nullptr;
+    a.cost = B->d_cost;
     a.cand = B->tree_mode ? B->d_cand : nullptr;
     a.cand_off = B->tree_mode ? B->d_cand_off : nullptr;
+}
+
+// One block per segment: bitonic sort of (cost << 16 | index in segment) in shared memory -> perm.
+__global__ void perm_sort_kernel(const unsigned short* cost, int* perm, int seg, int n_worlds, int npow2)
+{
+    extern __shared__ unsigned keys[];
+    const int base = blockIdx.x * seg;
+    const int cnt = min(seg, n_worlds - base);
+    for (int k = threadIdx.x; k < npow2; k += blockDim.x) keys[k] = k < cnt ? ((unsigned)cost[base + k] << 16) | (unsigned)k : 0xffffffffu;
+    __syncthreads();
+    for (int size = 2; size <= npow2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int k = threadIdx.x; k < npow2; k += blockDim.x) {
+                const int p = k ^ stride;
+                if (p > k) {
+                    const bool up = (k & size) == 0;
+                    const unsigned x = keys[k], y = keys[p];
+                    if ((x > y) == up) { keys[k] = y; keys[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) perm[base + k] = base + (int)(keys[k] & 0xffffu);
+}
+
+// Re-order the worlds inside their segments by the passes of their last step, every kResortSteps steps.
+// Which warp a world runs in changes nothing about its results.
+static const int* current_perm(Batch* B, int n_steps, cudaStream_t st)
+{
+    const int kResortSteps = 16;
+    const bool kPermDefault = false;  // (flipped to true once measured on the device)
+    const char* pe = getenv("PS_B200_PERM");
+    if (!(pe ? atoi(pe) != 0 : kPermDefault)) return nullptr;
+    if (B->wide || B->tree_mode || B->seg <= 0 || B->seg > 65536) return nullptr;
+    int npow2 = 1;
+    while (npow2 < B->seg) npow2 <<= 1;
+    if ((size_t)npow2 * sizeof(unsigned) > 48 * 1024) return nullptr;
+    if (B->cost_valid && B->steps_since_sort >= kResortSteps) {
+        const int nseg = (B->n_worlds + B->seg - 1) / B->seg;
+        perm_sort_kernel<<<nseg, 256, (size_t)npow2 * sizeof(unsigned), st>>>(B->d_cost, B->d_perm, B->seg, B->n_worlds, npow2);
+        B->perm_valid = true;
+        B->steps_since_sort = 0;
+    }
+    B->steps_since_sort += n_steps;
+    B->cost_valid = true;  // (after the launch this call is about to make)
+    return B->perm_valid ? B->d_perm : nullptr;
 }
 
 static void launch_fused(Batch* B, const KArgs& a, cudaStream_t st)
@@ -853,6 +918,7 @@ static int launch_step(Batch* B, int n_steps, cudaStream_t st)
         }
         return PS_OK;
     }
+    a.perm = current_perm(B, n_steps, st);
     launch_fused(B, a, st);
     CK(cudaGetLastError());
     return PS_OK;
@@ -964,19 +1030,15 @@ int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, cons
     if (!pos_in || !vel_in || !rot_in || !ang_mom_in || !pos_out || !vel_out || !rot_out || !ang_mom_out)
         return fail(PS_ERR_INVALID_ARGUMENT, "state array is null");
     if (B->n_worlds == 0) return PS_OK;
-    int chunks = 8;  // measured, C2 4096 worlds, e2e body-steps/s: 1 chunk 0.875e8, 2 1.00e8, 4 1.04e8, 8 1.08e8
-    if (const char* e = getenv("PS_B200_HOST_CHUNKS")) chunks = std::max(1, std::min(64, atoi(e)));  // tuning knob
-    if (B->wide || B->tree_mode || chunks == 1 || n_steps == 0) {
+    const int per = B->seg;  // chunk = segment (upload(): PS_B200_HOST_CHUNKS, default 8, borders on CTA borders)
+    int chunks = per > 0 ? (B->n_worlds + per - 1) / per : 1;
+    if (B->wide || B->tree_mode || chunks <= 1 || n_steps == 0) {
         int rc = ps_batch_set_state(handle, 0, B->n_worlds, pos_in, vel_in, rot_in, ang_mom_in);
         if (!rc) rc = ps_batch_step(handle, n_steps);
         if (!rc) rc = ps_batch_get_state(handle, 0, B->n_worlds, pos_out, vel_out, rot_out, ang_mom_out);
         return rc;
     }
     CK(cudaSetDevice(B->device));
-    const int wpc = 32 / B->threads;
-    int per = (B->n_worlds + chunks - 1) / chunks;
-    per = (per + wpc - 1) / wpc * wpc;  // chunk borders on CTA borders
-    chunks = (B->n_worlds + per - 1) / per;
     while ((int)B->chunk_streams.size() < chunks) {
         cudaStream_t s; cudaEvent_t e;
         CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -984,9 +1046,10 @@ int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, cons
         B->chunk_streams.push_back(s); B->chunk_done.push_back(e);
     }
     if (!B->chunk_start) CK(cudaEventCreateWithFlags(&B->chunk_start, cudaEventDisableTiming));
-    CK(cudaEventRecord(B->chunk_start, B->stream));  // after whatever the handle's own stream still holds
     KArgs a{};
     fill_kargs(B, a, n_steps);
+    a.perm = current_perm(B, n_steps, B->stream);    // (a re-sort runs on the handle's stream, before the chunks start)
+    CK(cudaEventRecord(B->chunk_start, B->stream));  // after whatever the handle's own stream still holds
     for (int k = 0; k < chunks; k++) {
         const int w0 = k * per, w1 = std::min(B->n_worlds, w0 + per);
         const int b0 = B->cur.off[w0], n = B->cur.off[w1] - b0;

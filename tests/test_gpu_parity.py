@@ -253,8 +253,10 @@ def test_tile_widths_and_multi_step_launches_agree(monkeypatch):
     from physicssimulator_b200.simulator import BatchSimulator
     worlds = [scenes.c3_mixed128(w, n_boxes=20, n_spheres=20)[0] for w in range(9)]  # 9: a partly filled last warp
     ref = None
-    for tile in ("4", "8", "16", "32"):
+    # both register builds of the step kernel (small batches default to the 255-register one)
+    for tile, minb in (("4", "8"), ("8", "8"), ("16", "8"), ("32", "8"), ("4", "16"), ("8", "16"), ("16", "16"), ("32", "16")):
         monkeypatch.setenv("PS_B200_TILE", tile)
+        monkeypatch.setenv("PS_B200_MINB", minb)
         sim = BatchSimulator(worlds, Configuration(), device=0)
         if tile == "8":
             for _ in range(60):
@@ -267,7 +269,7 @@ def test_tile_widths_and_multi_step_launches_agree(monkeypatch):
             ref = st
         else:
             for k in ("pos", "vel", "rot"):
-                assert same_bits(st[k], ref[k]), f"tile {tile}: {k}"
+                assert same_bits(st[k], ref[k]), f"tile {tile}, {minb} CTAs per SM: {k}"
 
 
 @pytest.mark.parametrize("path", ["wide", "fused"])
@@ -428,3 +430,31 @@ def test_step_host_on_the_spatial_tree_path_and_errors():
             b.batch.step_host(st, -1)
     finally:
         a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_world_reordering_changes_nothing(monkeypatch):
+    """worlds are re-ordered inside their segments by the passes of their last step (every 16 steps): which warp a
+    world runs in must not show in any bit — single-step calls, multi-step launches and ps_batch_step_host"""
+    worlds = [scenes.c2_spheres64(w)[0] for w in range(70)] + [scenes.c3_mixed128(w, n_boxes=6, n_spheres=6)[0] for w in range(9)]
+    cfg = Configuration()
+    ref = BatchSimulator(worlds, cfg, device=0)
+    a = BatchSimulator(worlds, cfg, device=0)
+    b = BatchSimulator(worlds, cfg, device=0)
+    try:
+        monkeypatch.setenv("PS_B200_PERM", "0")
+        ref.Step(75)
+        monkeypatch.setenv("PS_B200_PERM", "1")
+        for _ in range(40):
+            a.Step(1)
+        a.Step(35)
+        assert_state_bits(ref.State(), a.State(), "re-ordered worlds, step")
+        st = b.State()
+        for n in (1, 20, 17, 37):
+            st = b.StepHost(st, n)
+        assert_state_bits(ref.State(), st, "re-ordered worlds, step_host")
+        ra, rb_, rr = a.Stats(), b.Stats(), ref.Stats()
+        for k in ("pairs_colliding", "contacts", "steps", "body_steps"):
+            assert ra[k] == rr[k] == rb_[k], k
+    finally:
+        ref.close(); a.close(); b.close()
