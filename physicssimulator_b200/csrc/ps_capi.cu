@@ -776,7 +776,7 @@ __global__ void perm_sort_kernel(const unsigned short* cost, int* perm, int seg,
 static const int* current_perm(Batch* B, int n_steps, cudaStream_t st)
 {
     const int kResortSteps = 16;
-    const bool kPermDefault = false;  // (flipped to true once measured on the device)
+    const bool kPermDefault = false;  // measured: C2 1.636 ms re-ordered vs 1.595 ms in creation order -> off
     const char* pe = getenv("PS_B200_PERM");
     if (!(pe ? atoi(pe) != 0 : kPermDefault)) return nullptr;
     if (B->wide || B->tree_mode || B->seg <= 0 || B->seg > 65536) return nullptr;
