@@ -137,3 +137,27 @@ def test_cuda_path_replays_golden_snapshot(name):
         batch.close()
     for d in snapshot.compare(gold, got):  # dynamic bodies; a static body's L is quirk Q2
         assert d.bit_exact and d.candidates_equal and d.pairs_equal and d.features_equal and d.contact_max_abs == 0.0, f"{name}: {d}"
+
+
+def test_compare_tool_verdicts(tmp_path):
+    """tools/compare_snapshots.py: identical files pass; a file written by the (.NET) reference carries no feature ids
+    and is compared on pair sets and contact counts; a perturbation above the tolerance fails the run"""
+    import sys
+    name = sorted(CASES)[-1]
+    src = os.path.join(GOLD, name + ".pstj")
+    tool = os.path.join(ROOT, "tools", "compare_snapshots.py")
+    out = subprocess.run([sys.executable, tool, src, src], capture_output=True, text=True)
+    assert out.returncode == 0 and "discrete decisions identical in every frame" in out.stdout
+    t = snapshot.load(src)
+    t.producer = snapshot.PRODUCER_REFERENCE_DOTNET
+    for f in t.frames:
+        for c in f.contacts:
+            c["feature"][:] = 0
+    dyn = np.flatnonzero(~np.isinf(t.constants["mass"]))
+    t.frames[-1].state["vel"][dyn[0], 2] += 1e-11
+    ref = str(tmp_path / "ref.pstj")
+    snapshot.save(ref, t)
+    out = subprocess.run([sys.executable, tool, ref, src, "--rtol", "1e-9"], capture_output=True, text=True)
+    assert out.returncode == 0 and "reference (.NET)" in out.stdout and "within rtol" in out.stdout
+    out = subprocess.run([sys.executable, tool, ref, src, "--rtol", "1e-13"], capture_output=True, text=True)
+    assert out.returncode == 1 and "ABOVE rtol" in out.stdout
