@@ -289,7 +289,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "psk::step_kernel" if sched["path"] == "fused" else "psw::wide_* stages + psk::step_kernel (one step)", "algorithmic_bytes_per_body_step": B_ALG, "kernel_ms": kernel_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "traffic_note": "ncu dram bytes per launch of this workload (profiles/traffic.json); far above the algorithmic bytes: the per-pair routines spill their working arrays to the local-memory stack",
+                         "traffic_note": "ncu dram bytes per launch of this workload (profiles/traffic.json), cold-cache replay; above the algorithmic bytes: besides the published state the step streams its working and predicted copies, the per-step pair lists and the local-memory stack of the per-pair routines",
                          "note": "the per-world ordered contact solve is a dependent FP64 chain: the HBM roofline is the metric's denominator, not the kernel's limiter"},
             "multi_step_call": {"steps": args.steps, "ms_per_step": multi_ms / args.steps, "value_this_rank": n_dyn * per_gpu * args.steps / (multi_ms * 1e-3),
                                 "what": "ps_batch_step(K) in one call, no L2 flush between steps; informational, not the headline"},
