@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (default: the config's)")
     ap.add_argument("--settle", type=int, default=200, help="untimed setup steps so that bodies are in contact")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="bracket ONE extra step after the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -214,6 +216,13 @@ def main():
     total_body_steps = n_dyn * per_gpu * world * args.steps
     value = total_body_steps / (dev_ms_max * 1e-3)
     kernel_ms = dev_ms / args.steps  # this rank's average launch duration
+
+    if args.profile_step:  # one settled step for `ncu --profile-from-start off`; outside every timed region
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        sim.batch.step_async(1, stream)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
     # informational: the same K steps in ONE call (fused path: one launch, worlds do not wait for each other between steps)
     ms0, ms1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
