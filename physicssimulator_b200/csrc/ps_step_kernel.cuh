@@ -222,7 +222,6 @@ struct BlockShared {
     int redo;         // ... and one of them can no longer be ruled out -> restart with a wider margin
     int need_serial;  // a static pose moves / list full / too many levels -> exact serial walk
     int K, maxl, nstat;
-    unsigned short pick[32];  // ready-list scheduling: the pairs this pass hands to the tile's lanes
     unsigned tested, hits, contacts, overflow, ref_exc;
     unsigned long long max_pen_bits;
 };
@@ -418,9 +417,6 @@ PSD bool near_test_grown(const Smem& s, int N, int i, int j, double gi, double g
 
 #ifndef PS_SCRATCH_GLOBAL
 #define PS_SCRATCH_GLOBAL 0  // 1: per-pair working arrays in a per-thread global record instead of the local stack
-#endif
-#ifndef PS_READY_LIST
-#define PS_READY_LIST 0  // 1: wavefronts by ready list (a pair runs as soon as its predecessors are done); 0: by level
 #endif
 #ifndef PS_MINB32
 #define PS_MINB32 16  // resident one-warp CTAs per SM the register allocation must allow (65536 / (32 * regs))
@@ -648,85 +644,6 @@ __global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
             }
             __syncwarp();
             if (tid == 0 && live) { long long t = clock64(); cyc[1] += t - tk; tk = t; }
-#if PS_READY_LIST
-            // ---- C: predecessors.  A near pair waits for the previous near pair of each of its DYNAMIC bodies (a static
-            // body's pose is fixed, its pairs do not order each other): one lane per world walks the ordered list and
-            // leaves the two predecessor indices of every pair (kNoPred: none) where the level tables used to be.
-            constexpr unsigned kNoPred = 0xffffu;
-            if (fast && tid == 0) {
-                if (K >= (int)kNoPred) bs.need_serial = 1;  // (indices are 16 bit)
-                else
-                    for (int k = 0; k < K; k++) {
-                        unsigned ij = s.near[k];
-                        int i = ij & 0xffff, j = ij >> 16;
-                        unsigned p0 = kNoPred, p1 = kNoPred;
-                        if (!s.isstat[i]) { unsigned l = s.last[i]; if (l) p0 = l - 1u; s.last[i] = (unsigned short)(k + 1); }
-                        if (!s.isstat[j]) { unsigned l = s.last[j]; if (l) p1 = l - 1u; s.last[j] = (unsigned short)(k + 1); }
-                        s.level[k] = (unsigned short)p0;
-                        s.order[k] = (unsigned short)p1;
-                    }
-            }
-            __syncwarp();
-            if (fast && bs.need_serial) {  // list longer than the index type: exact serial walk next pass
-                fast = false;
-                attempt = 2; fb_reason = 2;
-            }
-            if (tid == 0 && live) { long long t = clock64(); cyc[2] += t - tk; tk = t; if (fast) sumK += K; }
-
-            // ---- D: wavefronts by ready list.  Every pass a tile hands its T lanes the first T pairs, in list order,
-            // that are not done and whose predecessors are (hit[k] bit 1 = done); it looks kWin entries ahead of the
-            // first pair that is not done.  Two pairs without a common dynamic body commute and a pair that misses
-            // changes nothing, so any order that respects the predecessors gives the bits of the serial fold.  (By
-            // level a tile took sum over levels of ceil(pairs / T) passes; a level of 9-16 pairs cost two.)
-            {
-                constexpr int kWin = 4;  // chunks of T entries scanned per pass
-                const unsigned tmask_ = (T == 32) ? FULL : (((1u << T) - 1u) << (tile * T));
-                const unsigned below = (1u << tid) - 1u;
-                int head = 0;
-                bool dact = fast && K > 0;
-                for (;;) {
-                    if (!__any_sync(FULL, dact)) break;
-                    if (dact) npass++;
-                    int found = 0;
-#pragma unroll 1
-                    for (int wi = 0; wi < kWin; wi++) {
-                        const int k = head + wi * T + tid;
-                        bool ready = false;
-                        if (dact && found < T && k < K && !(s.hit[k] & 2)) {
-                            const unsigned p0 = s.level[k], p1 = s.order[k];
-                            ready = (p0 == kNoPred || (s.hit[p0] & 2)) && (p1 == kNoPred || (s.hit[p1] & 2));
-                        }
-                        const unsigned mine = (__ballot_sync(FULL, ready) & tmask_) >> (tile * T);
-                        const int rank = found + __popc(mine & below);
-                        if (ready && rank < T) bs.pick[rank] = (unsigned short)k;
-                        found += __popc(mine);
-                    }
-                    if (found > T) found = T;
-                    __syncwarp();
-                    int pi_ = 0, pj_ = 0, pk_ = 0;
-                    const bool valid = dact && tid < found;
-                    if (valid) {
-                        pk_ = bs.pick[tid];
-                        unsigned ij = s.near[pk_];
-                        pi_ = ij & 0xffff; pj_ = ij >> 16;
-                    }
-                    if (valid) process_pair(c, pi_, pj_, pk_, true);
-                    if (valid) s.hit[pk_] |= 2;
-                    __syncwarp();
-                    // first pair that is not done (two chunks per pass are enough to keep up with T picks)
-#pragma unroll 1
-                    for (int r = 0; r < 2; r++) {
-                        const int k = head + tid;
-                        const bool dn = dact && (k >= K || (s.hit[k] & 2));
-                        const unsigned mine = (__ballot_sync(FULL, dn) & tmask_) >> (tile * T);
-                        const unsigned full = (T == 32) ? FULL : ((1u << T) - 1u);
-                        const int lead = (mine == full) ? T : (__ffs(~mine) - 1);  // leading done entries
-                        if (dact) head += lead;
-                    }
-                    if (dact && head >= K) dact = false;
-                }
-            }
-#else
             // ---- C: wavefront levels (serial scan of the ordered list by one lane per world) ------------------
             if (fast && tid == 0) {
                 int maxl = 0;
@@ -802,7 +719,6 @@ __global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
                     }
                 }
             }
-#endif
             // ---- exact serial walk over ALL candidates in order, one lane per world: Dummy order (BroadPhase.fs:33-39)
             // or the SpatialTree list ---------------------------------------------------------------------------------
             {
@@ -889,7 +805,7 @@ __global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
                     const int k = base + tid;
                     bool pred = false;
                     unsigned short ent = 0;
-                    if (k < Kf && (s.hit[k] & 1)) {
+                    if (k < Kf && s.hit[k]) {
                         const unsigned ij = s.near[k];
                         const int i = ij & 0xffff, j = ij >> 16;
                         // at most one body of a near pair is static (canIntersect); entry = partner | ordinal << 12
