@@ -1,5 +1,8 @@
 #!/bin/bash
-# Times builds of the CUDA library that differ in compile-time knobs (tools/variants/libps_<X>.so) on the same settled state.
+# Times builds of the CUDA library that differ in compile-time knobs on the same settled state.
+# Build them first, in-tree so that they travel to the GPU box (tools/variants/ is git-ignored through *.so):
+#   nvcc <flags of __graft_entry__.NVCC_FLAGS> -D<KNOB>=<value> -o tools/variants/libps_<X>.so physicssimulator_b200/csrc/ps_capi.cu physicssimulator_b200/csrc/ps_broadphase.cu
+# then: gpurun -- 'VARIANTS="X Y" bash tools/gpu_variants.sh'   (the Python binding loads $PS_B200_LIB instead of the product library)
 set -u
 mkdir -p gpurun_out
 run() { timeout 200 python tools/sweep.py --workload $1 --worlds $2 --steps $3 --settle $4 --variants "fused:1:16" 2>&1 | cut -c1-60; }
