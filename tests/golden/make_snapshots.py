@@ -21,6 +21,8 @@ from physicssimulator_b200 import snapshot  # noqa: E402
 # name -> (list of worlds (prototype lists), Configuration, marks)
 CASES = {
     "snap_c2_two_worlds": (lambda: [scenes.c2_spheres64(0)[0], scenes.c2_spheres64(1)[0]], scenes.c2_spheres64(0)[1], [1, 2, 20, 60]),
+    # the Gui's Stack scene in its OWN configuration (SpatialTree broad phase: candidate order of the persistent 2^3-tree)
+    "snap_stack_scene_tree": (lambda: [scenes.stack_scene()[0], scenes.stack_scene()[0]], scenes.stack_scene()[1], [1, 2, 25, 80]),
     "snap_c3_small_two_worlds": (lambda: [scenes.c3_mixed128(0, n_boxes=10, n_spheres=8)[0], scenes.c3_mixed128(3, n_boxes=12, n_spheres=6)[0]],
                                  Configuration(), [1, 2, 15, 40]),
 }
@@ -33,6 +35,10 @@ def oracle_steppers(worlds, cfg):
     bodies, off = P.concat_worlds(built)
     ncfg = to_native_config(cfg, record_contacts=True)
     ws = [OracleWorld(b, ncfg) for b in built]
+    tc = cfg.BroadPhaseCollisionDetectionKind.SpatialTree
+    if tc is not None:  # the oracle's persistent tree (pinned by the reference's known-answer facts)
+        for w in ws:
+            assert w.use_spatial_tree(tc.LeafCapacity, tc.MaxDepth, tc.SpaceBoundariesMin, tc.SpaceBoundariesMax) == 0
 
     def step(n):
         for w in ws:
