@@ -104,6 +104,69 @@ PSI void integrate(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o)
     o.R = orthonormalize(mulMM(rot, b.R));
 }
 
+// The literal form as a real function: the fallback of integrate_f, entered when a lane's operands leave the range
+// the straight-line arithmetic covers (a zero vector to normalise, a denormal quotient, an angle beyond pi/4, NaN).
+PSN void integrate_slow(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o) { integrate(b, p, sp, o); }
+// Straight-line integrate (ps_math.cuh, "_f" forms): identical results wherever ok stays true.  Two halves, so that a
+// caller with two bodies can put the two rotation halves — all the divisions and square roots — side by side in one
+// basic block (the integrator switch of the first half is a branch, uniform but a block boundary all the same).
+PSD d3 integrate_lin(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o)  // x, v, L; returns the rotation vector
+{
+    const double dt = sp.dt;
+    d3 acc = scale(p.inv_mass, p.F);
+    d3 nv = b.v + scale(dt, acc);
+    o.x = b.x + scale(dt, nv);
+    o.v = nv;
+    m33 Iw = inertia_inv_world(b.R, p.iinv);
+    d3 dL = scale(dt, p.T);
+    d3 axis;
+    if (sp.integrator == 0) {
+        d3 nL = b.L + dL;
+        axis = scale(dt, mulMV(Iw, nL));
+        o.L = nL;
+    } else {
+        d3 w = mulMV(Iw, b.L);
+        d3 vv = cross(w, b.L);
+        d3 deriv = mulMV(Iw, p.T - vv);
+        d3 comp1 = cross(deriv, w);
+        d3 avg = (w + scale(dt * 0.5, deriv)) + scale(dt * dt / 12.0, comp1);
+        axis = scale(dt, avg);
+        o.L = b.L + dL;
+    }
+    return axis;
+}
+// one body: straight-line first, literal on the rare miss
+PSD void integrate_a(const Dyn& b, const Par& p, const StepParams& sp, Dyn& o)
+{
+    bool ok = true;
+    const d3 axis = integrate_lin(b, p, sp, o);
+    m3<double> R;
+#pragma unroll
+    for (int k = 0; k < 9; k++) R.a[k] = b.R.a[k];
+    const m3<double> Rn = rotate_f(R, mkv<double>(axis.x, axis.y, axis.z), ok);
+#pragma unroll
+    for (int k = 0; k < 9; k++) o.R.a[k] = Rn.a[k];
+    if (!ok) integrate_slow(b, p, sp, o);
+}
+// the two bodies of a pair: the rotation halves run as ONE two-lane computation (ps_math.cuh, T = dd)
+PSD void integrate_2(const Dyn& b1, const Par& p1, Dyn& o1, const Dyn& b2, const Par& p2, Dyn& o2, const StepParams& sp)
+{
+    const d3 axis1 = integrate_lin(b1, p1, sp, o1);
+    const d3 axis2 = integrate_lin(b2, p2, sp, o2);
+    m3<dd> R;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { R.a[k].a = b1.R.a[k]; R.a[k].b = b2.R.a[k]; }
+    v3<dd> ax;
+    ax.x.a = axis1.x; ax.y.a = axis1.y; ax.z.a = axis1.z;
+    ax.x.b = axis2.x; ax.y.b = axis2.y; ax.z.b = axis2.z;
+    bb ok; ok.a = true; ok.b = true;
+    const m3<dd> Rn = rotate_f(R, ax, ok);
+#pragma unroll
+    for (int k = 0; k < 9; k++) { o1.R.a[k] = Rn.a[k].a; o2.R.a[k] = Rn.a[k].b; }
+    if (!ok.a) integrate_slow(b1, p1, sp, o1);
+    if (!ok.b) integrate_slow(b2, p2, sp, o2);
+}
+
 // ----------------------------------------------------------------------------------------
 // Oriented box in world space (OrientedBox.fs:10-27 over Box.fs:100-111)
 // ----------------------------------------------------------------------------------------
@@ -386,6 +449,72 @@ PSN bool bb_quick_separated(const Dyn& b1, const Dyn& b2, const OBox& o1, const 
     return bb_quick_separated_t<false>(b1, b2, o1, o2);
 }
 
+// generateEdgeContactPoints (CollisionDetection.fs:75-132): the supporting edge of each box along the SAT edge axis
+// (sel1 / sel2 = RigidBody.Axes entries of the winning pair of edges), the midpoint of their closest points.
+// returns 1 (one contact) or 0 with err set (List.maxBy on an empty list)
+template <bool F>
+PSD int bb_edge_contact(const OBox& o1, const OBox& o2, d3 sel1, d3 sel2, d3 normal, double best_pen, int best_i, int best_j,
+                        double eps, Contact* out, int& err)
+{
+    d3 ea[2], eb[2];
+    int eidx[2];
+#pragma unroll (F ? 2 : 1)
+    for (int side = 0; side < 2; side++) {
+        const OBox& ob = side == 0 ? o1 : o2;
+        d3 axis = side == 0 ? sel1 : sel2;
+        d3 nrm = side == 0 ? normal : -normal;
+        bool have = false;
+        double bestv = 0.0;
+        int idx = 0;
+        d3 bea = mk(0.0, 0.0, 0.0), beb = mk(0.0, 0.0, 0.0);
+        // OrientedBox.getEdges: faces 0..5, per face (v3,v0),(v0,v1),(v1,v2),(v2,v3); List.distinct on
+        // ordered pairs — every directed edge of a non-degenerate box appears once, so index = 4*f+k.
+#pragma unroll 1
+        for (int f = 0; f < 6; f++)
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                d3 a = face_vertex(ob, f, (k + 3) & 3), b = face_vertex(ob, f, k);
+                d3 dd = b - a;
+                d3 cr = cross(dd, axis);  // areParallel: axis |> crossProduct d = d x axis, isZero eps of its norm
+                // Exact shortcut: Hypotenuse never returns less than its larger argument (|x| * sqrt(1 + r*r) >= |x|), so
+                // the norm is >= every |component|; one component above eps decides "not parallel" without the two
+                // divisions and square roots (20 of the 24 edges end here; a NaN norm compares false either way).
+                if (fabs(cr.x) > eps || fabs(cr.y) > eps || fabs(cr.z) > eps) continue;
+                if (!near_eq(eps, 0.0, norm_t<F>(cr))) continue;
+                double pa = dot(nrm, a), pb = dot(nrm, b);
+                double key = (pb > pa) ? pb : pa;
+                if (!have || key > bestv) {
+                    have = true;
+                    bestv = key;
+                    idx = 4 * f + k;
+                    bea = a;
+                    beb = b;
+                }
+            }
+        if (!have) {
+            err = 1;  // List.maxBy on an empty list
+            return 0;
+        }
+        eidx[side] = idx;
+        ea[side] = bea;
+        eb[side] = beb;
+    }
+    d3 DA = eb[0] - ea[0], DB = eb[1] - ea[1];
+    d3 r = ea[0] - ea[1];
+    double a = dot(DA, DA), e = dot(DB, DB), f = dot(DB, r), c = dot(DA, r), b = dot(DA, DB);
+    double denom = a * e - b * b;
+    double TA = (b * f - c * e) / denom;
+    double TB = (b * TA + f) / e;
+    d3 CA = ea[0] + scale(TA, DA);
+    d3 CB = ea[1] + scale(TB, DB);
+    out[0].n = normal;
+    out[0].p = scale(0.5, CA) + scale(0.5, CB);
+    out[0].pen = -best_pen;
+    out[0].feat = 3u | (2u << 2) | ((unsigned)best_i << 4) | ((unsigned)best_j << 7) | ((unsigned)eidx[0] << 10) |
+                  ((unsigned)eidx[1] << 15);
+    return 1;
+}
+
 // detectBoxBoxCollision (CollisionDetection.fs:29-164) over SAT.tryFindSeparatingAxis (SAT.fs:206-240)
 // returns #contacts (0 = none); overflow set when the manifold would exceed PS_MAX_CONTACTS
 // boxes_ready: sc.o1/sc.o2 are already built and the quick test has already failed to separate them
@@ -587,67 +716,11 @@ PSD int detect_bb_t(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, 
     }
 
     // generateEdgeContactPoints (CollisionDetection.fs:75-132)
-    d3 normal = best_n;
-    d3 ea[2], eb[2];
-    int eidx[2];
     const d3 sel1 = best_i == 0 ? ax1[0] : (best_i == 1 ? ax1[1] : ax1[2]);
     const d3 sel2 = best_j == 0 ? ax2[0] : (best_j == 1 ? ax2[1] : ax2[2]);
-#pragma unroll (F ? 2 : 1)
-    for (int side = 0; side < 2; side++) {
-        const OBox& ob = side == 0 ? o1 : o2;
-        d3 axis = side == 0 ? sel1 : sel2;
-        d3 nrm = side == 0 ? normal : -normal;
-        bool have = false;
-        double bestv = 0.0;
-        int idx = 0;
-        d3 bea = mk(0.0, 0.0, 0.0), beb = mk(0.0, 0.0, 0.0);
-        // OrientedBox.getEdges: faces 0..5, per face (v3,v0),(v0,v1),(v1,v2),(v2,v3); List.distinct on
-        // ordered pairs — every directed edge of a non-degenerate box appears once, so index = 4*f+k.
-#pragma unroll 1
-        for (int f = 0; f < 6; f++)
-#pragma unroll 1
-            for (int k = 0; k < 4; k++) {
-                d3 a = face_vertex(ob, f, (k + 3) & 3), b = face_vertex(ob, f, k);
-                d3 dd = b - a;
-                d3 cr = cross(dd, axis);  // areParallel: axis |> crossProduct d = d x axis, isZero eps of its norm
-                // Exact shortcut: Hypotenuse never returns less than its larger argument (|x| * sqrt(1 + r*r) >= |x|), so
-                // the norm is >= every |component|; one component above eps decides "not parallel" without the two
-                // divisions and square roots (20 of the 24 edges end here; a NaN norm compares false either way).
-                if (fabs(cr.x) > eps || fabs(cr.y) > eps || fabs(cr.z) > eps) continue;
-                if (!near_eq(eps, 0.0, norm_t<F>(cr))) continue;
-                double pa = dot(nrm, a), pb = dot(nrm, b);
-                double key = (pb > pa) ? pb : pa;
-                if (!have || key > bestv) {
-                    have = true;
-                    bestv = key;
-                    idx = 4 * f + k;
-                    bea = a;
-                    beb = b;
-                }
-            }
-        if (!have) {
-            err = 1;  // List.maxBy on an empty list
-            return 0;
-        }
-        eidx[side] = idx;
-        ea[side] = bea;
-        eb[side] = beb;
-    }
-    d3 DA = eb[0] - ea[0], DB = eb[1] - ea[1];
-    d3 r = ea[0] - ea[1];
-    double a = dot(DA, DA), e = dot(DB, DB), f = dot(DB, r), c = dot(DA, r), b = dot(DA, DB);
-    double denom = a * e - b * b;
-    double TA = (b * f - c * e) / denom;
-    double TB = (b * TA + f) / e;
-    d3 CA = ea[0] + scale(TA, DA);
-    d3 CB = ea[1] + scale(TB, DB);
-    out[0].n = normal;
-    out[0].p = scale(0.5, CA) + scale(0.5, CB);
-    out[0].pen = -best_pen;
-    out[0].feat = 3u | (2u << 2) | ((unsigned)best_i << 4) | ((unsigned)best_j << 7) | ((unsigned)eidx[0] << 10) |
-                  ((unsigned)eidx[1] << 15);
+    const int ne = bb_edge_contact<F>(o1, o2, sel1, sel2, best_n, best_pen, best_i, best_j, eps, out, err);
     PS_CLK(5)
-    return 1;
+    return ne;
 }
 PSN int detect_bb(const Dyn& b1, const Par& p1, const Dyn& b2, const Par& p2, double eps, Contact* out, int& err,
                   int& overflow, PairScratch& sc, bool boxes_ready = false)
@@ -742,6 +815,74 @@ PSD void apply_impulse(Dyn& b, const Par& p, d3 off, d3 P)
 }
 PSD d3 velocity_at(const Dyn& b, const m33& Iw, d3 off) { return b.v + cross(mulMV(Iw, b.L), off); }
 
+// ContactPointImpulseData.init (ContactPointImpulseData.fs:23-52) + calculateBaumgarteBias (CollisionResponse.fs:35-41)
+// for ONE contact of a manifold; t0/t1 are the tangents of the manifold's FIRST contact (CollisionResponse.fs:80-81)
+PSD void contact_setup(const Dyn& b1, const Par& p1, const m33& Iw1, const Dyn& b2, const Par& p2, const m33& Iw2,
+                       const Contact& c, d3 t0, d3 t1, const StepParams& sp, CPData& d)
+{
+    d.bias = fmin_net(sp.max_corr, -sp.baumgarte / sp.dt * fmin_net(0.0, c.pen + sp.slop));  // :35-41
+    d.r1 = c.p - b1.x;
+    d.r2 = c.p - b2.x;
+    m33 K;
+#pragma unroll
+    for (int q = 0; q < 9; q++) K.a[q] = 0.0;
+    add_K(K, p1, Iw1, d.r1);
+    add_K(K, p2, Iw2, d.r2);
+    d.mN = dot(c.n, mulMV(K, c.n));
+    d.mT0 = dot(t0, mulMV(K, t0));
+    d.mT1 = dot(t1, mulMV(K, t1));
+    d.accN = 0.0;
+    d.accT0 = 0.0;
+    d.accT1 = 0.0;
+}
+// one contact of one solver iteration (CollisionResponse.fs:91-131: normal impulse, then friction, Friction.fs:39-68);
+// the velocity state of the two bodies (v, L) and the contact's accumulators are updated in place
+struct SolveConst {
+    double e, mu, inf;
+    int friction;
+};
+PSD void solve_contact(Dyn& b1, const Par& p1, const m33& Iw1, Dyn& b2, const Par& p2, const m33& Iw2, d3 n, d3 t0, d3 t1,
+                       CPData& d, const SolveConst& sc)
+{
+    d3 P;
+    if (d.mN == 0.0) {
+        P = mk(0.0, 0.0, 0.0);
+    } else {
+        d3 vrel = velocity_at(b2, Iw2, d.r2) - velocity_at(b1, Iw1, d.r1);
+        double vn = dot(vrel, n);
+        double j = (-(sc.e + 1.0) * vn + d.bias) / d.mN;
+        double old = d.accN;
+        d.accN = clamp_net(0.0, sc.inf, old + j);
+        P = scale(-(d.accN - old), n);
+    }
+    apply_impulse(b1, p1, d.r1, P);
+    apply_impulse(b2, p2, d.r2, -P);
+    if (sc.friction) {
+        d3 vrel = velocity_at(b2, Iw2, d.r2) - velocity_at(b1, Iw1, d.r1);
+        double maxF = sc.mu * d.accN;
+        double j0 = dot(t0, vrel) / d.mT0;
+        double j1 = dot(t1, vrel) / d.mT1;
+        double o0 = d.accT0, o1 = d.accT1;
+        d.accT0 = clamp_net(-maxF, maxF, o0 + j0);
+        d.accT1 = clamp_net(-maxF, maxF, o1 + j1);
+        d3 P0 = scale(d.accT0 - o0, t0);
+        d3 P1 = scale(d.accT1 - o1, t1);
+        apply_impulse(b1, p1, d.r1, P0);
+        apply_impulse(b1, p1, d.r1, P1);
+        apply_impulse(b2, p2, d.r2, -P0);
+        apply_impulse(b2, p2, d.r2, -P1);
+    }
+}
+PSD SolveConst solve_const(const Par& p1, const Par& p2, const StepParams& sp)
+{
+    SolveConst sc;
+    sc.e = fmin_net(p1.e, p2.e);
+    sc.mu = fmax_net(p2.mu, p1.mu);
+    sc.inf = from_bits(0x7ff0000000000000LL);
+    sc.friction = sp.friction;
+    return sc;
+}
+
 // resolves one pair in place; b1/b2 are the predicted bodies
 // FIX = 0: nc contacts at run time; FIX = 1: exactly one contact (every sphere pair), arrays collapse to registers
 template <int FIX>
@@ -757,59 +898,16 @@ PSD void resolve_t(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact
 #pragma unroll 1
     for (int k = 0; k < nc; k++) {
         CPData d;
-        d.bias = fmin_net(sp.max_corr, -sp.baumgarte / sp.dt * fmin_net(0.0, cs[k].pen + sp.slop));  // :35-41
-        d.r1 = cs[k].p - b1.x;
-        d.r2 = cs[k].p - b2.x;
-        m33 K;
-#pragma unroll
-        for (int q = 0; q < 9; q++) K.a[q] = 0.0;
-        add_K(K, p1, Iw1, d.r1);
-        add_K(K, p2, Iw2, d.r2);
-        d.mN = dot(cs[k].n, mulMV(K, cs[k].n));
-        d.mT0 = dot(t0, mulMV(K, t0));
-        d.mT1 = dot(t1, mulMV(K, t1));
-        d.accN = 0.0;
-        d.accT0 = 0.0;
-        d.accT1 = 0.0;
+        contact_setup(b1, p1, Iw1, b2, p2, Iw2, cs[k], t0, t1, sp, d);
         cp[k] = d;
     }
-    const double e = fmin_net(p1.e, p2.e);
-    const double mu = fmax_net(p2.mu, p1.mu);
-    const double inf = from_bits(0x7ff0000000000000LL);
+    const SolveConst sc = solve_const(p1, p2, sp);
 #pragma unroll 1
     for (int it = 0; it < sp.iterations; it++) {
 #pragma unroll 1
         for (int k = nc - 1; k >= 0; k--) {  // List.foldBack: reverse order
             CPData d = cp[k];
-            d3 n = cs[k].n;
-            d3 P;
-            if (d.mN == 0.0) {
-                P = mk(0.0, 0.0, 0.0);
-            } else {
-                d3 vrel = velocity_at(b2, Iw2, d.r2) - velocity_at(b1, Iw1, d.r1);
-                double vn = dot(vrel, n);
-                double j = (-(e + 1.0) * vn + d.bias) / d.mN;
-                double old = d.accN;
-                d.accN = clamp_net(0.0, inf, old + j);
-                P = scale(-(d.accN - old), n);
-            }
-            apply_impulse(b1, p1, d.r1, P);
-            apply_impulse(b2, p2, d.r2, -P);
-            if (sp.friction) {
-                d3 vrel = velocity_at(b2, Iw2, d.r2) - velocity_at(b1, Iw1, d.r1);
-                double maxF = mu * d.accN;
-                double j0 = dot(t0, vrel) / d.mT0;
-                double j1 = dot(t1, vrel) / d.mT1;
-                double o0 = d.accT0, o1 = d.accT1;
-                d.accT0 = clamp_net(-maxF, maxF, o0 + j0);
-                d.accT1 = clamp_net(-maxF, maxF, o1 + j1);
-                d3 P0 = scale(d.accT0 - o0, t0);
-                d3 P1 = scale(d.accT1 - o1, t1);
-                apply_impulse(b1, p1, d.r1, P0);
-                apply_impulse(b1, p1, d.r1, P1);
-                apply_impulse(b2, p2, d.r2, -P0);
-                apply_impulse(b2, p2, d.r2, -P1);
-            }
+            solve_contact(b1, p1, Iw1, b2, p2, Iw2, cs[k].n, t0, t1, d, sc);
             cp[k].accN = d.accN;
             cp[k].accT0 = d.accT0;
             cp[k].accT1 = d.accT1;

@@ -75,9 +75,9 @@ def host_harness():
         d = os.path.join(ROOT, "tests", "host_harness")
         so = os.path.join(d, "libps_host_harness.so")
         src = os.path.join(d, "physics_host.cpp")
-        deps = [src] + [os.path.join(ROOT, "physicssimulator_b200", "csrc", f) for f in ("ps_physics.cuh", "ps_math.cuh", "ps_sincos.h", "ps_octree.hpp")]
+        deps = [src] + [os.path.join(ROOT, "physicssimulator_b200", "csrc", f) for f in ("ps_physics.cuh", "ps_math.cuh", "ps_sincos.h", "ps_octree.hpp", "ps_coop.cuh", "ps_team.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-x", "c++", src, "-o", so])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-pthread", "-shared", "-x", "c++", src, "-o", so])
         _HH = ctypes.CDLL(so)
         _HH.hh_world_step_v.restype = None
         _HH.hh_tree_create.restype = ctypes.c_void_p
@@ -145,11 +145,11 @@ class ProductTree:
         return [(int(k) & 0xffff, int(k) >> 16) for k in out[:n]]
 
 
-def harness_step(bodies: dict, cfg_native, nsteps: int, cap_pairs=4096, cap_contacts=32768, fast=False):
+def harness_step(bodies: dict, cfg_native, nsteps: int, cap_pairs=4096, cap_contacts=32768, fast=False, mode=None):
     hh = host_harness()
     par, dyn = to_planar(bodies)
     n = len(bodies["mass"])
-    counters = np.zeros(5, dtype=np.int64)
+    counters = np.zeros(8, dtype=np.int64)
     pairs = np.zeros((cap_pairs, 3), dtype=np.int32)
     feats = np.zeros(cap_contacts, dtype=np.uint32)
     cont = np.zeros((cap_contacts, 7))
@@ -159,14 +159,15 @@ def harness_step(bodies: dict, cfg_native, nsteps: int, cap_pairs=4096, cap_cont
                        ctypes.byref(cfg_native), ctypes.c_int(nsteps), counters.ctypes.data_as(P_(ctypes.c_int64)),
                        pairs.ctypes.data_as(P_(ctypes.c_int32)), feats.ctypes.data_as(P_(ctypes.c_uint32)),
                        cont.ctypes.data_as(P_(ctypes.c_double)), counts.ctypes.data_as(P_(ctypes.c_int32)),
-                       ctypes.c_int(cap_pairs), ctypes.c_int(cap_contacts), ctypes.c_int(1 if fast else 0))
+                       ctypes.c_int(cap_pairs), ctypes.c_int(cap_contacts), ctypes.c_int(mode if mode is not None else (1 if fast else 0)))
     st = from_planar_dyn(dyn)
     npairs, nc = int(counts[0]), int(counts[1])
     first = np.concatenate([[0], np.cumsum(pairs[:npairs, 2])]).astype(np.int32)
     rec = {"pairs": pairs[:npairs, :2].copy(), "first": first, "normal": cont[:nc, 0:3].copy(), "position": cont[:nc, 3:6].copy(),
            "penetration": cont[:nc, 6].copy(), "feature": feats[:nc].copy()}
     return st, rec, {"pairs_tested": int(counters[0]), "pairs_colliding": int(counters[1]), "contacts": int(counters[2]),
-                     "errors": int(counters[3]), "overflow": int(counters[4])}
+                     "errors": int(counters[3]), "overflow": int(counters[4]),
+                     "team_runs": int(counters[5]), "team_literal": int(counters[6]), "team_mismatch": int(counters[7])}
 
 
 def assert_contacts_equal(a: dict, b: dict, what=""):

@@ -10,6 +10,8 @@
 
 #include "../../physicssimulator_b200/csrc/ps_physics.cuh"
 #include "../../physicssimulator_b200/csrc/ps_octree.hpp"
+#include "../../physicssimulator_b200/csrc/ps_coop.cuh"
+#include <thread>
 
 #include <cstring>
 #include <map>
@@ -45,10 +47,46 @@ void ld_par(const double* a, int N, int b, Par& p)
 }
 }  // namespace
 
+// box-box narrow phase by a team of 8 host threads (ps_coop.cuh under the barrier emulation of ps_team.cuh)
+static int team_detect_bb(const Dyn& di, const Par& pi, const Dyn& dj, const Par& pj, double eps, Contact* cs, int& err, bool& need_literal)
+{
+    using namespace psc;
+    static pstm::TeamShared<kTeam> sh;
+    static TeamScratch ts;
+    TeamContacts outs[kTeam];
+    int ncs[kTeam], errs[kTeam];
+    bool nl[kTeam];
+    std::thread th[kTeam];
+    for (int l = 0; l < kTeam; l++)
+        th[l] = std::thread([&, l] {
+            pstm::Team<kTeam> tm(&sh, l);
+            errs[l] = 0; nl[l] = false;
+            ncs[l] = detect_bb_team(tm, di, pi, dj, pj, eps, ts, outs[l], errs[l], nl[l]);
+        });
+    for (int l = 0; l < kTeam; l++) th[l].join();
+    for (int l = 1; l < kTeam; l++)
+        if (ncs[l] != ncs[0] || nl[l] != nl[0] || errs[l] != errs[0]) return -1000;  // lanes must agree
+    err = errs[0];
+    need_literal = nl[0];
+    int seen = 0;
+    for (int l = 0; l < kTeam; l++)
+        for (int t = 0; t < 2; t++)
+            if (outs[l].ord[t] >= 0) { cs[outs[l].ord[t]] = outs[l].c[t]; seen++; }
+    if (!need_literal && seen != ncs[0]) return -1001;
+    return ncs[0];
+}
+static bool same_contact(const Contact& a, const Contact& b)
+{
+    return memcmp(&a.n, &b.n, sizeof(d3)) == 0 && memcmp(&a.p, &b.p, sizeof(d3)) == 0 && memcmp(&a.pen, &b.pen, 8) == 0 && a.feat == b.feat;
+}
+
 extern "C" {
 
 // planar layouts as in ps_step_kernel.cuh: dyn[f*N+b] (18 planes), par[f*N+b] (16 planes, plane 0 = 1/mass)
-// fast = 1: the inlined/unrolled forms of the narrow phase (the ones the batch-wide kernels call)
+// fast bit 0: the inlined/unrolled forms of the narrow phase (the ones the batch-wide kernels call)
+// fast bit 1: the straight-line (select-based) integration (integrate_a)
+// fast bit 2: every box-box pair is ALSO run through the team form (ps_coop.cuh, 8 host threads per pair) and compared:
+//             counters[5] team runs, [6] literal requested, [7] mismatches
 void hh_world_step_v(int N, const double* par, double* dyn, const ps_step_config* cfg, int nsteps, int64_t* counters /*tested,hits,contacts,exc,overflow*/,
                      int32_t* last_pairs, uint32_t* last_feats, double* last_contacts /*7 per contact*/, int32_t* last_counts /*pairs,contacts*/, int cap_pairs, int cap_contacts,
                      int fast)
@@ -64,7 +102,7 @@ void hh_world_step_v(int N, const double* par, double* dyn, const ps_step_config
         auto get_pred = [&](int b, const Par& p, Dyn& out) {
             if (pvalid[b]) { ld_dyn(pred.data(), N, b, out); return; }
             Dyn cur; ld_dyn(dyn, N, b, cur);
-            integrate(cur, p, sp, out);
+            if (fast & 2) integrate_a(cur, p, sp, out); else integrate(cur, p, sp, out);
             st_dyn(pred.data(), N, b, out);
             pvalid[b] = 1;
         };
@@ -77,7 +115,20 @@ void hh_world_step_v(int N, const double* par, double* dyn, const ps_step_config
                 Contact* cs = sc.cs;
                 int err = 0, ovf = 0;
                 counters[0]++;
-                int nc = fast ? detect_t<true>(di, pi, dj, pj, sp.eps, cs, err, ovf, sc) : detect(di, pi, dj, pj, sp.eps, cs, err, ovf, sc);
+                int nc = (fast & 1) ? detect_t<true>(di, pi, dj, pj, sp.eps, cs, err, ovf, sc) : detect(di, pi, dj, pj, sp.eps, cs, err, ovf, sc);
+                if ((fast & 4) && pi.shape == 1 && pj.shape == 1) {  // the team form must give the literal answer (or ask for it)
+                    Contact tc[PS_MAX_CONTACTS];
+                    int terr = 0;
+                    bool nl = false;
+                    int tn = team_detect_bb(di, pi, dj, pj, sp.eps, tc, terr, nl);
+                    counters[5]++;
+                    if (nl) counters[6]++;
+                    else {
+                        bool okc = tn == nc && terr == err;
+                        for (int k = 0; okc && k < nc; k++) okc = same_contact(tc[k], cs[k]);
+                        if (!okc) counters[7]++;
+                    }
+                }
                 counters[3] += err; counters[4] += ovf;
                 if (nc <= 0) continue;
                 counters[1]++; counters[2] += nc;
@@ -100,7 +151,7 @@ void hh_world_step_v(int N, const double* par, double* dyn, const ps_step_config
         for (int b = 0; b < N; b++) {
             Dyn out;
             if (pvalid[b]) ld_dyn(pred.data(), N, b, out);
-            else { Par p; ld_par(par, N, b, p); Dyn cur; ld_dyn(dyn, N, b, cur); integrate(cur, p, sp, out); }
+            else { Par p; ld_par(par, N, b, p); Dyn cur; ld_dyn(dyn, N, b, cur); if (fast & 2) integrate_a(cur, p, sp, out); else integrate(cur, p, sp, out); }
             st_dyn(dyn, N, b, out);
         }
         if (last_counts) { last_counts[0] = np; last_counts[1] = ncs; }

@@ -92,3 +92,36 @@ def test_random_box_and_sphere_pairs_incl_axis_aligned():
                     Position=pos, Yaw=ang(), Pitch=ang(), Roll=ang(), Mass=rng.uniform(1, 50),
                     Velocity=(rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-1, 1))))
         _run(protos, Configuration(), [1, 3, 12], f"random trial {trial}")
+
+
+def test_team_form_of_box_box_and_straight_line_integrate():
+    """ps_coop.cuh (8 lanes per box pair, here 8 host threads behind a barrier) must give the literal routine's manifold —
+    normals, points, penetrations, feature ids, contact order — or ask for the literal routine; the straight-line
+    integration (integrate_a) must give integrate()'s bits.  Stacked axis-aligned boxes put exact ties on the arg-min."""
+    rng = scenes.SplitMix64(77)
+    total = {"team_runs": 0, "team_literal": 0, "team_mismatch": 0, "pairs_colliding": 0}
+    worlds = [scenes.c3_mixed128(1, n_boxes=24, n_spheres=8), scenes.c1_stack20()]
+    for trial in range(6):
+        protos = [P.createDefaultBox(6, 6, 1).With(Mass=P.INFINITE, UseGravity=False, Position=(0, 0, -0.5))]
+        for k in range(6):
+            aligned = trial % 2 == 0
+            ang = (lambda: 0.0) if aligned else (lambda: rng.uniform(-3.1, 3.1))
+            pos = (rng.uniform(-0.7, 0.7), rng.uniform(-0.7, 0.7), rng.uniform(0.3, 1.4))
+            if aligned:
+                pos = tuple(round(x * 4) / 4 for x in pos)
+            protos.append(P.createDefaultBox(rng.uniform(0.3, 1.0), rng.uniform(0.3, 1.0), rng.uniform(0.3, 1.0)).With(
+                Position=pos, Yaw=ang(), Pitch=ang(), Roll=ang(), Mass=rng.uniform(1, 50)))
+        worlds.append((protos, Configuration()))
+    for protos, cfg in worlds:
+        b = P.build_world(protos, cfg.StepConfig.GravitationalAccelerationMagnitude, cfg.StepConfig.GravityDirection)
+        nc = to_native_config(cfg)
+        o = OracleWorld(b, nc)
+        o.step(25)
+        st, rec, cnt = harness_step(b, nc, 25, mode=1 | 2 | 4)
+        assert_state_bits(o.get_state(), st, "team/straight-line")
+        assert_contacts_equal(o.contacts(), rec, "team/straight-line")
+        for k in total:
+            total[k] += cnt[k]
+    assert total["team_runs"] > 1000 and total["pairs_colliding"] > 100
+    assert total["team_mismatch"] == 0, total
+    assert total["team_literal"] * 20 <= total["team_runs"], total
