@@ -69,7 +69,9 @@ typedef struct {
     /* SpatialTreeConfiguration (Configuration.fs:13-23), read when broadphase_kind == 1 */
     int32_t tree_leaf_capacity;     /* LeafCapacity = 4 */
     int32_t tree_max_depth;         /* MaxDepth = 10 */
-    int32_t reserved;
+    int32_t aabb_mode;              /* extents handed to the SpatialTree: 0 = reference (a sphere's box has side =
+                                     * radius, SimulatorObject.fs:58-71, Appendix B Q5), 1 = conservative (side = 2r).
+                                     * Only read when broadphase_kind == 1: the Dummy order tests every pair. */
     double tree_min[3];             /* SpaceBoundaries.Min = (-15,-15,-15) */
     double tree_max[3];             /* SpaceBoundaries.Max = ( 15, 15, 15) */
 } ps_step_config;
@@ -154,8 +156,12 @@ int ps_batch_destroy(void* handle);
 
 /* Simulator.updateSimulation x n_steps (Simulator.fs:47-62): resolveAll then update, per world */
 int ps_batch_step(void* handle, int32_t n_steps);
-/* same, but on a caller stream (cudaStream_t passed as void*) and without the final
- * synchronise — for overlap and CUDA-graph capture */
+/* same, but on a caller stream (cudaStream_t passed as void*) and without the final synchronise.  The call orders
+ * the caller's stream after everything the handle's own stream holds, and the handle's stream (so
+ * ps_batch_synchronize and every later call on the handle) after the work launched here.  CUDA-graph capture of the
+ * caller's stream: supported for batches that step without a host round trip (ps_batch_schedule reports
+ * host_syncs_per_step = 0: the fused kernel and the device-driven batch-wide path); a SpatialTree-order batch returns
+ * PS_ERR_INVALID_OPERATION while capturing.  During a capture the two orderings above are the capture's business. */
 int ps_batch_step_async(void* handle, int32_t n_steps, void* cuda_stream);
 int ps_batch_synchronize(void* handle);
 

@@ -28,7 +28,7 @@ type PsStepConfig =
     val mutable exactAllPairs: int
     val mutable treeLeafCapacity: int
     val mutable treeMaxDepth: int
-    val mutable reserved: int
+    val mutable aabb_mode: int
     val mutable treeMinX: float
     val mutable treeMinY: float
     val mutable treeMinZ: float

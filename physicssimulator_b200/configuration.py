@@ -87,13 +87,13 @@ class ps_step_config(ctypes.Structure):
         ("exact_all_pairs", ctypes.c_int32),
         ("tree_leaf_capacity", ctypes.c_int32),
         ("tree_max_depth", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("aabb_mode", ctypes.c_int32),
         ("tree_min", ctypes.c_double * 3),
         ("tree_max", ctypes.c_double * 3),
     ]
 
 
-def to_native_config(cfg: Configuration, record_contacts: bool = False, exact_all_pairs: bool = False) -> ps_step_config:
+def to_native_config(cfg: Configuration, record_contacts: bool = False, exact_all_pairs: bool = False, aabb_mode: int = 0) -> ps_step_config:
     s = cfg.StepConfig
     t = cfg.BroadPhaseCollisionDetectionKind.SpatialTree
     tree = t or SpatialTreeConfiguration()
@@ -114,5 +114,5 @@ def to_native_config(cfg: Configuration, record_contacts: bool = False, exact_al
         restore_joints=1 if cfg.RestoreJoints else 0,
         record_contacts=1 if record_contacts else 0,
         exact_all_pairs=1 if exact_all_pairs else 0,
-        reserved=0,
+        aabb_mode=int(aabb_mode),
     )

@@ -79,11 +79,12 @@ struct Batch {
     int* d_row = nullptr;             // near-list row offsets
     unsigned char* d_lists = nullptr; // near list | level | order | hit of every world (9 B per pair of the world)
     long long* d_lists_off = nullptr;
-    PairScratch* d_scratch = nullptr; // one record per launched thread
     int* d_lvl = nullptr;
     unsigned short* d_last = nullptr;
     // batch-wide path (ps_wide.cuh)
+    bool broken = false;  // a failed re-upload left no device state: entry points refuse until ps_batch_reset succeeds
     bool wide = false;
+    bool wide_device_rounds = false;  // rounds driven from the device (no host read-back inside a step)
     int* d_body_world = nullptr;
     unsigned char *d_pvalid = nullptr, *d_nhit = nullptr, *d_isstat = nullptr, *d_isbox = nullptr, *d_always_fused = nullptr;
     int *d_K = nullptr, *d_maxl = nullptr;
@@ -107,6 +108,7 @@ struct Batch {
     int rec_pair_cap = 0, rec_contact_cap = 0;
     ps_stats* d_stats_sum = nullptr;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_own = nullptr, ev_foreign = nullptr;  // ordering between the handle's stream and a caller's stream
     std::vector<cudaStream_t> chunk_streams;  // ps_batch_step_host: one stream per world chunk
     std::vector<cudaEvent_t> chunk_done;
     cudaEvent_t chunk_start = nullptr;
@@ -220,31 +222,39 @@ __global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const 
 // SimulatorObject.getAABoundingBox (SimulatorObject.fs:58-71: a sphere's box has side = radius, quirk Q5;
 // Box.worldAxisAlignedSize, Box.fs:69-85) as objExtentProvider hands it to the tree (BroadPhase.fs:21-31: size and
 // MIN corner = centre - size / 2), from the body-major records
-__global__ void extent_kernel(int n, const double* __restrict__ dyn, const double* __restrict__ par, double* __restrict__ ext)
+// (host + device: ps_batch_add_body checks a new body against the tree's space before it changes anything)
+__host__ __device__ inline void body_extent6(const double* pos, const double* rot, const double* dims, bool sphere, int aabb_mode, double* o)
+{
+    // scalar on purpose (psm:: routines are device functions): mulMV's sums written out, `+ 0.0` = the zero position of
+    // toWorldCoordinates with the orientation only (Box.fs:69-85), scale(1/2, size) for the min corner (BroadPhase.fs:21-31)
+    double sx, sy, sz;
+    if (sphere) {
+        sx = sy = sz = (aabb_mode == 1) ? 2.0 * dims[0] : dims[0];  // Box.createCube radius (Q5); 1 = conservative, side 2r
+    } else {
+        const double h[3] = {dims[0] / 2.0, dims[1] / 2.0, dims[2] / 2.0};
+        double s[3];
+        for (int r = 0; r < 3; r++) {
+            double acc = 0.0;
+            for (int c = 0; c < 3; c++) {  // column c of R scaled by the half size: R * (h_c e_c) + 0
+                const double vx = c == 0 ? h[0] : 0.0, vy = c == 1 ? h[1] : 0.0, vz = c == 2 ? h[2] : 0.0;
+                const double e = (((0.0 + rot[3 * r] * vx) + rot[3 * r + 1] * vy) + rot[3 * r + 2] * vz) + 0.0;
+                acc = c == 0 ? fabs(e) : acc + fabs(e);
+            }
+            s[r] = acc * 2.0;
+        }
+        sx = s[0]; sy = s[1]; sz = s[2];
+    }
+    const double half = 1.0 / 2.0;
+    o[0] = sx; o[1] = sy; o[2] = sz;
+    o[3] = pos[0] - half * sx; o[4] = pos[1] - half * sy; o[5] = pos[2] - half * sz;
+}
+__global__ void extent_kernel(int n, const double* __restrict__ dyn, const double* __restrict__ par, double* __restrict__ ext, int aabb_mode)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const double* d = dyn + (size_t)g * kDynF;
     const double* p = par + (size_t)g * kParF;
-    double sx, sy, sz;
-    if (p[15] == 0.0) {
-        sx = sy = sz = p[12];  // Box.createCube radius
-    } else {
-        m33 R;
-#pragma unroll
-        for (int k = 0; k < 9; k++) R.a[k] = d[6 + k];
-        double hx = p[12] / 2.0, hy = p[13] / 2.0, hz = p[14] / 2.0;
-        d3 z = mk(0.0, 0.0, 0.0);
-        d3 ex = mulMV(R, mk(hx, 0.0, 0.0)) + z;  // toWorldCoordinates with the orientation only
-        d3 ey = mulMV(R, mk(0.0, hy, 0.0)) + z;
-        d3 ez = mulMV(R, mk(0.0, 0.0, hz)) + z;
-        sx = (fabs(ex.x) + fabs(ey.x) + fabs(ez.x)) * 2.0;
-        sy = (fabs(ex.y) + fabs(ey.y) + fabs(ez.y)) * 2.0;
-        sz = (fabs(ex.z) + fabs(ey.z) + fabs(ez.z)) * 2.0;
-    }
-    d3 mn = mk(d[0], d[1], d[2]) - scale(1.0 / 2.0, mk(sx, sy, sz));
-    double* o = ext + (size_t)g * 6;
-    o[0] = sx; o[1] = sy; o[2] = sz; o[3] = mn.x; o[4] = mn.y; o[5] = mn.z;
+    body_extent6(d, d + 6, p + 12, p[15] == 0.0, aabb_mode, ext + (size_t)g * 6);
 }
 
 // ---- helpers ---------------------------------------------------------------------------------------
@@ -256,7 +266,7 @@ void dfree(T*& p)
 }
 void free_device(Batch* B)
 {
-    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cost); dfree(B->d_perm); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_scratch); dfree(B->d_lvl); dfree(B->d_last);
+    dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cost); dfree(B->d_perm); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
     dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt);
@@ -279,6 +289,11 @@ int validate_bodies(const HostBodies& h)
         if (h.shape[i] != 0 && h.shape[i] != 1) return fail(PS_ERR_INVALID_ARGUMENT, "body %d: shape must be 0 (sphere) or 1 (box)", i);
         for (int k = 0; k < 3; k++)
             if (h.dims[3 * i + k] < 0.0) return fail(PS_ERR_INVALID_ARGUMENT, "body %d: Must be positive (size)", i);  // throwIfNegative
+        if (!(h.mass[i] > 0.0)) return fail(PS_ERR_INVALID_ARGUMENT, "body %d: Must be positive (mass)", i);  // Mass.Value rejects <= 0 (Base.fs:13-20); NaN too
+        // Mass.Infinite: the reference inverts an infinite inertia to exactly 0 (RigidBody.fs:76); the parallel paths fold a
+        // static body's angular momentum per pair, which is only the reference's value with that zero
+        if (std::isinf(h.mass[i]) && (h.iinv[3 * i] != 0.0 || h.iinv[3 * i + 1] != 0.0 || h.iinv[3 * i + 2] != 0.0))
+            return fail(PS_ERR_INVALID_ARGUMENT, "body %d: infinite mass needs inertia_inv = 0", i);
         if (h.e[i] < 0.0 || h.e[i] > 1.0) return fail(PS_ERR_INVALID_ARGUMENT, "body %d: elasticityCoeff Invalid value", i);
         if (h.muk[i] < 0.0 || h.mus[i] < 0.0) return fail(PS_ERR_INVALID_ARGUMENT, "body %d: staticFrictionCoeff Invalid value", i);
     }
@@ -358,8 +373,6 @@ int upload(Batch* B, bool with_state)
         CK(cudaMemcpy(B->d_lists_off, loff.data(), loff.size() * sizeof(long long), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&B->d_cull, nb * kCullF * sizeof(double)));
         CK(cudaMalloc(&B->d_row, (nb + (size_t)B->n_worlds + 1) * sizeof(int)));
-        const size_t wpc = 32 / B->threads, grid = ((size_t)B->n_worlds + wpc - 1) / wpc;
-        CK(cudaMalloc(&B->d_scratch, std::max<size_t>(grid, 1) * 32 * sizeof(PairScratch)));
         CK(cudaMalloc(&B->d_lvl, (size_t)std::max(1, B->n_worlds) * (kMaxLevels + 2) * sizeof(int)));
         CK(cudaMalloc(&B->d_last, nb * sizeof(unsigned short)));
     }
@@ -508,7 +521,7 @@ int upload(Batch* B, bool with_state)
 int tree_pull_extents(Batch* B, cudaStream_t st)
 {
     if (B->n_bodies == 0) return PS_OK;
-    extent_kernel<<<(B->n_bodies + 127) / 128, 128, 0, st>>>(B->n_bodies, B->d_dyn, B->d_par, B->d_ext);
+    extent_kernel<<<(B->n_bodies + 127) / 128, 128, 0, st>>>(B->n_bodies, B->d_dyn, B->d_par, B->d_ext, B->cfg.aabb_mode);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(B->h_ext, B->d_ext, (size_t)B->n_bodies * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -609,6 +622,8 @@ int check_view(const ps_bodies_view* v)
 // ====================================================================================================
 extern "C" {
 
+#define PS_REFUSE_IF_BROKEN(B) do { if ((B)->broken) return fail(PS_ERR_INVALID_OPERATION, "the batch lost its device state in a failed ps_batch_add_body; ps_batch_reset rebuilds it"); } while (0)
+
 int ps_version(void) { return 100; }
 const char* ps_last_error(void) { return g_err.c_str(); }
 
@@ -635,6 +650,7 @@ int ps_batch_create(void** handle, const ps_bodies_view* bodies, const ps_joints
     if (rc) return rc;
     if (config->solver_iterations < 0) return fail(PS_ERR_INVALID_ARGUMENT, "solver_iterations must be >= 0");
     if (config->broadphase_kind != 0 && config->broadphase_kind != 1) return fail(PS_ERR_INVALID_ARGUMENT, "broadphase_kind must be 0 (Dummy) or 1 (SpatialTree)");
+    if (config->aabb_mode != 0 && config->aabb_mode != 1) return fail(PS_ERR_INVALID_ARGUMENT, "aabb_mode must be 0 (reference) or 1 (conservative)");
     if (!(config->dt == config->dt)) return fail(PS_ERR_INVALID_ARGUMENT, "dt is NaN");
     if (g_device < 0) {
         rc = ps_init(-1);
@@ -716,6 +732,8 @@ int ps_batch_destroy(void* handle)
     for (cudaStream_t s : B->chunk_streams) cudaStreamDestroy(s);
     for (cudaEvent_t e : B->chunk_done) cudaEventDestroy(e);
     if (B->chunk_start) cudaEventDestroy(B->chunk_start);
+    if (B->ev_own) cudaEventDestroy(B->ev_own);
+    if (B->ev_foreign) cudaEventDestroy(B->ev_foreign);
     cudaStreamDestroy(B->stream);
     delete B;
     return PS_OK;
@@ -739,7 +757,7 @@ static void fill_kargs(Batch* B, KArgs& a, int n_steps)
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
     a.max_n = B->max_n;
     a.hitcnt = B->d_hitcnt; a.cur = B->d_cur; a.pred = B->d_pred; a.S = B->d_S;
-    a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.scratch = B->d_scratch; a.lvl = B->d_lvl; a.last = B->d_last;
+    a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.lvl = B->d_lvl; a.last = B->d_last;
     a.only_flagged = nullptr;
     a.world_base = 0;
     a.perm = nullptr;
@@ -895,6 +913,34 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     return PS_OK;
 }
 
+// Work launched on a caller's stream touches the same device buffers as everything the handle does on its own
+// stream (get/set_state, apply_impulse, step_host, stats ...).  enter: the caller's stream waits for what the handle's
+// stream holds; leave: the handle's stream (and so ps_batch_synchronize and every later call) waits for the caller's
+// work.  While the caller's stream is being captured into a CUDA graph neither is possible (an event recorded outside
+// a capture cannot be waited on inside it): the capture then owns the ordering, as the header says.
+static int foreign_enter(Batch* B, cudaStream_t st, bool* capturing)
+{
+    *capturing = false;
+    if (st == B->stream) return PS_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    CK(cudaStreamIsCapturing(st, &cs));
+    if (cs != cudaStreamCaptureStatusNone) { *capturing = true; return PS_OK; }
+    if (!B->ev_own) CK(cudaEventCreateWithFlags(&B->ev_own, cudaEventDisableTiming));
+    if (!B->ev_foreign) CK(cudaEventCreateWithFlags(&B->ev_foreign, cudaEventDisableTiming));
+    CK(cudaEventRecord(B->ev_own, B->stream));
+    CK(cudaStreamWaitEvent(st, B->ev_own, 0));
+    return PS_OK;
+}
+static int foreign_leave(Batch* B, cudaStream_t st, bool capturing)
+{
+    if (st == B->stream || capturing) return PS_OK;
+    CK(cudaEventRecord(B->ev_foreign, st));
+    CK(cudaStreamWaitEvent(B->stream, B->ev_foreign, 0));
+    return PS_OK;
+}
+
+static bool step_needs_host(const Batch* B) { return B->tree_mode || (B->wide && !B->wide_device_rounds); }
+
 static int launch_step(Batch* B, int n_steps, cudaStream_t st)
 {
     if (n_steps < 0) return fail(PS_ERR_INVALID_ARGUMENT, "n_steps must be >= 0");
@@ -928,6 +974,7 @@ int ps_batch_step(void* handle, int32_t n_steps)
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     CK(cudaSetDevice(B->device));
     int rc = launch_step(B, n_steps, B->stream);
     if (rc) return rc;
@@ -938,13 +985,23 @@ int ps_batch_step_async(void* handle, int32_t n_steps, void* cuda_stream)
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     CK(cudaSetDevice(B->device));
-    return launch_step(B, n_steps, cuda_stream ? (cudaStream_t)cuda_stream : B->stream);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : B->stream;
+    bool capturing = false;
+    int rc = foreign_enter(B, st, &capturing);
+    if (rc) return rc;
+    if (capturing && step_needs_host(B))
+        return fail(PS_ERR_INVALID_OPERATION, "this batch steps with a host round trip per step (SpatialTree order, or the batch-wide path's per-step bucket read-back): it cannot be captured into a CUDA graph");
+    rc = launch_step(B, n_steps, st);
+    if (rc) return rc;
+    return foreign_leave(B, st, capturing);
 }
 int ps_batch_synchronize(void* handle)
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     CK(cudaSetDevice(B->device));
     CK(cudaStreamSynchronize(B->stream));
     return PS_OK;
@@ -961,21 +1018,26 @@ int ps_batch_get_state_device(void* handle, int32_t w0, int32_t w1, double* d_po
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     int rc = check_range(B, w0, w1);
     if (rc) return rc;
     CK(cudaSetDevice(B->device));
     int b0 = B->cur.off[w0], n = B->cur.off[w1] - b0;
     if (n == 0) return PS_OK;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : B->stream;
+    bool capturing = false;
+    rc = foreign_enter(B, st, &capturing);
+    if (rc) return rc;
     unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_off, w0, w1, d_pos, d_vel, d_rot, d_ang_mom, B->d_dyn, b0);
     CK(cudaGetLastError());
-    return PS_OK;
+    return foreign_leave(B, st, capturing);
 }
 
 int ps_batch_get_state(void* handle, int32_t w0, int32_t w1, double* pos, double* vel, double* rot, double* ang_mom)
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     int rc = check_range(B, w0, w1);
     if (rc) return rc;
     CK(cudaSetDevice(B->device));
@@ -999,6 +1061,7 @@ int ps_batch_set_state(void* handle, int32_t w0, int32_t w1, const double* pos, 
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     int rc = check_range(B, w0, w1);
     if (rc) return rc;
     if (!pos || !vel || !rot || !ang_mom) return fail(PS_ERR_INVALID_ARGUMENT, "state array is null");
@@ -1026,6 +1089,7 @@ int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, cons
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     if (n_steps < 0) return fail(PS_ERR_INVALID_ARGUMENT, "n_steps must be >= 0");
     if (!pos_in || !vel_in || !rot_in || !ang_mom_in || !pos_out || !vel_out || !rot_out || !ang_mom_out)
         return fail(PS_ERR_INVALID_ARGUMENT, "state array is null");
@@ -1086,6 +1150,7 @@ int ps_batch_get_contacts(void* handle, int32_t world, int32_t* n_pairs, int32_t
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     if (world < 0 || world >= B->n_worlds) return fail(PS_ERR_OUT_OF_RANGE, "world %d outside [0,%d)", world, B->n_worlds);
     if (!B->d_rec_pairs) return fail(PS_ERR_INVALID_OPERATION, "batch was created with record_contacts = 0");
     if (!n_pairs) return fail(PS_ERR_INVALID_ARGUMENT, "n_pairs is null");
@@ -1153,6 +1218,7 @@ int ps_batch_apply_impulse(void* handle, int32_t world, int32_t body, const doub
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     if (world < 0 || world >= B->n_worlds) return fail(PS_ERR_OUT_OF_RANGE, "world %d outside [0,%d)", world, B->n_worlds);
     int N = B->cur.off[world + 1] - B->cur.off[world];
     if (body < 0 || body >= N) return fail(PS_ERR_OUT_OF_RANGE, "body %d outside [0,%d)", body, N);  // KeyNotFoundException
@@ -1169,6 +1235,7 @@ int ps_batch_add_body(void* handle, int32_t world, const ps_bodies_view* one)
 {
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     if (world < 0 || world >= B->n_worlds) return fail(PS_ERR_OUT_OF_RANGE, "world %d outside [0,%d)", world, B->n_worlds);
     int rc = check_view(one);
     if (rc) return rc;
@@ -1177,10 +1244,26 @@ int ps_batch_add_body(void* handle, int32_t world, const ps_bodies_view* one)
     copy_view(nb, one);
     rc = validate_bodies(nb);
     if (rc) return rc;
-    // pull the live state, splice the body in as id = max id + 1 of that world (SimulatorState.fs:90-92), re-upload
+    // Everything that can refuse the body is checked BEFORE anything changes (a failed call leaves the batch as it was):
+    // the per-world size limit, and in SpatialTree mode the tree's space (BroadPhase.onNewObjectAdded throws
+    // "out of space bounds", BroadPhase.fs:83-98 / SpatialTree.fs:171-172).
     HostBodies& h = B->cur;
+    if (h.off[world + 1] - h.off[world] + 1 > 1024)
+        return fail(PS_ERR_INVALID_ARGUMENT, "world %d would have %d bodies; the per-world stepper takes at most 1024", world, h.off[world + 1] - h.off[world] + 1);
+    if (B->tree_mode) {
+        double e6[6];
+        body_extent6(nb.pos.data(), nb.rot.data(), nb.dims.data(), nb.shape[0] == 0, B->cfg.aabb_mode, e6);
+        pst::Ext<3> oe;
+        for (int k = 0; k < 3; k++) { oe.size[k] = e6[k]; oe.pos[k] = e6[3 + k]; }
+        if (!B->trees[world].in_space(oe))
+            return fail(PS_ERR_INVALID_ARGUMENT, "world %d: object %d out of space bounds", world, h.off[world + 1] - h.off[world]);
+    }
+    // pull the live state, splice the body in as id = max id + 1 of that world (SimulatorState.fs:90-92), re-upload
     rc = ps_batch_get_state(B, 0, B->n_worlds, h.pos.data(), h.vel.data(), h.rot.data(), h.L.data());
     if (rc) return rc;
+    std::vector<WorldStats> keep(B->n_worlds);
+    CK(cudaMemcpy(keep.data(), B->d_stats, keep.size() * sizeof(WorldStats), cudaMemcpyDeviceToHost));
+    const HostBodies before = h;
     int at = h.off[world + 1];
     auto ins = [&](std::vector<double>& dst, const std::vector<double>& src, int per) { dst.insert(dst.begin() + (size_t)per * at, src.begin(), src.end()); };
     h.shape.insert(h.shape.begin() + at, nb.shape[0]);
@@ -1188,17 +1271,24 @@ int ps_batch_add_body(void* handle, int32_t world, const ps_bodies_view* one)
     ins(h.rot, nb.rot, 9); ins(h.L, nb.L, 3); ins(h.force, nb.force, 3); ins(h.torque, nb.torque, 3); ins(h.e, nb.e, 1);
     ins(h.muk, nb.muk, 1); ins(h.mus, nb.mus, 1);
     for (int w = world + 1; w <= B->n_worlds; w++) h.off[w]++;
-    std::vector<WorldStats> keep(B->n_worlds);
-    CK(cudaMemcpy(keep.data(), B->d_stats, keep.size() * sizeof(WorldStats), cudaMemcpyDeviceToHost));
     rc = upload(B, true);
-    if (rc) return rc;
+    if (rc) {  // (shared-memory limit of a grown world, out of device memory): back to the batch as it was
+        const std::string why = g_err;
+        B->cur = before;
+        if (upload(B, true) != PS_OK) {
+            B->broken = true;  // no device state left: every entry point but reset/destroy refuses from here on
+            return fail(PS_ERR_CUDA, "add_body failed (%s) and the previous batch could not be restored: call ps_batch_reset", why.c_str());
+        }
+        cudaMemcpy(B->d_stats, keep.data(), keep.size() * sizeof(WorldStats), cudaMemcpyHostToDevice);
+        return fail(rc, "%s", why.c_str());
+    }
     CK(cudaMemcpy(B->d_stats, keep.data(), keep.size() * sizeof(WorldStats), cudaMemcpyHostToDevice));
     if (B->tree_mode) {  // BroadPhase.onNewObjectAdded (BroadPhase.fs:83-98): the new id joins the existing tree
         rc = tree_pull_extents(B, B->stream);
         if (rc) return rc;
         const int o = h.off[world], id = h.off[world + 1] - o - 1;
         if (!B->trees[world].insert(id, [&](int x) { return ext_of(B, o + x); }))
-            return fail(PS_ERR_INVALID_ARGUMENT, "world %d: object %d out of space bounds", world, id);  // the reference throws after its state update too
+            return fail(PS_ERR_INVALID_ARGUMENT, "world %d: object %d out of space bounds", world, id);  // (ruled out above: same extent, same test)
         B->h_cand_off.assign((size_t)B->n_worlds + 1, 0);
         B->h_cand.clear();
     }
@@ -1210,8 +1300,10 @@ int ps_batch_reset(void* handle)
     if (!handle) return fail(PS_ERR_INVALID_ARGUMENT, "handle is null");
     Batch* B = (Batch*)handle;
     B->cur = B->init;  // bodies added later are dropped (Simulator.fs:36-40,113-121)
+    B->broken = false;
     int rc = upload(B, true);
     if (!rc && B->tree_mode) rc = tree_init_all(B);  // initSimulationState builds the tree anew
+    B->broken = rc != PS_OK;  // the initial batch uploaded at create; if it does not now, the device is gone
     return rc;
 }
 
@@ -1219,6 +1311,7 @@ int ps_batch_stats(void* handle, ps_stats* out)
 {
     if (!handle || !out) return fail(PS_ERR_INVALID_ARGUMENT, "handle/out is null");
     Batch* B = (Batch*)handle;
+    PS_REFUSE_IF_BROKEN(B);
     CK(cudaSetDevice(B->device));
     CK(cudaMemsetAsync(B->d_stats_sum, 0, sizeof(ps_stats), B->stream));
     if (B->n_worlds > 0) {

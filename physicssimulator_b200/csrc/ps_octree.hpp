@@ -93,6 +93,9 @@ public:
         return true;
     }
 
+    // would insert() accept this extent?  (the test insert starts with, :171-172)
+    bool in_space(const Ext<D>& oe) const { return intersecting(space_, oe); }
+
     // removeAll (:122-135): the ids for which gone(id) holds leave every leaf; the tree keeps its shape
     template <class Pred>
     void remove_if(Pred&& gone)

@@ -111,7 +111,6 @@ struct KArgs {
     unsigned short* last;     // [total_bodies] level of the last near pair of each body
     unsigned char* lists;     // per world: n_pairs * 9 bytes (near u32 | level u16 | order u16 | hit u8)
     const long long* lists_off; // n_worlds+1 byte offsets (16-byte aligned)
-    PairScratch* scratch;     // one record per launched thread
     // when set: only worlds with a non-zero flag are stepped (the batch-wide path hands its failed worlds over);
     // bit0 margin violated -> start at the 8x margin, bit1 static pose / too many statics -> exact serial walk
     const unsigned* only_flagged;
@@ -231,7 +230,6 @@ struct Ctx {
     int N, w;
     const KArgs* a;
     BlockShared* bs;
-    PairScratch* scratch;  // this thread's record in global memory
     // per-thread counters of the current attempt
     unsigned tested, hits, contacts, overflow, ref_exc;
     double max_pen;
@@ -347,12 +345,7 @@ PSD void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
         if (sj) dj.L = mk(0.0, 0.0, 0.0);
         resolve_t<1>(di, pi, dj, pj, cs, 1, cp, c.a->sp);
     } else {
-#if PS_SCRATCH_GLOBAL
-        PairScratch& sc = *c.scratch;
-#else
-        PairScratch sc_local;
-        PairScratch& sc = sc_local;
-#endif
+        PairScratch sc;  // clip buffers + manifold on the local stack (a per-thread global record was measured: slower)
         Contact* cs = sc.cs;
         nc = detect_bb(di, pi, dj, pj, c.a->sp.eps, cs, err, ovf, sc);
         if (err) c.ref_exc++;
@@ -415,9 +408,6 @@ PSD bool near_test_grown(const Smem& s, int N, int i, int j, double gi, double g
     return !(dd > r * r);
 }
 
-#ifndef PS_SCRATCH_GLOBAL
-#define PS_SCRATCH_GLOBAL 0  // 1: per-pair working arrays in a per-thread global record instead of the local stack
-#endif
 #ifndef PS_MINB32
 #define PS_MINB32 16  // resident one-warp CTAs per SM the register allocation must allow (65536 / (32 * regs))
 #endif
@@ -464,7 +454,6 @@ __global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
     const int N = live ? a.off[w + 1] - off : 0;
     Ctx c;
     c.N = N; c.w = w; c.a = &a; c.bs = &bs;
-    c.scratch = a.scratch + ((size_t)(a.world_base / (32 / T) + blockIdx.x) * 32 + threadIdx.x);
     carve(smem_raw + (size_t)tile * smem_bytes(a.max_n), N, c.s);
     Smem& s = c.s;
     {

@@ -143,14 +143,45 @@ def c3_mixed128(world: int, n_boxes: int = 64, n_spheres: int = 63) -> Tuple[Lis
 
 
 def c4_chain32(world: int, n_links: int = 32):
-    """C4: ground + static anchor cube + 32 box links 0.2x0.2x1.0 hanging diagonally; ball-socket joints
-    (1,2),(2,3)...; restore_joints=1.  Returns (prototypes, configuration, joints[(a, b, anchor_world)])."""
+    """C4: ground 80x80 + static anchor cube + 32 box links 0.2x0.2x1.0 in a nearly horizontal chain (pitch 1.35 +- 0.1,
+    any yaw) whose lowest link starts ~1 m above the ground; ball-socket joints (1,2),(2,3)...; restore_joints=1.
+    Joint.restore as written (Joints.fs:55-94) applies K.(-vRel) N times: a velocity feedback of gain ~ N.|K|^2 with
+    K ~ 1/mass.  With the links at 1000 kg the gain stays below 2 and the chains fall, land, pile up and come to rest
+    with finite states (oracle: 800 steps, ~53 colliding pairs and ~167 contacts per world-step at rest); lighter links
+    diverge (`c4_chain32_blowup`, kept for parity through the blow-up).
+    Returns (prototypes, configuration, joints[(a, b, anchor_world)])."""
+    rng = SplitMix64(scene_seed(4, world))
+    protos = [_ground(80.0, 80.0, 1.01)]
+    yaw = rng.uniform(-math.pi, math.pi)
+    pitch = 1.35 + rng.uniform(-0.1, 0.1)
+    # link long axis = local z in the reference's yaw/pitch/roll convention (Matrix3.fs:90-108)
+    R = P.from_yaw_pitch_roll(yaw, pitch, 0.0)
+    axis = R[:, 2]
+    if axis[2] < 0.0:
+        axis = -axis
+    span = axis * float(n_links)
+    top = (rng.uniform(-0.5, 0.5) + span[0] / 2.0, rng.uniform(-0.5, 0.5) + span[1] / 2.0, 1.5 + span[2])
+    protos.append(P.createDefaultCube(0.2).With(Mass=P.INFINITE, UseGravity=False, Position=top))
+    joints = []
+    end = np.array(top)
+    for k in range(n_links):
+        centre = end - axis * 0.5
+        protos.append(P.createDefaultBox(0.2, 0.2, 1.0).With(Mass=1000.0, Position=tuple(centre), Yaw=yaw, Pitch=pitch))
+        joints.append((1 + k, 2 + k, tuple(end)))
+        end = end - axis * 1.0
+    cfg = Configuration(RestoreJoints=True)
+    return protos, cfg, joints
+
+
+def c4_chain32_blowup(world: int, n_links: int = 32):
+    """The first C4 scene (round 1): 5 kg links hanging diagonally (pitch 0.3) from an anchor at z = 12 over a 15x15
+    ground.  With light links Joint.restore as written is an unstable feedback: the chains reach NaN within ~35
+    steps, in the reference semantics too.  Kept as a parity-only case (NaN = NaN through the blow-up)."""
     rng = SplitMix64(scene_seed(4, world))
     protos = [_ground(15.0, 15.0, 1.01)]
     top = (rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), 12.0)
     protos.append(P.createDefaultCube(0.2).With(Mass=P.INFINITE, UseGravity=False, Position=top))
     pitch = 0.3
-    # link long axis = local z rotated by `pitch` about y (reference YPR: pitch is about Y)
     R = P.from_yaw_pitch_roll(0.0, pitch, 0.0)
     axis = R[:, 2]
     joints = []

@@ -59,7 +59,7 @@ class BatchSimulator:
 
     def __init__(self, worlds: Sequence[Sequence[P.RigidBodyPrototype]], configuration: Optional[Configuration] = None,
                  joints: Optional[Sequence[Sequence[Tuple[int, int, Sequence[float]]]]] = None, device: int = -1,
-                 record_contacts: bool = False, exact_all_pairs: bool = False, _prebuilt=None):
+                 record_contacts: bool = False, exact_all_pairs: bool = False, _prebuilt=None, aabb_mode: int = 0):
         self.configuration = configuration or Configuration()
         # BroadPhaseCollisionDetectionKind.SpatialTree: the candidate ORDER is the persistent tree's (history dependent,
         # Q16); the library keeps one tree per world on the host and feeds the device the ordered list every step
@@ -73,7 +73,7 @@ class BatchSimulator:
         self._exact = exact_all_pairs
         self._device = device
         self._joints_spec = joints
-        self._native_cfg = to_native_config(self.configuration, record_contacts, exact_all_pairs)
+        self._native_cfg = to_native_config(self.configuration, record_contacts, exact_all_pairs, aabb_mode)
         self._create()
 
     # -- construction ---------------------------------------------------------------------------------

@@ -246,4 +246,9 @@ int hh_tree_candidates(void* p, const unsigned char* is_static, uint32_t* out, i
     for (int k = 0; k < (int)v.size() && k < cap; k++) out[k] = v[k];
     return (int)v.size();
 }
+// ps_sincos.h (shared by the device path and the oracle) on an array: tests/test_sincos_ulp.py holds it against libm
+void hh_sincos(int n, const double* x, double* s, double* c)
+{
+    for (int k = 0; k < n; k++) ps_sincos(x[k], &s[k], &c[k]);
+}
 }

@@ -1,0 +1,263 @@
+"""GPU tests added in round 2: parity at the size where each path is the DEFAULT one (full C2 batch, >= 4096 C3 worlds on
+the batch-wide path), the same worlds on one handle vs split over two (T10), stream ordering of
+ps_batch_step_async, the limits ps_batch_add_body must check before it changes anything, conservative SpatialTree
+extents (aabb_mode), input validation."""
+import os
+
+import numpy as np
+import pytest
+
+from common import (P, scenes, Configuration, to_native_config, same_bits, assert_state_bits)
+
+from physicssimulator_b200.simulator import BatchSimulator, Simulator
+
+pytestmark = pytest.mark.gpu
+
+
+def _built(fn, w0, n, **kw):
+    out, cfg = [], None
+    for w in range(w0, w0 + n):
+        r = fn(w, **kw)
+        cfg = r[1]
+        out.append(P.build_world(r[0], cfg.StepConfig.GravitationalAccelerationMagnitude, cfg.StepConfig.GravityDirection))
+    return out, cfg
+
+
+def _check_sample_against_oracle(sim, built, cfg, n_steps, sample, what):
+    from oracle.oracle import OracleWorld, batch_step
+    oracles = [OracleWorld(built[w], to_native_config(cfg)) for w in sample]
+    batch_step(oracles, n_steps, min(len(oracles), os.cpu_count() or 1))
+    for w, o in zip(sample, oracles):
+        got, ref = sim.batch.get_state(w, w + 1), o.get_state()
+        dyn = ~np.isinf(built[w]["mass"])
+        for k in ("pos", "vel", "rot", "ang_mom"):
+            assert same_bits(got[k][dyn], ref[k][dyn]), f"{what}: world {w} field {k} differs from the oracle after {n_steps} steps"
+
+
+def test_full_c2_batch_default_path_against_the_oracle():
+    """BASELINE configs[1] at full size (4096 worlds x 64 spheres), the path the library picks by itself, from creation;
+    16 worlds spread over the batch are held against the oracle bit for bit"""
+    built, cfg = _built(scenes.c2_spheres64, 0, 4096)
+    sim = BatchSimulator(None, cfg, device=0, _prebuilt=built)
+    n = 0
+    for chunk in (1, 39, 60):  # free fall, first landings, sphere-sphere contacts
+        sim.Step(chunk)
+        n += chunk
+    sample = sorted({(q * 4096) // 16 + (q * 37) % 200 for q in range(16)})
+    _check_sample_against_oracle(sim, built, cfg, n, sample, "full C2")
+    st = sim.Stats()
+    assert st["nan_worlds"] == 0 and st["contact_overflow"] == 0 and st["pairs_colliding"] > 4096
+    sim.close()
+
+
+def test_4096_c3_worlds_wide_path_by_default_against_the_oracle():
+    """4096 worlds x 128 mixed bodies = 524 288 bodies: above the size where the batch-wide path is the default (no
+    environment override here), many-CTA wide_levels / wide_scatter, 4096-world bucket tables; from creation through the
+    landing (box-box manifolds, friction); 16 worlds against the oracle bit for bit"""
+    assert "PS_B200_PATH" not in os.environ
+    built, cfg = _built(scenes.c3_mixed128, 0, 4096)
+    sim = BatchSimulator(None, cfg, device=0, _prebuilt=built)
+    assert sim.batch.schedule()["path"] == "wide"
+    n = 0
+    for chunk in (1, 29, 40):
+        sim.Step(chunk)
+        n += chunk
+    sample = sorted({(q * 4096) // 16 + (q * 53) % 250 for q in range(16)})
+    _check_sample_against_oracle(sim, built, cfg, n, sample, "4096 C3 worlds (wide)")
+    st = sim.Stats()
+    assert st["nan_worlds"] == 0 and st["contact_overflow"] == 0 and st["pairs_colliding"] > 4096
+    sim.close()
+
+
+def test_t10_same_worlds_on_one_handle_and_split_over_two():
+    """T10: 64 worlds stepped by one handle, and the same worlds as two shards of 32 on two handles (two
+    devices when the box has them): every body identical bit for bit, and the shard statistics sum to the whole"""
+    import torch
+    from physicssimulator_b200.sharding import shard_range, SUM_KEYS
+    built, cfg = _built(scenes.c3_mixed128, 100, 64, n_boxes=20, n_spheres=20)
+    one = BatchSimulator(None, cfg, device=0, _prebuilt=built)
+    ndev = torch.cuda.device_count()
+    shards = []
+    for r in range(2):
+        w0, w1 = shard_range(64, r, 2)
+        shards.append((w0, w1, BatchSimulator(None, cfg, device=(r if ndev >= 2 else 0), _prebuilt=built[w0:w1])))
+    for chunk in (1, 49, 70):
+        one.Step(chunk)
+        for _, _, s in shards:
+            s.Step(chunk)
+    whole = one.State()
+    off = one._offsets
+    for w0, w1, s in shards:
+        part = s.State()
+        for k in ("pos", "vel", "rot", "ang_mom"):
+            assert same_bits(part[k], whole[k][off[w0]:off[w1]]), f"T10: worlds [{w0},{w1}) field {k}"
+    tot, parts = one.Stats(), [s.Stats() for _, _, s in shards]
+    for k in SUM_KEYS:
+        assert tot[k] == sum(p[k] for p in parts), k
+    assert tot["max_penetration"] == max(p["max_penetration"] for p in parts)
+    one.close()
+    for _, _, s in shards:
+        s.close()
+
+
+@pytest.mark.parametrize("path", ["fused", "wide"])
+def test_step_async_on_a_foreign_stream_is_ordered_with_the_handle(monkeypatch, path):
+    """ps_batch_step_async launches on the caller's stream; get_state / apply_impulse / step on the handle's own stream
+    right after it (no synchronise in between) must see its result, and a later async step must see theirs"""
+    import torch
+    from oracle.oracle import OracleWorld
+    monkeypatch.setenv("PS_B200_PATH", path)
+    built, cfg = _built(scenes.c3_mixed128, 7, 6, n_boxes=16, n_spheres=16)
+    sim = BatchSimulator(None, cfg, device=0, _prebuilt=built)
+    oracles = [OracleWorld(b, to_native_config(cfg)) for b in built]
+    stream = torch.cuda.Stream()
+    J, offv = (3.0, -2.0, 5.0), (0.1, 0.0, -0.05)
+    for rnd in range(3):
+        sim.batch.step_async(25, stream.cuda_stream)
+        st = sim.batch.get_state()                      # handle's stream, no synchronise before
+        for o in oracles:
+            o.step(25)
+        for w, o in enumerate(oracles):
+            ref = o.get_state()
+            dyn = ~np.isinf(built[w]["mass"])
+            a, b = sim._offsets[w], sim._offsets[w + 1]
+            for k in ("pos", "vel", "rot"):
+                assert same_bits(st[k][a:b][dyn], ref[k][dyn]), f"async round {rnd} world {w} {k}"
+        sim.batch.step_async(3, stream.cuda_stream)
+        sim.ApplyImpulse(2, 5, J, offv)                 # handle's stream: must come after the 3 async steps
+        for o in oracles:
+            o.step(3)
+        oracles[2].apply_impulse(5, J, offv)
+    sim.batch.step_async(4, stream.cuda_stream)         # must come after the impulse
+    for o in oracles:
+        o.step(4)
+    sim.batch.synchronize()
+    st = sim.batch.get_state()
+    for w, o in enumerate(oracles):
+        ref = o.get_state()
+        dyn = ~np.isinf(built[w]["mass"])
+        a, b = sim._offsets[w], sim._offsets[w + 1]
+        for k in ("pos", "vel", "rot"):
+            assert same_bits(st[k][a:b][dyn], ref[k][dyn]), f"async tail world {w} {k}"
+    sim.close()
+
+
+def test_step_async_under_graph_capture():
+    """the fused path has no host round trip: a captured step replays; a SpatialTree-order batch refuses to be captured"""
+    import torch
+    built, cfg = _built(scenes.c2_spheres64, 0, 8)
+    sim = BatchSimulator(None, cfg, device=0, _prebuilt=built)
+    ref = BatchSimulator(None, cfg, device=0, _prebuilt=built)
+    sim.Step(30); ref.Step(30)
+    s = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        g.capture_begin()
+        sim.batch.step_async(2, s.cuda_stream)
+        g.capture_end()
+    torch.cuda.synchronize()
+    for _ in range(5):
+        g.replay()
+    torch.cuda.synchronize()
+    ref.Step(10)
+    assert_state_bits(ref.State(), sim.State(), "graph replay of the fused step")
+    sim.close(); ref.close()
+    protos, tcfg = scenes.stack_scene()
+    tree = BatchSimulator([protos], tcfg, device=0)
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        g2.capture_begin()
+        with pytest.raises(RuntimeError):
+            tree.batch.step_async(1, s.cuda_stream)
+        g2.capture_end()
+    tree.Step(3)
+    tree.close()
+
+
+def test_add_body_refuses_before_it_changes_anything():
+    """per-world size limit and (SpatialTree order) the tree's space are checked first: after the refusal the batch steps
+    on exactly as if the call had never been made (the handle used to be left half-built)"""
+    from oracle.oracle import OracleWorld
+    # 1) 1024 bodies is the limit of a world
+    protos = [P.createDefaultBox(400, 400, 1).With(Mass=P.INFINITE, UseGravity=False, Position=(0, 0, -0.5), Yaw=np.pi)]
+    for k in range(1023):
+        protos.append(P.createDefaultSphere(0.3).With(Position=(((k % 32) - 16) * 3.0, ((k // 32) - 16) * 3.0, 0.5), Mass=2.0))
+    small, _ = scenes.c2_spheres64(1, n_spheres=8)
+    sim = BatchSimulator([small, protos], Configuration(), device=0)
+    sim.Step(3)
+    before = sim.State()
+    with pytest.raises(ValueError):
+        sim.AddObject(1, P.createDefaultSphere(0.2).With(Position=(0, 0, 9.0)))
+    assert_state_bits(before, sim.State(), "state after a refused add_body")
+    sim.Step(2)
+    ok_id = sim.AddObject(0, P.createDefaultSphere(0.2).With(Position=(0, 0, 9.0)))  # the other world still takes one
+    assert ok_id == 9
+    sim.Step(2)
+    assert sim.Stats()["nan_worlds"] == 0
+    sim.close()
+    # 2) SpatialTree order: a body outside the tree's space
+    sp, cfg = scenes.stack_scene()
+    tc = cfg.BroadPhaseCollisionDetectionKind.SpatialTree
+    s2 = Simulator(sp, cfg, device=0)
+    o = OracleWorld(P.build_world(sp), to_native_config(cfg))
+    assert o.use_spatial_tree(tc.LeafCapacity, tc.MaxDepth, tc.SpaceBoundariesMin, tc.SpaceBoundariesMax) == 0
+    s2.Step(10); o.step(10)
+    with pytest.raises(ValueError):
+        s2.AddObject(P.createDefaultCube(0.5).With(Position=(500.0, 0.0, 3.0)))
+    s2.Step(30); o.step(30)
+    got, ref = s2._b.WorldState(0), o.get_state()
+    assert len(got["pos"]) == len(ref["pos"]) == len(sp)
+    for k in ("pos", "vel", "rot"):
+        assert same_bits(got[k], ref[k]), k
+    s2.Dispose()
+
+
+def test_spatial_tree_conservative_extents():
+    """ps_step_config.aabb_mode = 1: spheres enter the tree with side 2r instead of the reference's r (Q5); candidate
+    lists, contacts and states equal the oracle's tree run in the same mode"""
+    from oracle.oracle import OracleWorld
+    from physicssimulator_b200.configuration import BroadPhaseCollisionDetectionKind, SpatialTreeConfiguration
+    cfg = Configuration(BroadPhaseCollisionDetectionKind=BroadPhaseCollisionDetectionKind(SpatialTreeConfiguration(
+        LeafCapacity=3, MaxDepth=6, SpaceBoundariesMin=(-30.0, -30.0, -3.0), SpaceBoundariesMax=(30.0, 30.0, 30.0))))
+    tc = cfg.BroadPhaseCollisionDetectionKind.SpatialTree
+    worlds = [scenes.c3_mixed128(w, n_boxes=10, n_spheres=18)[0] for w in range(3)]
+    lists_differ = False
+    for mode in (0, 1):
+        sim = BatchSimulator(worlds, cfg, device=0, record_contacts=True, aabb_mode=mode)
+        oracles = []
+        for protos in worlds:
+            o = OracleWorld(P.build_world(protos), to_native_config(cfg))
+            assert o.use_spatial_tree(tc.LeafCapacity, tc.MaxDepth, tc.SpaceBoundariesMin, tc.SpaceBoundariesMax, mode) == 0
+            oracles.append(o)
+        for n in (1, 39, 40):
+            sim.Step(n)
+            for w, o in enumerate(oracles):
+                o.step(n)
+                assert np.array_equal(o.candidates(), sim.Candidates(w)), f"aabb_mode {mode}: candidate list of world {w}"
+                got, ref = sim.WorldState(w), o.get_state()
+                for k in ("pos", "vel", "rot"):
+                    assert same_bits(got[k], ref[k]), f"aabb_mode {mode} world {w} {k}"
+        if mode == 0:
+            first = [sim.Candidates(w).copy() for w in range(3)]
+        else:
+            lists_differ = any(len(first[w]) != len(sim.Candidates(w)) or not np.array_equal(first[w], sim.Candidates(w)) for w in range(3))
+        sim.close()
+    assert lists_differ, "the conservative extents should give longer candidate lists than the reference's r-sided boxes"
+
+
+def test_mass_and_static_inertia_are_validated():
+    protos, _ = scenes.stack_scene()
+    b = P.build_world(protos)
+    off = np.array([0, len(b["mass"])], dtype=np.int32)
+    from physicssimulator_b200 import _native
+    for field, idx, val in (("mass", 1, 0.0), ("mass", 1, -3.0), ("mass", 1, float("nan"))):
+        bad = {k: v.copy() for k, v in b.items()}
+        bad[field][idx] = val
+        with pytest.raises(ValueError):
+            _native.Batch(bad, off, to_native_config(Configuration()), device=0)
+    stat = int(np.flatnonzero(np.isinf(b["mass"]))[0])
+    bad = {k: v.copy() for k, v in b.items()}
+    bad["inertia_inv"][stat] = (0.0, 0.5, 0.0)
+    with pytest.raises(ValueError):
+        _native.Batch(bad, off, to_native_config(Configuration()), device=0)

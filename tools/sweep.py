@@ -15,7 +15,7 @@ ap.add_argument("--settle", type=int, default=200); ap.add_argument("--steps", t
 ap.add_argument("--variants", default="wide:2:16,fused:2:16", help="comma list of path:mscale:ncap[:tile]")
 ap.add_argument("--prof", action="store_true", help="PS_B200_WIDE_PROF for the wide variants (serialises)")
 a = ap.parse_args()
-built, cfg, joints = bench.build_worlds(a.workload, 0, a.worlds)
+built, cfg, joints = bench.build_worlds(a.workload, 0, a.worlds, min(16, os.cpu_count() or 1))
 sim = BatchSimulator(None, cfg, joints=joints, device=0, _prebuilt=built)
 sim.batch.step(a.settle)
 st = sim.batch.get_state()

@@ -10,7 +10,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c3"); ap.add_argument("--worlds", type=int, default=16384)
 ap.add_argument("--settle", type=int, default=200); ap.add_argument("--steps", type=int, default=5)
 a = ap.parse_args()
-built, cfg, joints = bench.build_worlds(a.workload, 0, a.worlds)
+built, cfg, joints = bench.build_worlds(a.workload, 0, a.worlds, min(16, os.cpu_count() or 1))
 os.environ.pop("PS_B200_WIDE_PROF", None)
 sim = BatchSimulator(None, cfg, joints=joints, device=0, _prebuilt=built)
 sim.batch.step(a.settle)
