@@ -95,6 +95,15 @@ struct Batch {
     unsigned* h_bucket = nullptr;  // pinned
     unsigned* d_tmp = nullptr;
     unsigned *d_surv = nullptr, *d_surv_cnt = nullptr;
+    int* d_nlev = nullptr;
+    // what the rounds of an earlier step held, read back asynchronously and never waited for: sizes the grids of the
+    // device-counted round kernels (ps_wide.cuh).  [0..kBuckets] bucket starts, then hit counts, then survivor counts
+    unsigned* h_est = nullptr;       // pinned
+    cudaEvent_t est_ready = nullptr;
+    bool est_pending = false, est_valid = false;
+    std::vector<unsigned> est;       // host copy the launches are sized from
+    int rounds_grid = 0;       // CTAs of the cooperative rounds kernel (all resident at once)
+    unsigned team_max = 0;     // box-box survivors per round up to which every survivor gets a team of 8 lanes
     unsigned long long* d_tmp_pen = nullptr;
     double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // PS_B200_WIDE_PROF: setup, integrate, ss, sb, bb, resolve, tail, fused
     long long prof_steps = 0, prof_rounds = 0;
@@ -269,8 +278,11 @@ void free_device(Batch* B)
     dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cost); dfree(B->d_perm); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
-    dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt);
+    dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev);
     if (B->h_bucket) { cudaFreeHost(B->h_bucket); B->h_bucket = nullptr; }
+    if (B->h_est) { cudaFreeHost(B->h_est); B->h_est = nullptr; }
+    if (B->est_ready) { cudaEventDestroy(B->est_ready); B->est_ready = nullptr; }
+    B->est_pending = B->est_valid = false;
     dfree(B->d_joff); dfree(B->d_ja); dfree(B->d_jb); dfree(B->d_jla); dfree(B->d_jlb); dfree(B->d_jlast);
     dfree(B->d_rec_pairs); dfree(B->d_rec_contacts); dfree(B->d_rec_counts); dfree(B->d_stats_sum);
     dfree(B->d_ext); dfree(B->d_cand); dfree(B->d_cand_off);
@@ -405,6 +417,21 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_surv, (size_t)B->entries_cap * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_surv_cnt, (psw::kWideMaxLevels + 2) * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_tmp_pen, nw * sizeof(unsigned long long)));
+        CK(cudaMalloc(&B->d_nlev, sizeof(int)));
+        CK(cudaMallocHost(&B->h_est, (size_t)(3 * psw::kBuckets + 8) * sizeof(unsigned)));
+        CK(cudaEventCreateWithFlags(&B->est_ready, cudaEventDisableTiming));
+        {   // the rounds of a step run in one cooperative launch whose CTAs must all be resident
+            int per_sm = 0, sms = 0, coop = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psw::wide_rounds, 128, 0));
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, B->device));
+            CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, B->device));
+            B->rounds_grid = per_sm * sms;
+            B->wide_device_rounds = coop != 0 && B->rounds_grid > 0;
+            if (const char* e = getenv("PS_B200_WIDE_HOST_ROUNDS")) { if (atoi(e) != 0) B->wide_device_rounds = false; }  // tuning/profiling: one launch per stage and round, driven by the host
+            // teams of 8 lanes where a thread per pair would leave lanes idle anyway: survivors x 8 <= resident lanes
+            B->team_max = (unsigned)((long long)B->rounds_grid * 128 / 8);
+            if (const char* e = getenv("PS_B200_TEAM_MAX")) B->team_max = (unsigned)std::max(0, atoi(e));  // tuning knob
+        }
         CK(cudaMemcpy(B->d_body_world, bw.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B->d_isstat, isstat.data(), nb, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B->d_isbox, isbox.data(), nb, cudaMemcpyHostToDevice));
@@ -713,8 +740,14 @@ int ps_batch_destroy(void* handle)
         cudaMemcpyFromSymbol(sm, psp::g_clk_sum, sizeof(sm)); cudaMemcpyFromSymbol(mx, psp::g_clk_max, sizeof(mx)); cudaMemcpyFromSymbol(cn, psp::g_clk_cnt, sizeof(cn));
         const char* nm[32] = {"bb: boxes+face axes", "bb: edge axes", "bb: face setup", "bb: clipping", "bb: contacts", "bb: edge contact", "", "", "bbkernel: loads", "bbkernel: detect_bb total", "", "",
                               "resolve: loads", "resolve: contact loads", "resolve: solve", "resolve: write-back + 2 integrations"};
+        static unsigned long long hs[32][32];
+        cudaMemcpyFromSymbol(hs, psp::g_clk_hist, sizeof(hs));
         for (int i = 0; i < 16; i++)
-            if (cn[i]) fprintf(stderr, "[clk] %-38s n=%9llu mean %8.0f max %8llu cycles\n", nm[i], cn[i], (double)sm[i] / cn[i], mx[i]);
+            if (cn[i]) {
+                fprintf(stderr, "[clk] %-38s n=%9llu mean %8.0f max %8llu cycles | log2 histogram:", nm[i], cn[i], (double)sm[i] / cn[i], mx[i]);
+                for (int b = 8; b < 24; b++) fprintf(stderr, " 2^%d:%llu", b, hs[i][b]);
+                fprintf(stderr, "\n");
+            }
     }
 #endif
     if (getenv("PS_B200_WIDE_PROF") && !B->prof_round.empty()) {
@@ -725,7 +758,7 @@ int ps_batch_destroy(void* handle)
         for (size_t r = 0; r * 6 < B->prof_round.size(); r++) {
             const float* q = &B->prof_round[r * 6];
             fprintf(stderr, "  round %3zu: %7.0f %7.0f %7.0f | %7u | %7u %7u %7u | %.3f %.3f %.3f\n", r + 1, q[0], q[1], q[2], sc[r + 1],
-                    hc[(r + 1) * 4], hc[(r + 1) * 4 + 1], hc[(r + 1) * 4 + 2], q[3], q[4], q[5]);
+                    hc[(r + 1) * 4], hc[(r + 1) * 4 + 1], hc[(r + 1) * 4 + 2] + hc[(r + 1) * 4 + 3], q[3], q[4], q[5]);
         }
     }
     free_device(B);
@@ -845,6 +878,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     a.stats = B->d_stats; a.tmp = B->d_tmp; a.tmp_pen = B->d_tmp_pen; a.surv = B->d_surv; a.surv_cnt = B->d_surv_cnt;
     a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
+    a.nlev = B->d_nlev; a.team_max = B->team_max;
     a.sp = ka.sp; a.margin_ncap = ka.margin_ncap;
     a.margin_scale = ka.margin_scale;
     const int nb = B->n_bodies, nw = B->n_worlds;
@@ -871,9 +905,63 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     wide_levels<<<gl, psw::kLvlThreads, psw::lvl_smem_bytes(B->max_n), st>>>(a);
     wide_bucket_scan<<<1, 32, 0, st>>>(a);
     wide_scatter<<<gl, psw::kLvlThreads, 0, st>>>(a);
+    B->launches += 8;
+    if (B->wide_device_rounds && !prof) {
+        // Device-counted rounds: no host round trip.  Grids are sized from the counts an earlier step left (if its
+        // read-back has arrived; the host never waits for it), every kernel reads the real counts on the device and walks
+        // its chunks with a grid stride; rounds beyond the ones enqueued here go to the cooperative catch-all.
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        CK(cudaStreamIsCapturing(st, &cap));
+        const bool capturing = cap != cudaStreamCaptureStatusNone;
+        if (B->est_pending && cudaEventQuery(B->est_ready) == cudaSuccess) {
+            B->est.assign(B->h_est, B->h_est + 3 * kBuckets + 8);
+            B->est_pending = false;
+            B->est_valid = true;
+        }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, B->device);
+        const unsigned dflt = (unsigned)sms * 8;   // no estimate yet: a grid that fills the device, strides do the rest
+        auto blocks = [&](unsigned n, unsigned per) { return (unsigned)(((unsigned long long)n * 9 / 8 + per - 1) / per) + 4u; };  // estimate + 12 %
+        int r_launch = 48;
+        const unsigned* hb = B->est_valid ? B->est.data() : nullptr;
+        const unsigned* hh = hb ? hb + kBuckets + 1 : nullptr;      // hit counts per (level, kind)
+        const unsigned* hs = hb ? hb + 2 * kBuckets + 1 : nullptr;  // survivors per level
+        if (hb) {
+            int top = 0;
+            for (int r = 1; r <= kWideMaxLevels; r++) if (hb[(r + 1) * 4] > hb[r * 4]) top = r;
+            r_launch = std::min(kWideMaxLevels, top + 3);
+        }
+        for (int r = 1; r <= r_launch; r++) {
+            unsigned g1 = dflt, g2 = dflt, g2t = dflt, g3 = dflt, ns_est = ~0u;
+            if (hb) {
+                const unsigned c0 = hb[r * 4 + 1] - hb[r * 4], c1 = hb[r * 4 + 2] - hb[r * 4 + 1], c2 = hb[r * 4 + 3] - hb[r * 4 + 2];
+                g1 = blocks(c0, 128) + blocks(c1, 128) + blocks(c2, 128);
+                ns_est = hs[r];
+                g2 = blocks(ns_est, 128); g2t = blocks(ns_est, 16);
+                g3 = blocks(hh[r * 4], 128) + blocks(hh[r * 4 + 1], 128) + blocks(hh[r * 4 + 2], 128) + blocks(hh[r * 4 + 3], 128);
+            }
+            wide_round_detect_d<<<g1, 128, 0, st>>>(a, r);
+            if (ns_est <= B->team_max) wide_round_bb_team_d<<<g2t, 128, 0, st>>>(a, r);
+            else wide_round_bb_d<<<g2, 128, 0, st>>>(a, r);
+            wide_round_resolve_d<<<g3, 128, 0, st>>>(a, r);
+        }
+        B->launches += 3 * (long long)r_launch;
+        if (r_launch < kWideMaxLevels) {
+            int r_begin = r_launch + 1;
+            void* args[] = {(void*)&a, (void*)&r_begin};
+            CK(cudaLaunchCooperativeKernel((const void*)wide_rounds, dim3((unsigned)B->rounds_grid), dim3(128), args, 0, st));
+            B->launches += 1;
+        }
+        if (!capturing && !B->est_pending) {  // this step's counts, for the grids of a later step
+            CK(cudaMemcpyAsync(B->h_est, B->d_bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(B->h_est + kBuckets + 1, B->d_hit_cnt, kBuckets * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(B->h_est + 2 * kBuckets + 1, B->d_surv_cnt, (kWideMaxLevels + 2) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(B->est_ready, st));
+            B->est_pending = true;
+        }
+    } else {
     CK(cudaMemcpyAsync(B->h_bucket, B->d_bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    B->launches += 8;
     lap(0);
     const unsigned* hb = B->h_bucket;
     const bool overflow = hb[kBuckets] > B->entries_cap;  // wide_scatter flagged every world: the fused kernel takes the step
@@ -894,6 +982,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
         if (prof) B->prof_round.push_back(lap_ms);
         B->prof_rounds++;
         B->launches += 2 + (c2 != 0);
+    }
     }
     wide_verify<<<gb, 128, 0, st>>>(a);
     wide_static_fold<<<gb, 128, 0, st>>>(a);

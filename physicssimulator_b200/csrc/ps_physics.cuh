@@ -16,11 +16,11 @@ using namespace psm;
 
 // -DPS_PROF_CLK: SM-cycle laps inside the pair routines of the batch-wide kernels (tools only; off in the product)
 #if defined(PS_PROF_CLK) && defined(__CUDACC__)
-__device__ unsigned long long g_clk_sum[32], g_clk_max[32], g_clk_cnt[32];
+__device__ unsigned long long g_clk_sum[32], g_clk_max[32], g_clk_cnt[32], g_clk_hist[32][32];  // hist: log2 buckets of the lap
 #endif
 #if defined(PS_PROF_CLK) && defined(__CUDA_ARCH__)
 #define PS_CLK_BEGIN(on) long long clk_t0_ = clock64(); const bool clk_on_ = (on);
-#define PS_CLK(i) { if (clk_on_) { long long t_ = clock64(); unsigned long long d_ = (unsigned long long)(t_ - clk_t0_); atomicAdd(&g_clk_sum[i], d_); atomicMax(&g_clk_max[i], d_); atomicAdd(&g_clk_cnt[i], 1ull); clk_t0_ = clock64(); } }
+#define PS_CLK(i) { if (clk_on_) { long long t_ = clock64(); unsigned long long d_ = (unsigned long long)(t_ - clk_t0_); atomicAdd(&g_clk_sum[i], d_); atomicMax(&g_clk_max[i], d_); atomicAdd(&g_clk_cnt[i], 1ull); atomicAdd(&g_clk_hist[i][d_ ? 63 - __clzll((long long)d_) : 0], 1ull); clk_t0_ = clock64(); } }
 #else
 #define PS_CLK_BEGIN(on)
 #define PS_CLK(i)
@@ -913,6 +913,171 @@ PSD void resolve_t(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact
             cp[k].accT1 = d.accT1;
         }
     }
+}
+
+// ----------------------------------------------------------------------------------------
+// The solve of the batch-wide kernels: resolve_t's operations on resolve_t's operands in resolve_t's order, arranged for
+// the latency of ONE thread (a round of the batch lasts as long as its slowest manifold; measured before: ~4 K cycles per
+// contact-iteration, i.e. ~400 FP64 operations at their full dependent latency — the zero tests of scale(), the clamps
+// and the division fall-backs cut the iteration into a dozen basic blocks, and the assembler interleaves independent
+// operations only inside a block):
+//   * ONE basic block per contact-iteration: every data-dependent decision is a select (scale_s, fmin_s/fmax_s, the
+//     "mN == 0 -> no impulse" case), no call, no branch;
+//   * the three divisions of a contact-iteration divide by the contact's constant masses: their reciprocals are refined
+//     once per contact (recip_seed) and a division is the last three operations of the device's own inline sequence
+//     (div_by_s); its acceptance test is folded into `ok` instead of branching to the complete IEEE routine;
+//   * a contact's solver data (incl. its normal) sits in one record; the NEXT contact's record is loaded while this one
+//     is being solved;
+//   * S1 = body 1 is a static body at rest (1/m = 0, I^-1 = 0, v = +0: the ground of every scene).  Its velocity at
+//     any point is +0 for as long as its angular-momentum accumulator and the contact offsets stay finite ((+-0) *
+//     finite sums to +0, and x - (+0) = x for every x), so vRel = velocity_at(body 2); its v stays +0
+//     (v + scale(0, P) = v); only the accumulator L1 (quirk Q2) still takes every impulse, in order.
+// Returns false when a quotient left the range the short division covers, or (S1) L1 / r1 left the finite range: the
+// results are then NOT the reference's, and the caller redoes the pair with the literal routine from the same inputs.
+// On the host (tests/host_harness) div_by_s is a plain division and the selects are the same selects.
+// ----------------------------------------------------------------------------------------
+struct CPFast {
+    d3 n, r1, r2;
+    double bias, mN, mT0, mT1, yN, yT0, yT1, accN, accT0, accT1;
+};
+PSD d3 scale_s(double s, d3 v)  // scale() with its zero case as selects
+{
+    const bool z = (s == 0.0);
+    const double px = s * v.x, py = s * v.y, pz = s * v.z;
+    return mk(z ? 0.0 : px, z ? 0.0 : py, z ? 0.0 : pz);
+}
+PSD double fmin_s(double a, double b)  // fmin_net
+{
+    const bool c = (a != b) && (a == a);
+    const double r1 = a < b ? a : b, r2 = is_neg(a) ? a : b;
+    return c ? r1 : r2;
+}
+PSD double fmax_s(double a, double b)  // fmax_net
+{
+    const double r1 = (a == a) ? (b < a ? a : b) : a, r2 = is_neg(b) ? a : b;
+    return (a != b) ? r1 : r2;
+}
+PSD double div_by_s(double a, double b, double y, bool& ok)
+{
+#if defined(__CUDA_ARCH__)
+    double q = __dmul_rn(a, y);
+    const double r = __fma_rn(-b, q, a);
+    q = __fma_rn(y, r, q);
+    // a numerator that is exactly zero (bodies at rest: a relative velocity of exactly 0 along a tangent) is the one
+    // frequent case the short sequence does not cover; its quotient is a zero with the sign of a xor the sign of b
+    // for every b that is neither zero nor NaN
+    const bool zero_num = (a == 0.0) && (b != 0.0) && (b == b);
+    const double qz = from_bits((bits_of(a) ^ bits_of(b)) & (int64_t)0x8000000000000000ULL);
+    ok = ok && (zero_num || div_ok(a, b, q));
+    return zero_num ? qz : q;
+#else
+    (void)y; (void)ok;
+    return a / b;
+#endif
+}
+struct SolveS {
+    d3 t0, t1;
+    double im1, im2, e1, mu, inf;  // e1 = -(min e + 1)
+    bool friction;                 // (uniform over the batch: the one branch of a contact-iteration)
+};
+template <bool S1>
+PSD void solve_contact_s(d3& v1, d3& L1, d3& v2, d3& L2, const m33& Iw1, const m33& Iw2, const SolveS& c, CPFast& d, bool& ok)
+{
+    const bool live = !(d.mN == 0.0);  // CollisionResponse.fs:45-49: mN = 0 -> no normal impulse
+    d3 vrel = v2 + cross(mulMV(Iw2, L2), d.r2);
+    if (!S1) vrel = vrel - (v1 + cross(mulMV(Iw1, L1), d.r1));
+    const double vn = dot(vrel, d.n);
+    bool okq = true;
+    const double j = div_by_s(c.e1 * vn + d.bias, d.mN, d.yN, okq);
+    ok = ok && (okq || !live);
+    const double old = d.accN;
+    const double acc = fmax_s(0.0, fmin_s(old + j, c.inf));
+    d3 P = scale_s(-(acc - old), d.n);
+    d.accN = live ? acc : old;
+    P = mk(live ? P.x : 0.0, live ? P.y : 0.0, live ? P.z : 0.0);
+    if (!S1) v1 = v1 + scale_s(c.im1, P);
+    L1 = L1 + cross(d.r1, P);
+    d3 nP = -P;
+    v2 = v2 + scale_s(c.im2, nP);
+    L2 = L2 + cross(d.r2, nP);
+    if (c.friction) {
+        d3 vr = v2 + cross(mulMV(Iw2, L2), d.r2);
+        if (!S1) vr = vr - (v1 + cross(mulMV(Iw1, L1), d.r1));
+        const double maxF = c.mu * d.accN;
+        const double j0 = div_by_s(dot(c.t0, vr), d.mT0, d.yT0, ok);
+        const double j1 = div_by_s(dot(c.t1, vr), d.mT1, d.yT1, ok);
+        const double o0 = d.accT0, o1 = d.accT1;
+        d.accT0 = fmax_s(-maxF, fmin_s(o0 + j0, maxF));
+        d.accT1 = fmax_s(-maxF, fmin_s(o1 + j1, maxF));
+        const d3 P0 = scale_s(d.accT0 - o0, c.t0);
+        const d3 P1 = scale_s(d.accT1 - o1, c.t1);
+        if (!S1) {
+            v1 = v1 + scale_s(c.im1, P0);
+            v1 = v1 + scale_s(c.im1, P1);
+        }
+        L1 = L1 + cross(d.r1, P0);
+        L1 = L1 + cross(d.r1, P1);
+        const d3 n0 = -P0, n1 = -P1;
+        v2 = v2 + scale_s(c.im2, n0);
+        L2 = L2 + cross(d.r2, n0);
+        v2 = v2 + scale_s(c.im2, n1);
+        L2 = L2 + cross(d.r2, n1);
+    }
+}
+PSD bool finite3(d3 v)
+{
+    const double big = 1.7976931348623157e308;
+    return fabs(v.x) <= big && fabs(v.y) <= big && fabs(v.z) <= big;
+}
+// FIX = 1: exactly one contact, no array
+template <int FIX, bool S1>
+PSD bool resolve_s(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* cs, int nc_in, CPFast* cp, const StepParams& sp)
+{
+    const int nc = FIX ? FIX : nc_in;
+    const m33 Iw1 = inertia_inv_world(b1.R, p1.iinv);
+    const m33 Iw2 = inertia_inv_world(b2.R, p2.iinv);
+    SolveS c;
+    tangents(cs[0].n, c.t0, c.t1);  // CollisionResponse.fs:80-81
+    {
+        const SolveConst sc = solve_const(p1, p2, sp);
+        c.im1 = p1.inv_mass; c.im2 = p2.inv_mass; c.e1 = -(sc.e + 1.0); c.mu = sc.mu; c.inf = sc.inf; c.friction = sc.friction != 0;
+    }
+    bool ok = true;
+    CPFast d;
+#pragma unroll 1
+    for (int k = 0; k < nc; k++) {
+        CPData q;
+        const Contact ck = cs[k];
+        contact_setup(b1, p1, Iw1, b2, p2, Iw2, ck, c.t0, c.t1, sp, q);
+        d.n = ck.n; d.r1 = q.r1; d.r2 = q.r2;
+        d.bias = q.bias; d.mN = q.mN; d.mT0 = q.mT0; d.mT1 = q.mT1;
+        d.yN = recip_seed(q.mN); d.yT0 = recip_seed(q.mT0); d.yT1 = recip_seed(q.mT1);
+        d.accN = 0.0; d.accT0 = 0.0; d.accT1 = 0.0;
+        if (S1) ok = ok && finite3(d.r1);
+        if (!FIX) cp[k] = d;
+    }
+    d3 v1 = b1.v, L1 = b1.L, v2 = b2.v, L2 = b2.L;
+    if (FIX == 1 || nc == 1) {  // d is the contact
+#pragma unroll 1
+        for (int it = 0; it < sp.iterations; it++) solve_contact_s<S1>(v1, L1, v2, L2, Iw1, Iw2, c, d, ok);
+    } else {  // d = cp[nc - 1], the first one in List.foldBack order
+#pragma unroll 1
+        for (int it = 0; it < sp.iterations; it++) {
+#pragma unroll 1
+            for (int k = nc - 1; k >= 0; k--) {
+                const CPFast nx = cp[k > 0 ? k - 1 : nc - 1];  // (nc >= 2: never this contact)
+                solve_contact_s<S1>(v1, L1, v2, L2, Iw1, Iw2, c, d, ok);
+                cp[k].accN = d.accN;
+                cp[k].accT0 = d.accT0;
+                cp[k].accT1 = d.accT1;
+                d = nx;
+            }
+        }
+    }
+    if (S1) ok = ok && finite3(L1);
+    if (!S1) b1.v = v1;
+    b1.L = L1; b2.v = v2; b2.L = L2;
+    return ok;
 }
 
 PSN void resolve(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* cs, int nc, CPData* cp,

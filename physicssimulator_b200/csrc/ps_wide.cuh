@@ -28,6 +28,7 @@
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
 #include "ps_step_kernel.cuh"
+#include "ps_coop.cuh"
 
 namespace psw {
 using namespace psk;
@@ -61,6 +62,8 @@ struct WArgs {
     Contact* cpool; unsigned cpool_cap; unsigned* cpool_cur;  // cursor per level
     unsigned* surv;              // [entries_cap] box-box pairs the quick test could not separate (listed from the bucket's start)
     unsigned* surv_cnt;          // per level
+    int* nlev;                   // [1] highest level that holds a pair (wide_bucket_scan); the device-driven rounds stop there
+    unsigned team_max;           // a round with at most this many box-box survivors gives every survivor a team of 8 lanes
     WorldStats* stats;
     unsigned* tmp;               // per world x 6 words of THIS step's wide pass: [0-1] tested | colliding | contacts packed in 64 bits (count_pair), [3] overflow, [4] ref_exc, [5] bodies that left their margin
     unsigned long long* tmp_pen; // per world: max |penetration| bits of this step
@@ -109,6 +112,7 @@ __global__ void wide_reset(WArgs a)
     if (t < kBuckets) a.bucket_cur[t] = 0;
     if (t < kBuckets) a.hit_cnt[t] = 0;
     if (t < kWideMaxLevels + 2) { a.cpool_cur[t] = 0; a.surv_cnt[t] = 0; }
+    if (t == 0) a.nlev[0] = 0;
     if (t < a.n_worlds) {
         a.wflags[t] = a.always_fused[t] ? WF_STATIC : 0u;
         a.K[t] = 0; a.maxl[t] = 0;
@@ -311,8 +315,10 @@ __global__ void wide_bucket_scan(WArgs a)  // one warp: kBuckets is ~4 K
     __syncwarp();
     unsigned base = 0;
     for (int l = 0; l < lane; l++) base += part[l];
-    for (int b = lane * per; b < (lane + 1) * per; b++) { unsigned t = a.bucket[b]; a.bucket[b] = base; base += t; }
+    int top = 0;
+    for (int b = lane * per; b < (lane + 1) * per; b++) { unsigned t = a.bucket[b]; a.bucket[b] = base; base += t; if (t) top = b / 4; }
     if (lane == 31) a.bucket[kBuckets] = base;
+    if (top) atomicMax(a.nlev, top);
 }
 __global__ void __launch_bounds__(kLvlThreads) wide_scatter(WArgs a)  // same CTA -> worlds map as wide_levels
 {
@@ -364,6 +370,45 @@ __device__ __forceinline__ void wide_bb_quick_body(const WArgs& a, unsigned firs
     a.surv[first + slot] = first + t;
 }
 
+// a colliding pair whose nc contacts sit at cpool[cf ..): entry, the round's hit list, max penetration, recording
+constexpr int kSmallManifold = 2;
+__device__ __forceinline__ void wide_publish_hit(const WArgs& a, Entry& e, unsigned ei, unsigned first, unsigned bucket_count, int level, int kind, int w,
+                                                 int i, int j, int nc, unsigned cf, double mp)
+{
+    e.knc |= (unsigned)nc << 24; e.cfirst = cf;
+    // Box pairs: a warp of the solve runs as long as its largest manifold, so manifolds of one or two contacts (edge
+    // contacts, corners) and larger ones (faces) are listed apart — small ones from the front of the bucket's region of
+    // the hit list, large ones from its back (the region holds every box pair of the round; hit_cnt[4 level + 3] counts
+    // the large ones).  ncu before: 16 of 32 threads per instruction in the solve.
+    if (kind == 2 && nc > kSmallManifold) {
+        const unsigned slot = agg_reserve(&a.hit_cnt[level * 4 + 3], 1u);
+        a.hitlist[first + bucket_count - 1u - slot] = ei;
+    } else {
+        const unsigned slot = agg_reserve(&a.hit_cnt[level * 4 + kind], 1u);
+        a.hitlist[first + slot] = ei;
+    }
+    const unsigned long long mpb = (unsigned long long)__double_as_longlong(mp);
+    if (mpb > __ldcg(&a.tmp_pen[w])) atomicMax(&a.tmp_pen[w], mpb);  // the maximum rarely moves
+    if (a.rec_pairs) {
+        int* cnt = a.rec_counts + 2 * w;
+        int slot2 = atomicAdd(&cnt[0], 1);
+        int f2 = atomicAdd(&cnt[1], nc);
+        if (slot2 < a.rec_pair_cap && f2 + nc <= a.rec_contact_cap) {
+            RecPair rp; rp.i = i; rp.j = j; rp.first = f2; rp.count = nc;
+            a.rec_pairs[(size_t)w * a.rec_pair_cap + slot2] = rp;
+            RecContact* out = a.rec_contacts + (size_t)w * a.rec_contact_cap + f2;
+            for (int k = 0; k < nc; k++) {
+                const Contact c = a.cpool[cf + k];
+                RecContact r;
+                r.n[0] = c.n.x; r.n[1] = c.n.y; r.n[2] = c.n.z;
+                r.p[0] = c.p.x; r.p[1] = c.p.y; r.p[2] = c.p.z;
+                r.pen = c.pen; r.feat = c.feat; r.pad = 0;
+                out[k] = r;
+            }
+        }
+    }
+}
+
 // narrow phase of one kind: thread per entry of bucket (level, kind)
 template <int KIND>
 __device__ __forceinline__ void wide_detect_body(const WArgs& a, unsigned first, unsigned count, int level, unsigned t)
@@ -408,41 +453,61 @@ __device__ __forceinline__ void wide_detect_body(const WArgs& a, unsigned first,
     unsigned cf = agg_reserve(&a.cpool_cur[level], (unsigned)nc);
     if (cf + (unsigned)nc > a.cpool_cap) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); return; }
     for (int k = 0; k < nc; k++) a.cpool[cf + k] = cs[k];
-    e.knc |= (unsigned)nc << 24; e.cfirst = cf;
-    unsigned slot = agg_reserve(&a.hit_cnt[level * 4 + KIND], 1u);
-    a.hitlist[first + slot] = ei;
     double mp = 0.0;
     for (int k = 0; k < nc; k++) mp = fmax(mp, fabs(cs[k].pen));
-    const unsigned long long mpb = (unsigned long long)__double_as_longlong(mp);
-    if (mpb > __ldcg(&a.tmp_pen[w])) atomicMax(&a.tmp_pen[w], mpb);  // the maximum rarely moves
-    if (a.rec_pairs) {
-        int* cnt = a.rec_counts + 2 * w;
-        int slot2 = atomicAdd(&cnt[0], 1);
-        int f2 = atomicAdd(&cnt[1], nc);
-        if (slot2 < a.rec_pair_cap && f2 + nc <= a.rec_contact_cap) {
-            RecPair rp; rp.i = i; rp.j = j; rp.first = f2; rp.count = nc;
-            a.rec_pairs[(size_t)w * a.rec_pair_cap + slot2] = rp;
-            RecContact* out = a.rec_contacts + (size_t)w * a.rec_contact_cap + f2;
-            for (int k = 0; k < nc; k++) {
-                RecContact r;
-                r.n[0] = cs[k].n.x; r.n[1] = cs[k].n.y; r.n[2] = cs[k].n.z;
-                r.p[0] = cs[k].p.x; r.p[1] = cs[k].p.y; r.p[2] = cs[k].p.z;
-                r.pen = cs[k].pen; r.feat = cs[k].feat; r.pad = 0;
-                out[k] = r;
-            }
-        }
-    }
+    wide_publish_hit(a, e, ei, first, count, level, KIND, w, i, j, nc, cf, mp);
+}
+
+// the literal box-box routine on ONE survivor entry (fallback of the team form); a real function
+static __device__ __noinline__ void wide_bb_literal(const WArgs& a, unsigned ei, unsigned first, unsigned c2, int level)
+{
+    Entry& e = a.entries[ei];
+    const int w = e.w, o = a.off[w];
+    const int i = e.ij & 0xffff, j = e.ij >> 16;
+    Par pi, pj; Dyn di, dj;
+    ld_par(a.par, 0, o + i, pi);
+    ld_par(a.par, 0, o + j, pj);
+    ld_dyn(a.pred, 0, o + i, di);
+    ld_dyn(a.pred, 0, o + j, dj);
+    PairScratch scb;
+    int err = 0, ovf = 0;
+    const int nc = detect_bb(di, pi, dj, pj, a.sp.eps, scb.cs, err, ovf, scb, false);
+    unsigned* tm = a.tmp + 6 * (size_t)w;
+    if (err) atomicAdd(&tm[4], 1u);
+    if (ovf) atomicAdd(&tm[3], 1u);
+    count_pair(a, w, nc > 0 ? 1u : 0u, nc > 0 ? (unsigned)nc : 0u);
+    if (nc <= 0) return;
+    unsigned cf = atomicAdd(&a.cpool_cur[level], (unsigned)nc);
+    if (cf + (unsigned)nc > a.cpool_cap) { atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY); return; }
+    double mp = 0.0;
+    for (int k = 0; k < nc; k++) { a.cpool[cf + k] = scb.cs[k]; mp = fmax(mp, fabs(scb.cs[k].pen)); }
+    wide_publish_hit(a, e, ei, first, c2, level, 2, w, i, j, nc, cf, mp);
+}
+
+// the literal solve of one pair from the predicted records (fallback of the straight-line solve; a real function)
+static __device__ __noinline__ void wide_resolve_literal(const WArgs& a, int gi, int gj, bool si, bool sj, const Contact* cs, int nc, Dyn& di, Dyn& dj)
+{
+    Par pi, pj;
+    ld_par(a.par, 0, gi, pi);
+    ld_par(a.par, 0, gj, pj);
+    ld_dyn(a.pred, 0, gi, di);
+    ld_dyn(a.pred, 0, gj, dj);
+    if (si) di.L = mk(0.0, 0.0, 0.0);
+    if (sj) dj.L = mk(0.0, 0.0, 0.0);
+    CPData cp[PS_MAX_CONTACTS];
+    resolve(di, pi, dj, pj, cs, nc, cp, a.sp);
 }
 
 // solve + write-back: thread per colliding pair of bucket (level, kind).  A body the solve changed is integrated
 // again right here (its next use — the next pair or the final sweep — needs exactly this predicted copy), which
 // keeps that work in a dense kernel; its margin only matters if a later near pair will test it.
 template <int KIND>
-__device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first, int level, unsigned t)
+__device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first, unsigned c2, int level, unsigned t)
 {
-    PS_CLK_BEGIN(KIND == 2 && level >= 3)
+    // KIND 3 = the large box manifolds, listed from the back of the box bucket's region (wide_publish_hit)
+    PS_CLK_BEGIN(KIND >= 2 && level >= 3)
     if (t >= a.hit_cnt[level * 4 + KIND]) return;
-    const Entry& e = a.entries[a.hitlist[first + t]];
+    const Entry& e = a.entries[a.hitlist[KIND == 3 ? first + c2 - 1u - t : first + t]];
     const int w = e.w;
     if (a.wflags[w]) return;
     const int o = a.off[w], N = a.off[w + 1] - o;
@@ -456,17 +521,24 @@ __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first
     if (si) di.L = mk(0.0, 0.0, 0.0);
     if (sj) dj.L = mk(0.0, 0.0, 0.0);
     PS_CLK(12)
-    if (KIND == 2) {
+    // the straight-line solve (ps_physics.cuh, resolve_s); S1: body i is a static body at rest — the ground pairs of round 1
+    const bool s1 = si && !sj && bits_of(di.v.x) == 0 && bits_of(di.v.y) == 0 && bits_of(di.v.z) == 0;
+    bool ok;
+    if (KIND >= 2) {
         const int nc = (int)(e.knc >> 24);
-        CPData cp[PS_MAX_CONTACTS];
+        CPFast cp[PS_MAX_CONTACTS];
         PS_CLK(13)
-        resolve_t<0>(di, pi, dj, pj, a.cpool + e.cfirst, nc, cp, a.sp);  // the manifold is read where the narrow phase left it
+        const Contact* cs = a.cpool + e.cfirst;  // the manifold is read where the narrow phase left it
+        ok = s1 ? resolve_s<0, true>(di, pi, dj, pj, cs, nc, cp, a.sp) : resolve_s<0, false>(di, pi, dj, pj, cs, nc, cp, a.sp);
         PS_CLK(14)
     } else {  // sphere pairs always carry exactly one contact
         Contact cs[1];
-        CPData cp[1];
         cs[0] = a.cpool[e.cfirst];
-        resolve_t<1>(di, pi, dj, pj, cs, 1, cp, a.sp);
+        ok = s1 ? resolve_s<1, true>(di, pi, dj, pj, cs, 1, nullptr, a.sp) : resolve_s<1, false>(di, pi, dj, pj, cs, 1, nullptr, a.sp);
+    }
+    if (!ok) {  // a quotient outside the short division's range, a non-finite accumulator: the literal routine, same inputs
+        PS_COLD_PATH;
+        wide_resolve_literal(a, o + i, o + j, si, sj, a.cpool + e.cfirst, (int)(e.knc >> 24), di, dj);
     }
     w_hit(a, w)[e.knc & 0xffffffu] = 1;
     double* Sw = a.S + (size_t)o * 3 * kMaxStatics;
@@ -517,9 +589,178 @@ __global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_resolve(WArgs a,
 {
     const unsigned b0 = (c0 + 127) / 128, b1 = (c1 + 127) / 128;
     const unsigned blk = blockIdx.x;
-    if (blk < b0) wide_resolve_body<0>(a, first, level, blk * 128 + threadIdx.x);
-    else if (blk < b0 + b1) wide_resolve_body<1>(a, first + c0, level, (blk - b0) * 128 + threadIdx.x);
-    else wide_resolve_body<2>(a, first + c0 + c1, level, (blk - b0 - b1) * 128 + threadIdx.x);
+    // (host-driven form: the box bucket's CTAs cover its small manifolds from the front and its large ones from the back)
+    if (blk < b0) wide_resolve_body<0>(a, first, 0u, level, blk * 128 + threadIdx.x);
+    else if (blk < b0 + b1) wide_resolve_body<1>(a, first + c0, 0u, level, (blk - b0) * 128 + threadIdx.x);
+    else {
+        wide_resolve_body<2>(a, first + c0 + c1, c2, level, (blk - b0 - b1) * 128 + threadIdx.x);
+        wide_resolve_body<3>(a, first + c0 + c1, c2, level, (blk - b0 - b1) * 128 + threadIdx.x);
+    }
+}
+
+// ---- box-box stage by TEAMS: 8 lanes per surviving pair (ps_coop.cuh) ----------------------------------------------
+// The 15 SAT axes, the clipped polygon's edges and the manifold's contacts are spread over the team's lanes; a warp holds
+// four pairs.  Used for the rounds whose survivors leave lanes idle anyway (a.team_max): there a pair's latency is the
+// round's duration.  The contacts go to the pool straight from the lanes that made them; lane 0 does the bookkeeping.
+__device__ __forceinline__ void wide_bb_team_body(const WArgs& a, unsigned first, unsigned c2, int level, unsigned slot, unsigned ns, psc::TeamScratch& ts)
+{
+    using namespace psc;
+    if (slot >= ns) return;  // (the whole team)
+    const pstm::Team<kTeam> tm;
+    const unsigned ei = a.surv[first + slot];
+    Entry& e = a.entries[ei];
+    const int w = e.w;
+    if (a.wflags[w]) return;
+    const int o = a.off[w];
+    const int i = e.ij & 0xffff, j = e.ij >> 16;
+    Par pi, pj; Dyn di, dj;
+    ld_par(a.par, 0, o + i, pi);
+    ld_par(a.par, 0, o + j, pj);
+    ld_dyn(a.pred, 0, o + i, di);
+    ld_dyn(a.pred, 0, o + j, dj);
+    TeamContacts out;
+    int err = 0;
+    bool lit = false;
+    int nc = detect_bb_team(tm, di, pi, dj, pj, a.sp.eps, ts, out, err, lit);
+    if (lit) {  // NaN penetrations / a clipped polygon of more than 16 vertices: lane 0 runs the literal routine
+        PS_COLD_PATH;
+        if (tm.lane == 0) wide_bb_literal(a, ei, first, c2, level);
+        return;
+    }
+    unsigned cf = 0;
+    if (tm.lane == 0) {
+        if (err) atomicAdd(&a.tmp[6 * (size_t)w + 4], 1u);
+        count_pair(a, w, nc > 0 ? 1u : 0u, nc > 0 ? (unsigned)nc : 0u);
+        if (nc > 0) cf = agg_reserve(&a.cpool_cur[level], (unsigned)nc);
+    }
+    if (nc <= 0) return;
+    cf = (unsigned)tm.shfl((int)cf, 0);
+    if (cf + (unsigned)nc > a.cpool_cap) {
+        if (tm.lane == 0) atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY);
+        return;
+    }
+    double mp = 0.0;
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+        if (out.ord[t] >= 0) {
+            a.cpool[cf + out.ord[t]] = out.c[t];
+            mp = fmax(mp, fabs(out.c[t].pen));
+        }
+#pragma unroll
+    for (int m = kTeam / 2; m; m >>= 1) mp = fmax(mp, tm.shfl_xor(mp, m));
+    tm.sync();  // the manifold is in the pool (lane 0 may read it back for the recording)
+    if (tm.lane == 0) wide_publish_hit(a, e, ei, first, c2, level, 2, w, i, j, nc, cf, mp);
+}
+
+// ---- device-counted round kernels ------------------------------------------------------------------------------------
+// One launch per stage and round as above, but the COUNTS are read from the bucket table in device memory and a CTA
+// walks its chunks with a grid stride: the host sizes the grid from what the same round held a step or two ago (an
+// estimate read back asynchronously, never waited for), and whatever the estimate, every pair of the round is
+// processed.  A round the step does not have costs an empty launch.  No host round trip inside a step.
+struct RoundCounts { unsigned first, c0, c1, c2; };
+__device__ __forceinline__ RoundCounts round_counts(const WArgs& a, int r)
+{
+    RoundCounts q;
+    q.first = a.bucket[r * 4];
+    q.c0 = a.bucket[r * 4 + 1] - q.first; q.c1 = a.bucket[r * 4 + 2] - a.bucket[r * 4 + 1]; q.c2 = a.bucket[r * 4 + 3] - a.bucket[r * 4 + 2];
+    return q;
+}
+__global__ void __launch_bounds__(128) wide_round_detect_d(WArgs a, int r)
+{
+    if (r > a.nlev[0] || a.bucket[kBuckets] > a.entries_cap) return;
+    const RoundCounts q = round_counts(a, r);
+    const unsigned b0 = (q.c0 + 127) / 128, b1 = (q.c1 + 127) / 128, b2 = (q.c2 + 127) / 128;
+    for (unsigned blk = blockIdx.x; blk < b0 + b1 + b2; blk += gridDim.x) {
+        if (blk < b0) wide_detect_body<0>(a, q.first, q.c0, r, blk * 128 + threadIdx.x);
+        else if (blk < b0 + b1) wide_detect_body<1>(a, q.first + q.c0, q.c1, r, (blk - b0) * 128 + threadIdx.x);
+        else wide_bb_quick_body(a, q.first + q.c0 + q.c1, q.c2, r, (blk - b0 - b1) * 128 + threadIdx.x);
+    }
+}
+__global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_bb_d(WArgs a, int r)
+{
+    if (r > a.nlev[0] || a.bucket[kBuckets] > a.entries_cap) return;
+    const RoundCounts q = round_counts(a, r);
+    const unsigned ns = a.surv_cnt[r];
+    for (unsigned blk = blockIdx.x; blk < (ns + 127) / 128; blk += gridDim.x)
+        wide_detect_body<2>(a, q.first + q.c0 + q.c1, q.c2, r, blk * 128 + threadIdx.x);
+}
+// the same stage by teams of 8 lanes (16 pairs per CTA), for rounds whose survivors leave lanes idle anyway
+__global__ void __launch_bounds__(128, 4) wide_round_bb_team_d(WArgs a, int r)
+{
+    __shared__ psc::TeamScratch ts_all[16];
+    if (r > a.nlev[0] || a.bucket[kBuckets] > a.entries_cap) return;
+    const RoundCounts q = round_counts(a, r);
+    const unsigned ns = a.surv_cnt[r];
+    for (unsigned blk = blockIdx.x; blk < (ns + 15) / 16; blk += gridDim.x)
+        wide_bb_team_body(a, q.first + q.c0 + q.c1, q.c2, r, blk * 16 + threadIdx.x / psc::kTeam, ns, ts_all[threadIdx.x / psc::kTeam]);
+}
+__global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_resolve_d(WArgs a, int r)
+{
+    if (r > a.nlev[0] || a.bucket[kBuckets] > a.entries_cap) return;
+    const RoundCounts q = round_counts(a, r);
+    const unsigned h0 = a.hit_cnt[r * 4], h1 = a.hit_cnt[r * 4 + 1], h2 = a.hit_cnt[r * 4 + 2], h3 = a.hit_cnt[r * 4 + 3];
+    const unsigned b0 = (h0 + 127) / 128, b1 = (h1 + 127) / 128, b2 = (h2 + 127) / 128, b3 = (h3 + 127) / 128;
+    for (unsigned blk = blockIdx.x; blk < b0 + b1 + b2 + b3; blk += gridDim.x) {  // the large manifolds first: they are the long ones
+        if (blk < b3) wide_resolve_body<3>(a, q.first + q.c0 + q.c1, q.c2, r, blk * 128 + threadIdx.x);
+        else if (blk < b3 + b2) wide_resolve_body<2>(a, q.first + q.c0 + q.c1, q.c2, r, (blk - b3) * 128 + threadIdx.x);
+        else if (blk < b3 + b2 + b1) wide_resolve_body<1>(a, q.first + q.c0, 0u, r, (blk - b3 - b2) * 128 + threadIdx.x);
+        else wide_resolve_body<0>(a, q.first, 0u, r, (blk - b3 - b2 - b1) * 128 + threadIdx.x);
+    }
+}
+
+// ---- the rounds from r_begin on in ONE cooperative launch -------------------------------------------------------------
+// The catch-all behind the per-round launches above: the host enqueues launches for as many rounds as the previous steps
+// had (plus a few); should this step have more, this kernel runs the rest — as many CTAs as are resident at once, a
+// round is three stages separated by grid barriers, counts from the bucket table.  (Measured as the ONLY form, C3: 22.9 ms
+// per step against 16.1 with a launch per stage: one register allocation for all stages, static chunk assignment.)
+// A stage hands chunk c (32 consecutive pairs of one kind, or 4 team pairs) to warp  c mod #warps  in an order that
+// walks the CTAs first (warp 0 of every CTA, then warp 1 ...): a small round spreads over all SMs.
+__global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_rounds(WArgs a, int r_begin)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ psc::TeamScratch ts_all[16];
+    if (a.bucket[kBuckets] > a.entries_cap) return;  // (grid-uniform) wide_scatter flagged every world: the fused kernel takes the step
+    const int nlev = a.nlev[0];
+    const unsigned lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
+    const unsigned gw = wic * gridDim.x + blockIdx.x, nw = gridDim.x * (blockDim.x >> 5);
+    for (int r = r_begin; r <= nlev; r++) {
+        const unsigned first = a.bucket[r * 4];
+        const unsigned c0 = a.bucket[r * 4 + 1] - first, c1 = a.bucket[r * 4 + 2] - a.bucket[r * 4 + 1], c2 = a.bucket[r * 4 + 3] - a.bucket[r * 4 + 2];
+        if (c0 + c1 + c2 == 0) continue;
+        {   // stage 1
+            const unsigned ch0 = (c0 + 31) / 32, ch1 = (c1 + 31) / 32, ch2 = (c2 + 31) / 32;
+            for (unsigned c = gw; c < ch0 + ch1 + ch2; c += nw) {
+                if (c < ch0) wide_detect_body<0>(a, first, c0, r, c * 32 + lane);
+                else if (c < ch0 + ch1) wide_detect_body<1>(a, first + c0, c1, r, (c - ch0) * 32 + lane);
+                else wide_bb_quick_body(a, first + c0 + c1, c2, r, (c - ch0 - ch1) * 32 + lane);
+            }
+        }
+        grid.sync();
+        if (c2) {  // stage 2
+            const unsigned ns = __ldcg(&a.surv_cnt[r]);
+            const unsigned fbb = first + c0 + c1;
+            if (ns <= a.team_max) {
+                for (unsigned c = gw; c < (ns + 3) / 4; c += nw)
+                    wide_bb_team_body(a, fbb, c2, r, c * 4 + lane / psc::kTeam, ns, ts_all[wic * 4 + lane / psc::kTeam]);
+            } else {
+                for (unsigned c = gw; c < (ns + 31) / 32; c += nw) wide_detect_body<2>(a, fbb, c2, r, c * 32 + lane);
+            }
+            grid.sync();
+        }
+        {   // stage 3
+            const unsigned h0 = __ldcg(&a.hit_cnt[r * 4]), h1 = __ldcg(&a.hit_cnt[r * 4 + 1]), h2 = __ldcg(&a.hit_cnt[r * 4 + 2]), h3 = __ldcg(&a.hit_cnt[r * 4 + 3]);
+            const unsigned ch0 = (h0 + 31) / 32, ch1 = (h1 + 31) / 32, ch2 = (h2 + 31) / 32, ch3 = (h3 + 31) / 32;
+            // the large manifolds first: they are the long ones
+            for (unsigned c = gw; c < ch0 + ch1 + ch2 + ch3; c += nw) {
+                if (c < ch3) wide_resolve_body<3>(a, first + c0 + c1, c2, r, c * 32 + lane);
+                else if (c < ch3 + ch2) wide_resolve_body<2>(a, first + c0 + c1, c2, r, (c - ch3) * 32 + lane);
+                else if (c < ch3 + ch2 + ch1) wide_resolve_body<1>(a, first + c0, 0u, r, (c - ch3 - ch2) * 32 + lane);
+                else wide_resolve_body<0>(a, first, 0u, r, (c - ch3 - ch2 - ch1) * 32 + lane);
+            }
+        }
+        grid.sync();
+    }
 }
 
 // ---- V: bodies that left their margin (thread per body).  A culled pair (b, x) stays impossible if the spheres grown

@@ -85,6 +85,7 @@ extern "C" {
 // planar layouts as in ps_step_kernel.cuh: dyn[f*N+b] (18 planes), par[f*N+b] (16 planes, plane 0 = 1/mass)
 // fast bit 0: the inlined/unrolled forms of the narrow phase (the ones the batch-wide kernels call)
 // fast bit 1: the straight-line (select-based) integration (integrate_a)
+// fast bit 3: the straight-line solve (resolve_s) instead of the literal one
 // fast bit 2: every box-box pair is ALSO run through the team form (ps_coop.cuh, 8 host threads per pair) and compared:
 //             counters[5] team runs, [6] literal requested, [7] mismatches
 void hh_world_step_v(int N, const double* par, double* dyn, const ps_step_config* cfg, int nsteps, int64_t* counters /*tested,hits,contacts,exc,overflow*/,
@@ -144,7 +145,16 @@ void hh_world_step_v(int N, const double* par, double* dyn, const ps_step_config
                         ncs++;
                     }
                 }
-                resolve(di, pi, dj, pj, cs, nc, sc.cp, sp);
+                if (fast & 8) {  // the straight-line solve of the batch-wide kernels (resolve_s), all its template forms
+                    CPFast cpf[PS_MAX_CONTACTS];
+                    const bool s1 = pi.is_static && !pj.is_static && bits_of(di.v.x) == 0 && bits_of(di.v.y) == 0 && bits_of(di.v.z) == 0;
+                    bool ok;
+                    const bool one = nc == 1 && (pi.shape == 0 || pj.shape == 0);
+                    if (one) ok = s1 ? resolve_s<1, true>(di, pi, dj, pj, cs, nc, cpf, sp) : resolve_s<1, false>(di, pi, dj, pj, cs, nc, cpf, sp);
+                    else ok = s1 ? resolve_s<0, true>(di, pi, dj, pj, cs, nc, cpf, sp) : resolve_s<0, false>(di, pi, dj, pj, cs, nc, cpf, sp);
+                    if (!ok) counters[6] += 1000000;  // (cannot happen on the host: plain divisions, finite states)
+                } else
+                    resolve(di, pi, dj, pj, cs, nc, sc.cp, sp);
                 st_dyn(dyn, N, i, di); pvalid[i] = 0;
                 st_dyn(dyn, N, j, dj); pvalid[j] = 0;
             }

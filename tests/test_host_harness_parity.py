@@ -22,8 +22,9 @@ def _run(protos, cfg, chunks, what):
         # both forms of the narrow phase: the compact one of the fused kernel and the inlined one of the wide kernels
         st, rec, cnt = harness_step(cur, nc, n)
         st_f, rec_f, cnt_f = harness_step(cur, nc, n, fast=True)
+        st_s, rec_s, cnt_s = harness_step(cur, nc, n, mode=1 | 2 | 8)  # + straight-line integration and straight-line solve
         done += n
-        for s_, r_, c_, form in ((st, rec, cnt, "compact"), (st_f, rec_f, cnt_f, "inlined")):
+        for s_, r_, c_, form in ((st, rec, cnt, "compact"), (st_f, rec_f, cnt_f, "inlined"), (st_s, rec_s, cnt_s, "straight-line")):
             assert_state_bits(o.get_state(), s_, f"{what}/{form} @ {done}")
             assert_contacts_equal(o.contacts(), r_, f"{what}/{form} @ {done}")
             assert c_["overflow"] == 0
