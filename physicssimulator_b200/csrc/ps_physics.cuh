@@ -1057,20 +1057,33 @@ PSD bool resolve_s(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact
         if (!FIX) cp[k] = d;
     }
     d3 v1 = b1.v, L1 = b1.L, v2 = b2.v, L2 = b2.L;
-    if (FIX == 1 || nc == 1) {  // d is the contact
+    if (FIX == 1) {  // d is the contact
 #pragma unroll 1
         for (int it = 0; it < sp.iterations; it++) solve_contact_s<S1>(v1, L1, v2, L2, Iw1, Iw2, c, d, ok);
-    } else {  // d = cp[nc - 1], the first one in List.foldBack order
+    } else {
+        // The lanes of a warp hold manifolds of different sizes.  The record array lives in local memory, which is
+        // interleaved across the lanes: the SAME index in every lane is one contiguous access, a different index per lane
+        // is 32 scattered sectors (ncu: 4.7 useful bytes per 32-byte sector with `k = nc - 1 ... 0` per lane).  So the
+        // walk is over kk = (largest manifold of the warp) - 1 ... 0 for everybody and a lane takes part while kk < nc:
+        // its own contacts still come up in List.foldBack order nc - 1 ... 0.
+#if defined(__CUDA_ARCH__)
+        const int ncmax = __reduce_max_sync(__activemask(), nc);
+#else
+        const int ncmax = nc;
+#endif
+        d = cp[ncmax - 1];
 #pragma unroll 1
         for (int it = 0; it < sp.iterations; it++) {
 #pragma unroll 1
-            for (int k = nc - 1; k >= 0; k--) {
-                const CPFast nx = cp[k > 0 ? k - 1 : nc - 1];  // (nc >= 2: never this contact)
-                solve_contact_s<S1>(v1, L1, v2, L2, Iw1, Iw2, c, d, ok);
-                cp[k].accN = d.accN;
-                cp[k].accT0 = d.accT0;
-                cp[k].accT1 = d.accT1;
-                d = nx;
+            for (int kk = ncmax - 1; kk >= 0; kk--) {
+                const CPFast nx = cp[kk > 0 ? kk - 1 : ncmax - 1];  // the next record of the walk, loaded while this one is solved
+                if (kk < nc) {
+                    solve_contact_s<S1>(v1, L1, v2, L2, Iw1, Iw2, c, d, ok);
+                    cp[kk].accN = d.accN;
+                    cp[kk].accT0 = d.accT0;
+                    cp[kk].accT1 = d.accT1;
+                }
+                if (ncmax > 1) d = nx;  // (a single record stays where it is, accumulators included: nx was read before the stores)
             }
         }
     }

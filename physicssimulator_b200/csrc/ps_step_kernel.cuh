@@ -40,6 +40,11 @@
 #pragma once
 #include "ps_physics.cuh"
 
+#ifndef PS_FUSED_STRAIGHT_SOLVE
+#define PS_FUSED_STRAIGHT_SOLVE 0  // 1: sphere pairs of the fused kernel take the straight-line solve (resolve_s).  Measured, ms per step: C2 4096 worlds
+                                   // 1.70 against 1.51, C4 7.89 against 7.76, C3 2048 worlds 8.68 against 8.49 — two more inlined copies of the solver in a
+                                   // kernel that lives on its instruction cache; the batch-wide kernels, one routine per launch, do profit from it
+#endif
 namespace psk {
 using namespace psp;
 
@@ -343,7 +348,20 @@ PSD void process_pair(Ctx& c, int i, int j, int near_k, bool fast)
         record_pair(c, i, j, cs, 1);
         if (si) di.L = mk(0.0, 0.0, 0.0);
         if (sj) dj.L = mk(0.0, 0.0, 0.0);
+#if PS_FUSED_STRAIGHT_SOLVE
+        {   // the straight-line solve (ps_physics.cuh, resolve_s); the literal one where a quotient leaves its range
+            const d3 v1 = di.v, L1 = di.L, v2 = dj.v, L2 = dj.L;
+            const bool s1 = pi.is_static && !pj.is_static && bits_of(v1.x) == 0 && bits_of(v1.y) == 0 && bits_of(v1.z) == 0;
+            const bool ok = s1 ? resolve_s<1, true>(di, pi, dj, pj, cs, 1, nullptr, c.a->sp) : resolve_s<1, false>(di, pi, dj, pj, cs, 1, nullptr, c.a->sp);
+            if (!ok) {
+                PS_COLD_PATH;
+                di.v = v1; di.L = L1; dj.v = v2; dj.L = L2;
+                resolve_t<1>(di, pi, dj, pj, cs, 1, cp, c.a->sp);
+            }
+        }
+#else
         resolve_t<1>(di, pi, dj, pj, cs, 1, cp, c.a->sp);
+#endif
     } else {
         PairScratch sc;  // clip buffers + manifold on the local stack (a per-thread global record was measured: slower)
         Contact* cs = sc.cs;

@@ -74,6 +74,9 @@ struct WArgs {
 };
 
 enum { WF_MARGIN = 1, WF_STATIC = 2, WF_CAPACITY = 4 };
+#ifndef PS_WIDE_DETECT_MINB
+#define PS_WIDE_DETECT_MINB 4  // stage 1 (sphere narrow phase + box-box quick test): 4 CTAs of 128 threads per SM, up to 128 registers
+#endif
 #ifndef PS_WIDE_MINB
 #define PS_WIDE_MINB 2  // resident 128-thread CTAs per SM the box-box and resolve kernels are compiled for (2 -> up to 255 registers)
 #endif
@@ -543,6 +546,8 @@ __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first
     w_hit(a, w)[e.knc & 0xffffffu] = 1;
     double* Sw = a.S + (size_t)o * 3 * kMaxStatics;
     double* cu = a.cull + (size_t)o * kCullF;
+    // (measured: the two re-integrations as one two-lane straight-line computation (integrate_2) spill in this kernel —
+    //  round 1 of C3 1.88 -> 2.01 ms, the other rounds unchanged — so they stay the literal routine, one after the other)
 #pragma unroll 1
     for (int side = 0; side < 2; side++) {
         const int b = side ? j : i, other = side ? i : j;
@@ -665,7 +670,7 @@ __device__ __forceinline__ RoundCounts round_counts(const WArgs& a, int r)
     q.c0 = a.bucket[r * 4 + 1] - q.first; q.c1 = a.bucket[r * 4 + 2] - a.bucket[r * 4 + 1]; q.c2 = a.bucket[r * 4 + 3] - a.bucket[r * 4 + 2];
     return q;
 }
-__global__ void __launch_bounds__(128) wide_round_detect_d(WArgs a, int r)
+__global__ void __launch_bounds__(128, PS_WIDE_DETECT_MINB) wide_round_detect_d(WArgs a, int r)
 {
     if (r > a.nlev[0] || a.bucket[kBuckets] > a.entries_cap) return;
     const RoundCounts q = round_counts(a, r);
@@ -685,7 +690,7 @@ __global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_bb_d(WArgs a, in
         wide_detect_body<2>(a, q.first + q.c0 + q.c1, q.c2, r, blk * 128 + threadIdx.x);
 }
 // the same stage by teams of 8 lanes (16 pairs per CTA), for rounds whose survivors leave lanes idle anyway
-__global__ void __launch_bounds__(128, 4) wide_round_bb_team_d(WArgs a, int r)
+__global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_bb_team_d(WArgs a, int r)
 {
     __shared__ psc::TeamScratch ts_all[16];
     if (r > a.nlev[0] || a.bucket[kBuckets] > a.entries_cap) return;
