@@ -437,6 +437,8 @@ int upload(Batch* B, bool with_state)
         CK(cudaMemcpy(B->d_isbox, isbox.data(), nb, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B->d_always_fused, af.data(), nw, cudaMemcpyHostToDevice));
         CK(cudaFuncSetAttribute(psw::wide_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psw::lvl_smem_bytes(B->max_n)));
+        CK(cudaFuncSetAttribute(psw::wide_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psw::predict_smem_bytes()));
+        CK(cudaFuncSetAttribute(psw::wide_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psw::kTileBytes));
         // the wide path pays one pass through memory per stage and ~5 launches per level: it wins when the batch
         // is large enough to fill the GPU per round
         B->wide = !B->cfg.exact_all_pairs && !(B->cfg.restore_joints && !B->joints.a.empty()) && B->n_bodies >= 500000;  // measured: C3 (2.1 M bodies) 24 vs 53 ms per step, C2 (0.27 M bodies) 3.9 vs 3.4 ms
@@ -898,7 +900,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     if (prof) B->prof_round.clear();
     const int greset = (std::max(nw, kBuckets + 1) + 255) / 256;
     wide_reset<<<greset, 256, 0, st>>>(a);
-    wide_predict<<<gb, 128, 0, st>>>(a);
+    wide_predict<<<gb, psw::kTile, psw::predict_smem_bytes(), st>>>(a);
     wide_near_count<<<gb, 128, 0, st>>>(a);
     wide_near_scan<<<gw, 64, 0, st>>>(a);
     wide_near_fill<<<gb, 128, 0, st>>>(a);
@@ -986,7 +988,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     }
     wide_verify<<<gb, 128, 0, st>>>(a);
     wide_static_fold<<<gb, 128, 0, st>>>(a);
-    wide_final<<<gb, 128, 0, st>>>(a);
+    wide_final<<<gb, psw::kTile, psw::kTileBytes, st>>>(a);
     wide_account<<<gw, 64, 0, st>>>(a);
     B->launches += 4;
     lap(6);

@@ -29,6 +29,7 @@
 #include <cooperative_groups/scan.h>
 #include "ps_step_kernel.cuh"
 #include "ps_coop.cuh"
+#include "ps_tma.cuh"
 
 namespace psw {
 using namespace psk;
@@ -126,37 +127,70 @@ __global__ void wide_reset(WArgs a)
     }
 }
 
-// ---- A: predicted copies + cull spheres (thread per body) -------------------------------------------------
-__global__ void __launch_bounds__(128) wide_predict(WArgs a)
+// ---- A: predicted copies + cull spheres (thread per body, tile of 128 bodies per CTA) ---------------------------------
+// The CTA's tile of the published state (128 x 144 B, contiguous) comes in with ONE bulk copy (ps_tma.cuh); it leaves
+// again as the working copy `cur` straight from shared memory — no thread touches it — and the predicted records are
+// written to a second shared tile and leave with one bulk copy as well.  Parameters are read with __ldg (128 B per
+// thread = one full line each; at a 128-byte stride a shared tile of them would put a quarter warp on one bank group).
+constexpr int kTile = 128;
+constexpr size_t kTileBytes = (size_t)kTile * kDynF * sizeof(double);  // 18 432 B
+__host__ __device__ inline size_t predict_smem_bytes() { return 2 * kTileBytes; }
+__global__ void __launch_bounds__(kTile) wide_predict(WArgs a)
 {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.n_bodies) return;
-    const int w = a.body_world[g], o = a.off[w], N = a.off[w + 1] - o, b = g - o;
-    Par p; Dyn cur, pr;
-    ld_par(a.par, 0, g, p);
-    ld_dyn(a.dyn, 0, g, cur);   // the published state is the step's input
-    st_dyn(a.cur, 0, g, cur);
-    integrate(cur, p, a.sp, pr);
-    st_dyn(a.pred, 0, g, pr);
-    a.pvalid[g] = 1; a.nhit[g] = 0;
-    if (p.is_static && !pose_fixed(cur, pr)) atomicOr(&a.wflags[w], (unsigned)WF_STATIC);
-    double* cu = a.cull + (size_t)o * kCullF;
-    cu[b] = pr.x.x; cu[N + b] = pr.x.y; cu[2 * N + b] = pr.x.z;
-    double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
-    double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
-    int np_ = a.nprev[g];
-    double n = (double)(np_ < a.margin_ncap ? np_ : a.margin_ncap) + 2.0;
-    const double mscale = a.margin_scale * (a.stats[w].boost > 0 ? 2.0 : 1.0);
-    double m = p.is_static ? 0.0 : mscale * (0.01 + n * a.sp.dt * (speed + n * acc * a.sp.dt + 0.5));
-    if (!(m == m)) m = 0.0;
-    double rs, rb;
-    if (p.shape == 0) { rs = p.dims[0]; rb = 1.7320508075688774 * p.dims[0]; }
-    else { double hx = 0.5 * p.dims[0], hy = 0.5 * p.dims[1], hz = 0.5 * p.dims[2]; rs = rb = sqrt(hx * hx + hy * hy + hz * hz); }
-    const double slack = 1.0 + 1e-6;
-    cu[3 * N + b] = rs * slack + 1e-9 + m;
-    cu[4 * N + b] = rb * slack + 1e-9 + m;
-    cu[5 * N + b] = m * m;
-    cu[6 * N + b] = 0.0;
+    extern __shared__ __align__(128) unsigned char tile_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    double* s_in = reinterpret_cast<double*>(tile_raw);
+    double* s_pred = reinterpret_cast<double*>(tile_raw + kTileBytes);
+    const int g0 = blockIdx.x * kTile;
+    const int n = min(kTile, a.n_bodies - g0);
+    const unsigned bytes = (unsigned)n * kDynF * (unsigned)sizeof(double);
+    if (threadIdx.x == 0) pst_tma::mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pst_tma::mbar_arrive_expect_tx(&bar, bytes);
+        pst_tma::bulk_g2s(s_in, a.dyn + (size_t)g0 * kDynF, bytes, &bar);   // the published state is the step's input
+    }
+    const int t = threadIdx.x, g = g0 + t;
+    Par p;
+    if (t < n) ld_par(a.par, 0, g, p);                                      // (overlaps the bulk copy)
+    pst_tma::mbar_wait(&bar, 0);
+    if (threadIdx.x == 0) {                                                  // working copy = the tile as it came in
+        pst_tma::bulk_s2g(a.cur + (size_t)g0 * kDynF, s_in, bytes);
+        pst_tma::bulk_commit();
+    }
+    if (t < n) {
+        const int w = a.body_world[g], o = a.off[w], N = a.off[w + 1] - o, b = g - o;
+        Dyn cur, pr;
+        ld_dyn(s_in, 0, t, cur);
+        integrate(cur, p, a.sp, pr);
+        st_dyn(s_pred, 0, t, pr);
+        a.pvalid[g] = 1; a.nhit[g] = 0;
+        if (p.is_static && !pose_fixed(cur, pr)) atomicOr(&a.wflags[w], (unsigned)WF_STATIC);
+        double* cu = a.cull + (size_t)o * kCullF;
+        cu[b] = pr.x.x; cu[N + b] = pr.x.y; cu[2 * N + b] = pr.x.z;
+        double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
+        double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);
+        int np_ = a.nprev[g];
+        double nn = (double)(np_ < a.margin_ncap ? np_ : a.margin_ncap) + 2.0;
+        const double mscale = a.margin_scale * (a.stats[w].boost > 0 ? 2.0 : 1.0);
+        double m = p.is_static ? 0.0 : mscale * (0.01 + nn * a.sp.dt * (speed + nn * acc * a.sp.dt + 0.5));
+        if (!(m == m)) m = 0.0;
+        double rs, rb;
+        if (p.shape == 0) { rs = p.dims[0]; rb = 1.7320508075688774 * p.dims[0]; }
+        else { double hx = 0.5 * p.dims[0], hy = 0.5 * p.dims[1], hz = 0.5 * p.dims[2]; rs = rb = sqrt(hx * hx + hy * hy + hz * hz); }
+        const double slack = 1.0 + 1e-6;
+        cu[3 * N + b] = rs * slack + 1e-9 + m;
+        cu[4 * N + b] = rb * slack + 1e-9 + m;
+        cu[5 * N + b] = m * m;
+        cu[6 * N + b] = 0.0;
+    }
+    pst_tma::fence_proxy_async();  // the predicted tile was written by threads: make it visible to the copy engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pst_tma::bulk_s2g(a.pred + (size_t)g0 * kDynF, s_pred, bytes);
+        pst_tma::bulk_commit();
+        pst_tma::bulk_wait_read();  // both stores have read their tiles: the CTA may go
+    }
 }
 
 // ---- B: near list ---------------------------------------------------------------------------------------
@@ -828,28 +862,58 @@ __global__ void __launch_bounds__(128) wide_static_fold(WArgs a)
     pb[15] = Lf.x; pb[16] = Lf.y; pb[17] = Lf.z;
 }
 
-// ---- F: final integration + publish (thread per body) ---------------------------------------------------------
-__global__ void __launch_bounds__(128) wide_final(WArgs a)
+// ---- F: publish (tile of 128 bodies per CTA) --------------------------------------------------------------------------
+// On this path every body's predicted copy is current when the rounds are over (the solve re-integrates what it changes),
+// so SimulatorState.update's integration (SimulatorState.fs:169-173) is that copy: the tile of `pred` comes in with one
+// bulk copy, is checked for non-finite values from shared memory, and goes out to the published state with one bulk copy.
+// Worlds the pass gave up on (wflags) keep their published state: their records are put back before the tile leaves.
+__global__ void __launch_bounds__(kTile) wide_final(WArgs a)
 {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.n_bodies) return;
-    const int w = a.body_world[g];
-    if (a.wflags[w]) return;  // the fused kernel redoes this world from the published state
-    Dyn out;
-    if (a.pvalid[g]) {
-        ld_dyn(a.pred, 0, g, out);
-    } else {
-        Par p; ld_par(a.par, 0, g, p);
-        Dyn cur; ld_dyn(a.cur, 0, g, cur);
-        integrate(cur, p, a.sp, out);
+    extern __shared__ __align__(128) unsigned char tile_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int any_flagged;
+    double* s_t = reinterpret_cast<double*>(tile_raw);
+    const int g0 = blockIdx.x * kTile;
+    const int n = min(kTile, a.n_bodies - g0);
+    const unsigned bytes = (unsigned)n * kDynF * (unsigned)sizeof(double);
+    if (threadIdx.x == 0) { pst_tma::mbar_init(&bar, 1); any_flagged = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pst_tma::mbar_arrive_expect_tx(&bar, bytes);
+        pst_tma::bulk_g2s(s_t, a.pred + (size_t)g0 * kDynF, bytes, &bar);
     }
-    st_dyn(a.dyn, 0, g, out);
-    a.nprev[g] = a.nhit[g];
-    bool bad = !(isfinite(out.x.x) && isfinite(out.x.y) && isfinite(out.x.z) && isfinite(out.v.x) && isfinite(out.v.y) && isfinite(out.v.z) &&
-                 isfinite(out.L.x) && isfinite(out.L.y) && isfinite(out.L.z));
-    for (int k = 0; k < 9; k++) bad = bad || !isfinite(out.R.a[k]);
-    if (bad) a.stats[w].nan_flag = 1;
-
+    const int t = threadIdx.x, g = g0 + t;
+    int w = 0;
+    bool flagged = false;
+    if (t < n) {
+        w = a.body_world[g];
+        flagged = a.wflags[w] != 0;  // the fused kernel redoes this world from the published state
+        if (flagged) any_flagged = 1;
+        else a.nprev[g] = a.nhit[g];
+    }
+    pst_tma::mbar_wait(&bar, 0);
+    if (t < n && !flagged) {
+        const double* q = s_t + (size_t)t * kDynF;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < kDynF; k++) bad = bad || !isfinite(q[k]);
+        if (bad) a.stats[w].nan_flag = 1;
+    }
+    __syncthreads();
+    if (any_flagged) {  // rare: keep the published records of flagged worlds
+        if (t < n && flagged) {
+            Dyn keep;
+            ld_dyn(a.dyn, 0, g, keep);
+            st_dyn(s_t, 0, t, keep);
+        }
+        pst_tma::fence_proxy_async();
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        pst_tma::bulk_s2g(a.dyn + (size_t)g0 * kDynF, s_t, bytes);
+        pst_tma::bulk_commit();
+        pst_tma::bulk_wait_read();
+    }
 }
 
 // account the worlds handed over to the fused kernel (thread per world)
