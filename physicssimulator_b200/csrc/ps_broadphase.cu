@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -126,9 +127,21 @@ __global__ void aabb_kernel(int n, const int* __restrict__ shape, const double* 
 
 // big/small split + bounds of the small bodies; reduced per CTA before touching the 7 global words
 // (1.1 M threads hammering them directly took milliseconds)
+__device__ __forceinline__ unsigned long long warp_min64(unsigned long long v)
+{
+    for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_max64(unsigned long long v)
+{
+    for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
 __global__ void classify_kernel(int n, Aabb* __restrict__ aabb, const double* __restrict__ side, GridInfo* gi,
                                 int* __restrict__ big_list, int big_cap)
 {
+    // reduced per warp with shuffles, then per CTA in shared memory, before touching the 7 global words
+    // (first version: every thread on the global words, milliseconds; second: every thread on 7 shared words, 37 us)
     __shared__ unsigned long long s_h, s_lo[3], s_hi[3];
     if (threadIdx.x == 0) {
         s_h = 0ull;
@@ -136,21 +149,26 @@ __global__ void classify_kernel(int n, Aabb* __restrict__ aabb, const double* __
     }
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long h = 0ull, lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0ull, 0ull, 0ull};
     if (i < n) {
         double mean = gi->sum_side / (double)n;
         double s = side[i];
-        bool big = !(s <= 8.0 * mean) || !isfinite(aabb[i].cen[0]) || !isfinite(aabb[i].cen[1]) || !isfinite(aabb[i].cen[2]);
+        const double c0 = aabb[i].cen[0], c1 = aabb[i].cen[1], c2 = aabb[i].cen[2];
+        bool big = !(s <= 8.0 * mean) || !isfinite(c0) || !isfinite(c1) || !isfinite(c2);
         if (big) {
             unsigned k = atomicAdd(&gi->n_big, 1u);
             if ((int)k < big_cap) big_list[k] = i;
             aabb[i].flags |= 2u;
         } else {
-            atomicMax(&s_h, ord(s));
-            for (int k = 0; k < 3; k++) {
-                atomicMin(&s_lo[k], ord(aabb[i].cen[k]));
-                atomicMax(&s_hi[k], ord(aabb[i].cen[k]));
-            }
+            h = ord(s);
+            lo[0] = hi[0] = ord(c0); lo[1] = hi[1] = ord(c1); lo[2] = hi[2] = ord(c2);
         }
+    }
+    h = warp_max64(h);
+    for (int k = 0; k < 3; k++) { lo[k] = warp_min64(lo[k]); hi[k] = warp_max64(hi[k]); }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&s_h, h);
+        for (int k = 0; k < 3; k++) { atomicMin(&s_lo[k], lo[k]); atomicMax(&s_hi[k], hi[k]); }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -191,17 +209,25 @@ __global__ void key_kernel(int n, const Aabb* __restrict__ aabb, Grid g, u64* __
     keys[i] = ((u64)cell << 32) | (unsigned)i;
 }
 
-// ---- exclusive scan of unsigned (block = 1024 threads x 2 items, recursive over block sums) --------------
-constexpr int SCAN_T = 1024;
-__global__ void scan_block_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ out, int n, unsigned* __restrict__ bsum)
+// ---- exclusive scan of unsigned (block = 512 threads x 8 items, recursive over block sums) ---------------------------
+constexpr int SCAN_T = 512, SCAN_I = 8, SCAN_TILE = SCAN_T * SCAN_I;
+__global__ void __launch_bounds__(SCAN_T) scan_block_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ out, int n, unsigned* __restrict__ bsum)
 {
     __shared__ unsigned wsum[32];
-    int base = blockIdx.x * SCAN_T * 2;
-    int i0 = base + 2 * threadIdx.x;
-    unsigned a = i0 < n ? in[i0] : 0u, b = i0 + 1 < n ? in[i0 + 1] : 0u;
-    unsigned v = a + b;
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned x = v;
+    const int base = blockIdx.x * SCAN_TILE + SCAN_I * threadIdx.x;
+    unsigned v[SCAN_I];
+    if (base + SCAN_I <= n && (((size_t)in & 15) == 0)) {
+        const uint4 a = *reinterpret_cast<const uint4*>(in + base), b = *reinterpret_cast<const uint4*>(in + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_I; k++) v[k] = base + k < n ? in[base + k] : 0u;
+    }
+    unsigned tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_I; k++) { unsigned t = v[k]; v[k] = tsum; tsum += t; }  // exclusive inside the thread
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned x = tsum;
     for (int o = 1; o < 32; o <<= 1) {
         unsigned y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
@@ -209,33 +235,48 @@ __global__ void scan_block_kernel(const unsigned* __restrict__ in, unsigned* __r
     if (lane == 31) wsum[wid] = x;
     __syncthreads();
     if (wid == 0) {
-        unsigned t = wsum[lane];
-        unsigned s = t;
+        unsigned t = lane < SCAN_T / 32 ? wsum[lane] : 0u;
+        unsigned sc = t;
         for (int o = 1; o < 32; o <<= 1) {
-            unsigned y = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += y;
+            unsigned y = __shfl_up_sync(0xffffffffu, sc, o);
+            if (lane >= o) sc += y;
         }
-        wsum[lane] = s - t;  // exclusive warp offsets
-        if (lane == 31 && bsum) bsum[blockIdx.x] = s;
+        if (lane < SCAN_T / 32) wsum[lane] = sc - t;  // exclusive warp offsets
+        if (lane == 31 && bsum) bsum[blockIdx.x] = sc;
     }
     __syncthreads();
-    unsigned excl = x - v + wsum[wid];
-    if (i0 < n) out[i0] = excl;
-    if (i0 + 1 < n) out[i0 + 1] = excl + a;
+    const unsigned excl = x - tsum + wsum[wid];
+    if (base + SCAN_I <= n && (((size_t)out & 15) == 0)) {
+        *reinterpret_cast<uint4*>(out + base) = make_uint4(v[0] + excl, v[1] + excl, v[2] + excl, v[3] + excl);
+        *reinterpret_cast<uint4*>(out + base + 4) = make_uint4(v[4] + excl, v[5] + excl, v[6] + excl, v[7] + excl);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_I; k++)
+            if (base + k < n) out[base + k] = v[k] + excl;
+    }
 }
-__global__ void scan_add_kernel(unsigned* __restrict__ out, int n, const unsigned* __restrict__ boff)
+__global__ void __launch_bounds__(SCAN_T) scan_add_kernel(unsigned* __restrict__ out, int n, const unsigned* __restrict__ boff)
 {
-    int i = blockIdx.x * SCAN_T * 2 + threadIdx.x;
-    unsigned o = boff[blockIdx.x];
-    if (i < n) out[i] += o;
-    if (i + SCAN_T < n) out[i + SCAN_T] += o;
+    const int base = blockIdx.x * SCAN_TILE + SCAN_I * threadIdx.x;
+    const unsigned o = boff[blockIdx.x];
+    if (o == 0u) return;
+    if (base + SCAN_I <= n && (((size_t)out & 15) == 0)) {
+        uint4 a = *reinterpret_cast<uint4*>(out + base), b = *reinterpret_cast<uint4*>(out + base + 4);
+        a.x += o; a.y += o; a.z += o; a.w += o; b.x += o; b.y += o; b.z += o; b.w += o;
+        *reinterpret_cast<uint4*>(out + base) = a;
+        *reinterpret_cast<uint4*>(out + base + 4) = b;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_I; k++)
+            if (base + k < n) out[base + k] += o;
+    }
 }
-int exclusive_scan(unsigned* d_in_out, int n, unsigned* scratch /* >= n/2048 + n/2048^2 + 4 */, cudaStream_t st)
+int exclusive_scan(unsigned* d_in_out, int n, unsigned* scratch /* >= n/4096 + n/4096^2 + 4 */, cudaStream_t st)
 {
-    int nb = (n + SCAN_T * 2 - 1) / (SCAN_T * 2);
+    int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     scan_block_kernel<<<nb, SCAN_T, 0, st>>>(d_in_out, d_in_out, n, nb > 1 ? scratch : nullptr);
     if (nb > 1) {
-        int rc = exclusive_scan(scratch, nb, scratch + nb, st);
+        int rc = exclusive_scan(scratch, nb, scratch + ((nb + 3) & ~3), st);
         if (rc) return rc;
         scan_add_kernel<<<nb, SCAN_T, 0, st>>>(d_in_out, n, scratch);
     }
@@ -396,6 +437,178 @@ __global__ void split_pairs_kernel(long long n, const u64* __restrict__ keys, in
     out[2 * k + 1] = (int)(keys[k] & 0xffffffffu);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast path (round 2): counting sort by cell, cell-sorted COPIES of the boxes, ownership by the lower id.
+//   cell_kernel      per body: cell id + its rank inside the cell (the histogram's atomicAdd returns it)
+//   scan             cell histogram -> start of every cell in the sorted order (no key sort, no cell_range pass)
+//   scatter_kernel   48-byte box + id + static flag + cell to their sorted slot: the neighbours of a body are then
+//                    CONTIGUOUS — the three cells x-1, x, x+1 of a grid row are one span of the sorted arrays, so a body
+//                    walks 9 spans instead of 27 cells and never gathers a box by id
+//   own_pairs_kernel thread per sorted body i: partners j > i among the 9 spans and among the big bodies, kept as a short
+//                    SORTED list in registers (insertion), count to cnt[i] — every pair has one owner, no atomics
+//   big_owner_*      a big body as the owner: ordered compaction over all j > g (flags + scan)
+//   scan cnt         -> first pair of every body in the output: the list comes out sorted by (i, j) by construction,
+//                    the pair keys are never sorted
+//   write_pairs_kernel
+// A body with more partners than the list holds (dense clusters) or more than a few big bodies send the call to the
+// general path below (global emission + radix sort of the pair keys); results are identical either way.
+// ---------------------------------------------------------------------------------------------------------------------
+struct SBox {  // 48 B, cell-sorted copy of an Aabb's numbers
+    double size[3], cen[3];
+};
+constexpr int kListCap = 12;
+constexpr int kMaxBigFast = 4;
+
+__global__ void cell_kernel(int n, const Aabb* __restrict__ aabb, Grid g, unsigned* __restrict__ cellid, unsigned* __restrict__ rank,
+                            unsigned* __restrict__ hist)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Aabb& a = aabb[i];
+    if (a.flags & 2u) { cellid[i] = 0xffffffffu; return; }
+    int ix = cell_coord(a.cen[0], g.org[0], g.inv_h, g.dim[0]);
+    int iy = cell_coord(a.cen[1], g.org[1], g.inv_h, g.dim[1]);
+    int iz = cell_coord(a.cen[2], g.org[2], g.inv_h, g.dim[2]);
+    unsigned c = (unsigned)ix + (unsigned)g.dim[0] * ((unsigned)iy + (unsigned)g.dim[1] * (unsigned)iz);
+    cellid[i] = c;
+    rank[i] = atomicAdd(&hist[c], 1u);
+}
+__global__ void scatter_kernel(int n, const Aabb* __restrict__ aabb, const unsigned* __restrict__ cellid, const unsigned* __restrict__ rank,
+                               const unsigned* __restrict__ cstart, SBox* __restrict__ sbox, unsigned* __restrict__ sid,
+                               unsigned* __restrict__ scell, unsigned char* __restrict__ sstat)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned c = cellid[i];
+    if (c == 0xffffffffu) return;
+    const unsigned pos = cstart[c] + rank[i];
+    const Aabb a = aabb[i];
+    double2* q = reinterpret_cast<double2*>(sbox + pos);  // 48-byte records: three 16-byte stores
+    q[0] = make_double2(a.size[0], a.size[1]);
+    q[1] = make_double2(a.size[2], a.cen[0]);
+    q[2] = make_double2(a.cen[1], a.cen[2]);
+    sid[pos] = (unsigned)i;
+    scell[pos] = c;
+    sstat[pos] = (unsigned char)(a.flags & 1u);
+}
+__device__ __forceinline__ bool overlap_s(const SBox& A, const SBox& B)
+{
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (!((A.size[k] + B.size[k]) / 2.0 > fabs(B.cen[k] - A.cen[k]))) return false;
+    return true;
+}
+constexpr int OP_T = 128;
+__global__ void __launch_bounds__(OP_T) own_pairs_kernel(int n_small, Grid g, const unsigned* __restrict__ cstart, const SBox* __restrict__ sbox,
+                                                         const unsigned* __restrict__ sid, const unsigned* __restrict__ scell,
+                                                         const unsigned char* __restrict__ sstat, const Aabb* __restrict__ aabb,
+                                                         const int* __restrict__ big_list, int n_big, unsigned* __restrict__ cnt,
+                                                         unsigned* __restrict__ lists, unsigned* __restrict__ overflow)
+{
+    __shared__ SBox bigb[kMaxBigFast];
+    __shared__ unsigned bigid[kMaxBigFast], bigst[kMaxBigFast];
+    if ((int)threadIdx.x < n_big) {
+        const Aabb a = aabb[big_list[threadIdx.x]];
+        for (int k = 0; k < 3; k++) { bigb[threadIdx.x].size[k] = a.size[k]; bigb[threadIdx.x].cen[k] = a.cen[k]; }
+        bigid[threadIdx.x] = (unsigned)big_list[threadIdx.x];
+        bigst[threadIdx.x] = a.flags & 1u;
+    }
+    __syncthreads();
+    const int s = blockIdx.x * OP_T + threadIdx.x;
+    if (s >= n_small) return;
+    const SBox A = sbox[s];
+    const unsigned i = sid[s], c = scell[s], ast = sstat[s];
+    const int ix = (int)(c % (unsigned)g.dim[0]), iy = (int)((c / (unsigned)g.dim[0]) % (unsigned)g.dim[1]), iz = (int)(c / ((unsigned)g.dim[0] * (unsigned)g.dim[1]));
+    unsigned list[kListCap];
+    int m = 0;
+    bool over = false;
+    auto add = [&](unsigned j) {  // sorted insertion; partners are few
+        if (m == kListCap) { over = true; return; }
+        int q = m++;
+#pragma unroll 1
+        while (q > 0 && list[q - 1] > j) { list[q] = list[q - 1]; q--; }
+        list[q] = j;
+    };
+    const int x0 = max(ix - 1, 0), x1 = min(ix + 1, g.dim[0] - 1);
+#pragma unroll 1
+    for (int dz = -1; dz <= 1; dz++) {
+        const int z = iz + dz;
+        if (z < 0 || z >= g.dim[2]) continue;
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; dy++) {
+            const int y = iy + dy;
+            if (y < 0 || y >= g.dim[1]) continue;
+            const unsigned row = (unsigned)g.dim[0] * ((unsigned)y + (unsigned)g.dim[1] * (unsigned)z);
+            const unsigned b = cstart[row + (unsigned)x0], e = cstart[row + (unsigned)x1 + 1u];  // one span: cells x0..x1 of the row
+#pragma unroll 1
+            for (unsigned t = b; t < e; t++) {
+                const unsigned j = sid[t];
+                if (j <= i) continue;  // the lower id owns the pair
+                if (ast & sstat[t]) continue;  // static-static (canIntersect)
+                if (overlap_s(A, sbox[t])) add(j);
+            }
+        }
+    }
+    for (int q = 0; q < n_big; q++) {
+        const unsigned gidx = bigid[q];
+        if (gidx <= i || (ast & bigst[q])) continue;
+        if (overlap_s(A, bigb[q])) add(gidx);
+    }
+    cnt[i] = (unsigned)m;
+    if (over) atomicOr(overflow, 1u);
+    unsigned* L = lists + (size_t)i * kListCap;
+    for (int q = 0; q < m; q++) L[q] = list[q];
+}
+// a big body g as the owner: flag of every j > g that overlaps it (1 / 0), to be scanned into ordered slots
+__global__ void big_owner_flag_kernel(int n, int gidx, const Aabb* __restrict__ aabb, unsigned* __restrict__ flags)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    unsigned f = 0;
+    if (j > gidx) {
+        const Aabb& G = aabb[gidx];
+        const Aabb& B = aabb[j];
+        if (!(G.flags & B.flags & 1u) && overlap(G, B)) f = 1u;
+    }
+    flags[j] = f;
+}
+// cnt[g] = total of the scanned flags (slot of the last body + its own flag)
+__global__ void big_owner_count_kernel(int n, int gidx, const Aabb* __restrict__ aabb, const unsigned* __restrict__ slots, unsigned* __restrict__ cnt)
+{
+    const int j = n - 1;
+    unsigned f = 0;
+    if (j > gidx) {
+        const Aabb& G = aabb[gidx];
+        const Aabb& B = aabb[j];
+        if (!(G.flags & B.flags & 1u) && overlap(G, B)) f = 1u;
+    }
+    cnt[gidx] = slots[j] + f;
+}
+__global__ void big_owner_write_kernel(int n, int gidx, const Aabb* __restrict__ aabb, const unsigned* __restrict__ slots,
+                                       const unsigned* __restrict__ off, int* __restrict__ out, long long cap)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || j <= gidx) return;
+    const Aabb& G = aabb[gidx];
+    const Aabb& B = aabb[j];
+    if ((G.flags & B.flags & 1u) || !overlap(G, B)) return;
+    const long long k = (long long)off[gidx] + slots[j];
+    if (k < cap) { out[2 * k] = gidx; out[2 * k + 1] = j; }
+}
+__global__ void write_pairs_kernel(int n, const Aabb* __restrict__ aabb, const unsigned* __restrict__ cnt, const unsigned* __restrict__ off,
+                                   const unsigned* __restrict__ lists, int* __restrict__ out, long long cap)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (aabb[i].flags & 2u) return;  // big owners write their own
+    const unsigned m = cnt[i];
+    if (!m) return;
+    const unsigned* L = lists + (size_t)i * kListCap;
+    long long k = off[i];
+    for (unsigned q = 0; q < m && q < (unsigned)kListCap; q++, k++)
+        if (k < cap) { out[2 * k] = i; out[2 * k + 1] = (int)L[q]; }
+}
+
 template <class T>
 struct DBuf {
     T* p = nullptr;
@@ -425,6 +638,9 @@ extern "C" int ps_broadphase_pairs(int32_t n, const int32_t* shape, const double
     DBuf<u64> d_k0, d_k1, d_p0, d_p1;
     DBuf<unsigned> d_hist, d_scr, d_cs, d_ce;
     DBuf<unsigned long long> d_count;
+    DBuf<unsigned> d_cellid, d_rank, d_sid, d_scell, d_cnt, d_off, d_lists, d_flags, d_over;
+    DBuf<SBox> d_sbox;
+    DBuf<unsigned char> d_sstat;
     const int big_cap = 4096;
     long long cap = std::max<long long>(pair_capacity, 1);
     BCK(d_shape.alloc(n)); BCK(d_dims.alloc(3 * (size_t)n)); BCK(d_mass.alloc(n)); BCK(d_pos.alloc(3 * (size_t)n));
@@ -433,11 +649,14 @@ extern "C" int ps_broadphase_pairs(int32_t n, const int32_t* shape, const double
     long long nsort = std::max<long long>(n, cap);
     int nblocks_max = (int)((nsort + RS_TILE - 1) / RS_TILE);
     BCK(d_hist.alloc(256 * (size_t)nblocks_max));
-    BCK(d_scr.alloc((size_t)(256 * (size_t)nblocks_max) / (SCAN_T * 2) + 4096));
+    BCK(d_scr.alloc((size_t)(256 * (size_t)nblocks_max) / SCAN_TILE + 67108864u / SCAN_TILE + 8192));
     // cell tables for the largest grid the sizing loop below may pick, and the output: no allocation inside the timed region
     const size_t max_cells = 67108864u;
-    BCK(d_cs.alloc(max_cells + 1)); BCK(d_ce.alloc(max_cells + 1));
+    BCK(d_cs.alloc(max_cells + 2)); BCK(d_ce.alloc(max_cells + 1));
     BCK(d_out.alloc(2 * (size_t)cap));
+    BCK(d_cellid.alloc(n)); BCK(d_rank.alloc(n)); BCK(d_sid.alloc(n)); BCK(d_scell.alloc(n)); BCK(d_sstat.alloc(n)); BCK(d_sbox.alloc(n));
+    BCK(d_cnt.alloc((size_t)n + 1)); BCK(d_off.alloc((size_t)n + 1)); BCK(d_lists.alloc((size_t)n * kListCap));
+    BCK(d_flags.alloc((size_t)n * kMaxBigFast)); BCK(d_over.alloc(1));
     BCK(cudaMemcpy(d_shape.p, shape, n * sizeof(int), cudaMemcpyHostToDevice));
     BCK(cudaMemcpy(d_dims.p, dims, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     BCK(cudaMemcpy(d_mass.p, mass, n * sizeof(double), cudaMemcpyHostToDevice));
@@ -456,7 +675,9 @@ extern "C" int ps_broadphase_pairs(int32_t n, const int32_t* shape, const double
     int nb = (n + 255) / 256;
     aabb_kernel<<<nb, 256, 0, st>>>(n, d_shape.p, d_dims.p, d_mass.p, d_pos.p, d_rot.p, aabb_mode, d_aabb.p, d_side.p, d_gi.p);
     classify_kernel<<<nb, 256, 0, st>>>(n, d_aabb.p, d_side.p, d_gi.p, d_big.p, big_cap);
+    int big_head[kMaxBigFast] = {0, 0, 0, 0};  // (the first few big ids travel with the grid numbers: one host round trip)
     BCK(cudaMemcpyAsync(&gi, d_gi.p, sizeof gi, cudaMemcpyDeviceToHost, st));
+    BCK(cudaMemcpyAsync(big_head, d_big.p, sizeof big_head, cudaMemcpyDeviceToHost, st));
     BCK(cudaStreamSynchronize(st));
     if ((int)gi.n_big > big_cap) return PS_ERR_CAPACITY;
     int n_small = n - (int)gi.n_big;
@@ -480,6 +701,51 @@ extern "C" int ps_broadphase_pairs(int32_t n, const int32_t* shape, const double
     } else {
         g.dim[0] = g.dim[1] = g.dim[2] = 1; g.ncells = 1; g.inv_h = 1.0;
     }
+    // ---- fast path: counting sort by cell, owned pair lists, output sorted by construction (see the kernels) ----------
+    bool done = false;
+    unsigned long long cnt = 0;
+    if ((int)gi.n_big <= kMaxBigFast && !getenv("PS_B200_BROADPHASE_GENERAL")) {
+        const int nbig = (int)gi.n_big;
+        BCK(cudaMemsetAsync(d_cs.p, 0, ((size_t)g.ncells + 2) * sizeof(unsigned), st));
+        BCK(cudaMemsetAsync(d_cnt.p, 0, ((size_t)n + 1) * sizeof(unsigned), st));
+        BCK(cudaMemsetAsync(d_over.p, 0, sizeof(unsigned), st));
+        if (n_small > 0) {
+            cell_kernel<<<nb, 256, 0, st>>>(n, d_aabb.p, g, d_cellid.p, d_rank.p, d_cs.p);
+            if (exclusive_scan(d_cs.p, (int)g.ncells + 1, d_scr.p, st)) return PS_ERR_CUDA;   // d_cs: start of every cell; [ncells] = n_small
+            scatter_kernel<<<nb, 256, 0, st>>>(n, d_aabb.p, d_cellid.p, d_rank.p, d_cs.p, d_sbox.p, d_sid.p, d_scell.p, d_sstat.p);
+            own_pairs_kernel<<<(n_small + OP_T - 1) / OP_T, OP_T, 0, st>>>(n_small, g, d_cs.p, d_sbox.p, d_sid.p, d_scell.p, d_sstat.p, d_aabb.p, d_big.p, nbig,
+                                                                            d_cnt.p, d_lists.p, d_over.p);
+        }
+        for (int q = 0; q < nbig; q++) {  // the big bodies as owners: ordered slots of their partners j > g
+            unsigned* fl = d_flags.p + (size_t)q * n;
+            big_owner_flag_kernel<<<nb, 256, 0, st>>>(n, big_head[q], d_aabb.p, fl);
+            if (exclusive_scan(fl, n, d_scr.p, st)) return PS_ERR_CUDA;
+            big_owner_count_kernel<<<1, 1, 0, st>>>(n, big_head[q], d_aabb.p, fl, d_cnt.p);
+        }
+        BCK(cudaMemcpyAsync(d_off.p, d_cnt.p, ((size_t)n + 1) * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+        if (exclusive_scan(d_off.p, n + 1, d_scr.p, st)) return PS_ERR_CUDA;                   // first pair of every body; [n] = number of pairs
+        unsigned tot_over[2] = {0, 0};
+        BCK(cudaMemcpyAsync(&tot_over[0], d_off.p + n, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        BCK(cudaMemcpyAsync(&tot_over[1], d_over.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        BCK(cudaStreamSynchronize(st));
+        if (!tot_over[1]) {
+            cnt = tot_over[0];
+            *n_pairs = (int64_t)cnt;
+            if ((long long)cnt > pair_capacity) {
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+                return PS_ERR_CAPACITY;
+            }
+            if (cnt > 0) {
+                write_pairs_kernel<<<nb, 256, 0, st>>>(n, d_aabb.p, d_cnt.p, d_off.p, d_lists.p, d_out.p, cap);
+                for (int q = 0; q < nbig; q++)
+                    big_owner_write_kernel<<<nb, 256, 0, st>>>(n, big_head[q], d_aabb.p, d_flags.p + (size_t)q * n, d_off.p, d_out.p, cap);
+            }
+            done = true;
+        }
+    }
+    if (!done) {
+    // ---- general path: any number of big bodies, any cluster density ---------------------------------------------------
+    BCK(cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), st));
     BCK(cudaMemsetAsync(d_cs.p, 0, ((size_t)g.ncells + 1) * sizeof(unsigned), st));
     BCK(cudaMemsetAsync(d_ce.p, 0, ((size_t)g.ncells + 1) * sizeof(unsigned), st));
     key_kernel<<<nb, 256, 0, st>>>(n, d_aabb.p, g, d_k0.p);
@@ -497,7 +763,6 @@ extern "C" int ps_broadphase_pairs(int32_t n, const int32_t* shape, const double
         BCK(cudaStreamSynchronize(st));
         for (int gidx : big) big_pair_kernel<<<nb, 256, 0, st>>>(n, gidx, d_aabb.p, d_p0.p, d_count.p, cap);
     }
-    unsigned long long cnt = 0;
     BCK(cudaMemcpyAsync(&cnt, d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
     BCK(cudaStreamSynchronize(st));
     *n_pairs = (int64_t)cnt;
@@ -515,6 +780,7 @@ extern "C" int ps_broadphase_pairs(int32_t n, const int32_t* shape, const double
     if (cnt > 0) {
         split_pairs_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((long long)cnt, pa, d_out.p);
     }
+    }  // general path
     BCK(cudaEventRecord(e1, st));
     BCK(cudaEventSynchronize(e1));
     float ms = 0.f;
