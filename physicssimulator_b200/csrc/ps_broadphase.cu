@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(OP_T) own_pairs_kernel(int n_small, Grid g, co
     const SBox A = sbox[s];
     const unsigned i = sid[s], c = scell[s], ast = sstat[s];
     const int ix = (int)(c % (unsigned)g.dim[0]), iy = (int)((c / (unsigned)g.dim[0]) % (unsigned)g.dim[1]), iz = (int)(c / ((unsigned)g.dim[0] * (unsigned)g.dim[1]));
-    unsigned list[kListCap];
+    unsigned list[kListCap] = {};
     int m = 0;
     bool over = false;
     auto add = [&](unsigned j) {  // sorted insertion; partners are few

@@ -56,7 +56,16 @@ struct HostJoints {
 struct Batch {
     int device = 0;
     ps_step_config cfg{};
-    HostBodies init, cur;  // `cur` holds parameters (+ possibly added bodies); dynamic state lives on the device
+    HostBodies init, cur;  // `cur`: parameters of the bodies as of the last upload (compact ABI layout); dynamic state lives on the device
+    // Device layout: world w owns the slots [cap_off[w], cap_off[w + 1]) of every per-body array and fills the first
+    // cnt[w] of them; the spare slots are what makes Simulator.AddObject a record write instead of a re-upload
+    // (SimulatorState.fs:89-107).  abi_off = prefix of cnt = the caller's compact body index.
+    std::vector<int> cap_off, cnt, abi_off;
+    std::vector<double> slot_mass;   // per slot (static tests on the host: candidates, trees)
+    std::vector<HostBodies> added;   // bodies added since the last upload, in order (spliced into `cur` when a re-layout is needed)
+    std::vector<int> added_world;
+    int n_slots = 0;
+    int *d_cnt = nullptr, *d_abi_off = nullptr;
     HostJoints joints;
     int n_worlds = 0, n_bodies = 0, n_dynamic = 0, max_n = 0;
     int threads = 8;  // lanes per world
@@ -136,22 +145,26 @@ struct Batch {
 
 // ---- layout kernels ------------------------------------------------------------------------------
 // ABI (pos[3n] vel[3n] rot[9n] L[3n]) <-> per-world planar dyn
-__global__ void pack_dyn_kernel(const int* __restrict__ off, int w0, int w1, const double* __restrict__ pos,
-                                const double* __restrict__ vel, const double* __restrict__ rot,
-                                const double* __restrict__ L, double* __restrict__ dyn, int body0)
+// one thread per body of the worlds [w0, w1) in the caller's compact order; abi = prefix of the body counts, off = first
+// slot of every world on the device
+__device__ __forceinline__ int slot_of(const int* __restrict__ abi, const int* __restrict__ off, int w0, int w1, int s)
 {
-    // one thread per (world-local) body in [off[w0], off[w1])
-    int g = blockIdx.x * blockDim.x + threadIdx.x + off[w0];
-    if (g >= off[w1]) return;
-    // binary search of the world
-    int lo = w0, hi = w1;
+    int lo = w0, hi = w1;  // world of compact index s: abi[lo] <= s < abi[lo + 1]
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
-        if (off[mid] <= g) lo = mid; else hi = mid;
+        if (abi[mid] <= s) lo = mid; else hi = mid;
     }
-    (void)lo;
-    double* d = dyn + (size_t)g * kDynF;  // body-major record
-    int s = g - body0;  // index into the caller arrays (which start at world w0)
+    return off[lo] + (s - abi[lo]);
+}
+__global__ void pack_dyn_kernel(const int* __restrict__ abi, const int* __restrict__ off, int w0, int w1, const double* __restrict__ pos,
+                                const double* __restrict__ vel, const double* __restrict__ rot,
+                                const double* __restrict__ L, double* __restrict__ dyn)
+{
+    const int body0 = abi[w0];
+    int c = blockIdx.x * blockDim.x + threadIdx.x + body0;
+    if (c >= abi[w1]) return;
+    double* d = dyn + (size_t)slot_of(abi, off, w0, w1, c) * kDynF;  // body-major record
+    int s = c - body0;  // index into the caller arrays (which start at world w0)
     for (int k = 0; k < 3; k++) {
         d[k] = pos[3 * s + k];
         d[3 + k] = vel[3 * s + k];
@@ -159,20 +172,15 @@ __global__ void pack_dyn_kernel(const int* __restrict__ off, int w0, int w1, con
     }
     for (int k = 0; k < 9; k++) d[6 + k] = rot[9 * s + k];
 }
-__global__ void unpack_dyn_kernel(const int* __restrict__ off, int w0, int w1, double* __restrict__ pos,
+__global__ void unpack_dyn_kernel(const int* __restrict__ abi, const int* __restrict__ off, int w0, int w1, double* __restrict__ pos,
                                   double* __restrict__ vel, double* __restrict__ rot, double* __restrict__ L,
-                                  const double* __restrict__ dyn, int body0)
+                                  const double* __restrict__ dyn)
 {
-    int g = blockIdx.x * blockDim.x + threadIdx.x + off[w0];
-    if (g >= off[w1]) return;
-    int lo = w0, hi = w1;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (off[mid] <= g) lo = mid; else hi = mid;
-    }
-    (void)lo;
-    const double* d = dyn + (size_t)g * kDynF;
-    int s = g - body0;
+    const int body0 = abi[w0];
+    int c = blockIdx.x * blockDim.x + threadIdx.x + body0;
+    if (c >= abi[w1]) return;
+    const double* d = dyn + (size_t)slot_of(abi, off, w0, w1, c) * kDynF;
+    int s = c - body0;
     for (int k = 0; k < 3; k++) {
         if (pos) pos[3 * s + k] = d[k];
         if (vel) vel[3 * s + k] = d[3 + k];
@@ -186,7 +194,7 @@ __global__ void unpack_dyn_kernel(const int* __restrict__ off, int w0, int w1, d
 __global__ void apply_impulse_kernel(double* dyn, const double* par, const int* off, int w, int b, double jx, double jy,
                                      double jz, double ox, double oy, double oz)
 {
-    int o = off[w], N = off[w + 1] - o;
+    int o = off[w], N = 0;
     Dyn d;
     Par p;
     ld_dyn(dyn + (size_t)o * kDynF, N, b, d);
@@ -196,7 +204,7 @@ __global__ void apply_impulse_kernel(double* dyn, const double* par, const int* 
 }
 
 // K6: per-world counters -> one ps_stats (integer sums + max)
-__global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const double* par, int n_worlds, ps_stats* out)
+__global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const int* cnt, const double* par, int n_worlds, ps_stats* out)
 {
     unsigned long long steps = 0, tested = 0, hits = 0, contacts = 0, fallback = 0, overflow = 0, exc = 0, nanw = 0, bsteps = 0;
     unsigned long long fbm = 0, fbc = 0, fbs = 0, ver = 0;
@@ -207,7 +215,7 @@ __global__ void stats_reduce_kernel(const WorldStats* ws, const int* off, const 
         fallback += s.fallback; overflow += s.overflow; exc += s.ref_exc; nanw += s.nan_flag ? 1 : 0;
         fbm += s.fb_margin; fbc += s.fb_capacity; fbs += s.fb_static; ver += s.verified;
         mp = fmax(mp, s.max_pen);
-        int o = off[w], N = off[w + 1] - o, dynb = 0;
+        int o = off[w], N = cnt[w], dynb = 0;
         const double* p = par + (size_t)o * kParF;
         for (int b = 0; b < N; b++) dynb += (p[(size_t)b * kParF] != 0.0);
         bsteps += s.steps * (unsigned long long)dynb;
@@ -278,7 +286,7 @@ void free_device(Batch* B)
     dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cost); dfree(B->d_perm); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
-    dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev);
+    dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev); dfree(B->d_cnt); dfree(B->d_abi_off);
     if (B->h_bucket) { cudaFreeHost(B->h_bucket); B->h_bucket = nullptr; }
     if (B->h_est) { cudaFreeHost(B->h_est); B->h_est = nullptr; }
     if (B->est_ready) { cudaEventDestroy(B->est_ready); B->est_ready = nullptr; }
@@ -312,6 +320,22 @@ int validate_bodies(const HostBodies& h)
     return PS_OK;
 }
 
+// the 16-double parameter record of body c of a compact HostBodies (slot 0 = 1.0/mass, IEEE division as on the reference's `v / mass`)
+static void par_record(const HostBodies& h, int c, double* p)
+{
+    for (int k = 0; k < kParF; k++) p[k] = 0.0;
+    p[0] = 1.0 / h.mass[c];
+    for (int k = 0; k < 3; k++) {
+        p[1 + k] = h.iinv[3 * c + k];
+        p[4 + k] = h.force[3 * c + k];
+        p[7 + k] = h.torque[3 * c + k];
+        p[12 + k] = h.dims[3 * c + k];
+    }
+    p[10] = h.e[c];
+    p[11] = h.muk[c];
+    p[15] = (double)h.shape[c];
+}
+
 // upload parameters + (optionally) dynamic state of B->cur, (re)allocating device buffers
 int upload(Batch* B, bool with_state)
 {
@@ -322,7 +346,25 @@ int upload(Batch* B, bool with_state)
     B->n_bodies = h.n();
     B->max_n = 0;
     B->n_dynamic = 0;
-    for (int w = 0; w < B->n_worlds; w++) B->max_n = std::max(B->max_n, h.off[w + 1] - h.off[w]);
+    B->added.clear(); B->added_world.clear();
+    {   // slots: every world gets room for a few more bodies than it has (PS_B200_SPARE overrides the rule below)
+        int spare_min = 4;
+        if (const char* e = getenv("PS_B200_SPARE")) spare_min = std::max(0, atoi(e));
+        B->cap_off.assign((size_t)B->n_worlds + 1, 0);
+        B->cnt.assign((size_t)B->n_worlds, 0);
+        B->abi_off = h.off;
+        for (int w = 0; w < B->n_worlds; w++) {
+            const int N = h.off[w + 1] - h.off[w];
+            const int cap = std::min(1024, N + std::max(spare_min, N / 16));
+            B->cnt[w] = N;
+            B->cap_off[w + 1] = B->cap_off[w] + std::max(cap, N);
+            B->max_n = std::max(B->max_n, std::max(cap, N));
+        }
+        B->n_slots = B->cap_off[B->n_worlds];
+        B->slot_mass.assign((size_t)std::max(1, B->n_slots), 1.0);
+        for (int w = 0; w < B->n_worlds; w++)
+            for (int b = 0; b < B->cnt[w]; b++) B->slot_mass[B->cap_off[w] + b] = h.mass[h.off[w] + b];
+    }
     for (int i = 0; i < B->n_bodies; i++) B->n_dynamic += std::isinf(h.mass[i]) ? 0 : 1;
     // lanes per world (tile): a wavefront level of a 128-body pile holds ~10 pairs, so 8 lanes per world and 4
     // worlds per warp keep the lanes busy; with few worlds wider tiles give the SMs more warps to overlap
@@ -364,8 +406,11 @@ int upload(Batch* B, bool with_state)
 #undef PS_SET_ATTRS
     }
 
-    size_t nb = (size_t)std::max(1, B->n_bodies);
+    size_t nb = (size_t)std::max(1, B->n_slots);  // per-body device arrays are per SLOT
     CK(cudaMalloc(&B->d_dyn, nb * kDynF * sizeof(double)));
+    CK(cudaMemsetAsync(B->d_dyn, 0, nb * kDynF * sizeof(double), B->stream));
+    CK(cudaMalloc(&B->d_cnt, (size_t)std::max(1, B->n_worlds) * sizeof(int)));
+    CK(cudaMalloc(&B->d_abi_off, (size_t)(B->n_worlds + 1) * sizeof(int)));
     CK(cudaMalloc(&B->d_par, nb * kParF * sizeof(double)));
     CK(cudaMalloc(&B->d_stage, nb * kDynF * sizeof(double)));
     CK(cudaMalloc(&B->d_off, (size_t)(B->n_worlds + 1) * sizeof(int)));
@@ -377,7 +422,7 @@ int upload(Batch* B, bool with_state)
     {   // per-step lists of every world: 9 bytes per pair of the world
         std::vector<long long> loff(B->n_worlds + 1, 0);
         for (int w = 0; w < B->n_worlds; w++) {
-            long long N = h.off[w + 1] - h.off[w], np = N * (N - 1) / 2;
+            long long N = B->cap_off[w + 1] - B->cap_off[w], np = N * (N - 1) / 2;  // room for the world at its capacity
             loff[w + 1] = loff[w] + ((np * 9 + 15) / 16) * 16;
         }
         CK(cudaMalloc(&B->d_lists, (size_t)std::max<long long>(loff[B->n_worlds], 16)));
@@ -393,10 +438,11 @@ int upload(Batch* B, bool with_state)
         std::vector<unsigned char> isstat(nb, 0), isbox(nb, 0), af(std::max(1, B->n_worlds), 0);
         for (int w = 0; w < B->n_worlds; w++) {
             int ns = 0;
-            for (int g = h.off[w]; g < h.off[w + 1]; g++) {
-                bw[g] = w;
-                isbox[g] = h.shape[g] != 0;
-                if (std::isinf(h.mass[g])) { ns++; isstat[g] = (unsigned char)std::min(ns, kMaxStatics); }
+            for (int g = B->cap_off[w]; g < B->cap_off[w + 1]; g++) bw[g] = w;  // spare slots know their world too
+            for (int b = 0; b < B->cnt[w]; b++) {
+                const int g = B->cap_off[w] + b, c = h.off[w] + b;
+                isbox[g] = h.shape[c] != 0;
+                if (std::isinf(h.mass[c])) { ns++; isstat[g] = (unsigned char)std::min(ns, kMaxStatics); }
             }
             af[w] = ns > kMaxStatics;
         }
@@ -459,23 +505,14 @@ int upload(Batch* B, bool with_state)
         B->steps_since_sort = 1 << 20;
     }
     CK(cudaMemsetAsync(B->d_stats, 0, (size_t)std::max(1, B->n_worlds) * sizeof(WorldStats), B->stream));
-    CK(cudaMemcpyAsync(B->d_off, h.off.data(), (size_t)(B->n_worlds + 1) * sizeof(int), cudaMemcpyHostToDevice, B->stream));
+    CK(cudaMemcpyAsync(B->d_off, B->cap_off.data(), (size_t)(B->n_worlds + 1) * sizeof(int), cudaMemcpyHostToDevice, B->stream));
+    CK(cudaMemcpyAsync(B->d_abi_off, B->abi_off.data(), (size_t)(B->n_worlds + 1) * sizeof(int), cudaMemcpyHostToDevice, B->stream));
+    if (B->n_worlds > 0) CK(cudaMemcpyAsync(B->d_cnt, B->cnt.data(), (size_t)B->n_worlds * sizeof(int), cudaMemcpyHostToDevice, B->stream));
 
     // parameters -> body-major records (slot 0 = 1.0/mass, IEEE division as on the reference's `v / mass`)
     std::vector<double> par(nb * kParF, 0.0);
-    for (int g = 0; g < B->n_bodies; g++) {
-        double* p = par.data() + (size_t)g * kParF;
-        p[0] = 1.0 / h.mass[g];
-        for (int k = 0; k < 3; k++) {
-            p[1 + k] = h.iinv[3 * g + k];
-            p[4 + k] = h.force[3 * g + k];
-            p[7 + k] = h.torque[3 * g + k];
-            p[12 + k] = h.dims[3 * g + k];
-        }
-        p[10] = h.e[g];
-        p[11] = h.muk[g];
-        p[15] = (double)h.shape[g];
-    }
+    for (int w = 0; w < B->n_worlds; w++)
+        for (int b = 0; b < B->cnt[w]; b++) par_record(h, h.off[w] + b, par.data() + (size_t)(B->cap_off[w] + b) * kParF);
     CK(cudaMemcpyAsync(B->d_par, par.data(), nb * kParF * sizeof(double), cudaMemcpyHostToDevice, B->stream));
     CK(cudaStreamSynchronize(B->stream));  // `par` is a local
 
@@ -532,7 +569,7 @@ int upload(Batch* B, bool with_state)
     if (B->tree_mode) {
         B->wide = false;  // the batch-wide path builds its lists from the Dummy order
         size_t np = 0;
-        for (int w = 0; w < B->n_worlds; w++) { size_t N = (size_t)(h.off[w + 1] - h.off[w]); np += N * (N > 0 ? N - 1 : 0) / 2; }
+        for (int w = 0; w < B->n_worlds; w++) { size_t N = (size_t)(B->cap_off[w + 1] - B->cap_off[w]); np += N * (N > 0 ? N - 1 : 0) / 2; }
         CK(cudaMalloc(&B->d_ext, nb * 6 * sizeof(double)));
         CK(cudaMallocHost(&B->h_ext, nb * 6 * sizeof(double)));
         CK(cudaMalloc(&B->d_cand, std::max<size_t>(np, 1) * sizeof(unsigned)));
@@ -549,10 +586,10 @@ int upload(Batch* B, bool with_state)
 // extents of every body at the state the device holds now -> B->h_ext
 int tree_pull_extents(Batch* B, cudaStream_t st)
 {
-    if (B->n_bodies == 0) return PS_OK;
-    extent_kernel<<<(B->n_bodies + 127) / 128, 128, 0, st>>>(B->n_bodies, B->d_dyn, B->d_par, B->d_ext, B->cfg.aabb_mode);
+    if (B->n_slots == 0) return PS_OK;
+    extent_kernel<<<(B->n_slots + 127) / 128, 128, 0, st>>>(B->n_slots, B->d_dyn, B->d_par, B->d_ext, B->cfg.aabb_mode);  // (spare slots: unread)
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(B->h_ext, B->d_ext, (size_t)B->n_bodies * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(B->h_ext, B->d_ext, (size_t)B->n_slots * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PS_OK;
 }
@@ -567,7 +604,7 @@ static pst::Ext<3> ext_of(const Batch* B, int g)
 // makes the reference throw ArgumentException (SpatialTree.fs:171-172)
 int tree_init_world(Batch* B, int w)
 {
-    const int o = B->cur.off[w], N = B->cur.off[w + 1] - o;
+    const int o = B->cap_off[w], N = B->cnt[w];
     pst::Tree<3>& t = B->trees[w];
     if (!t.init(B->cfg.tree_leaf_capacity, B->cfg.tree_max_depth, B->cfg.tree_min, B->cfg.tree_max))
         return fail(PS_ERR_INVALID_ARGUMENT, "SpatialTree: must be positive (maxLeafObjects / maxDepth)");
@@ -601,9 +638,9 @@ int tree_update_and_upload(Batch* B, cudaStream_t st)
     std::vector<uint32_t> one;
     std::vector<unsigned char> stat;
     for (int w = 0; w < B->n_worlds; w++) {
-        const int o = B->cur.off[w], N = B->cur.off[w + 1] - o;
+        const int o = B->cap_off[w], N = B->cnt[w];
         stat.assign((size_t)N, 0);
-        for (int b = 0; b < N; b++) stat[b] = std::isinf(B->cur.mass[o + b]) ? 1 : 0;
+        for (int b = 0; b < N; b++) stat[b] = std::isinf(B->slot_mass[o + b]) ? 1 : 0;
         pst::Tree<3>& t = B->trees[w];
         t.remove_if([&](int id) { return !stat[id]; });
         for (int id = 0; id < N; id++)
@@ -617,6 +654,39 @@ int tree_update_and_upload(Batch* B, cudaStream_t st)
     CK(cudaMemcpyAsync(B->d_cand_off, B->h_cand_off.data(), B->h_cand_off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));  // the host vectors are reused by the next step
     return PS_OK;
+}
+
+// compact description of the batch as it stands NOW: `cur` (as of the last upload) + every body added since, spliced in
+// at the end of its world, + the live dynamic state from the device
+int merged_description(Batch* B, HostBodies& out)
+{
+    const HostBodies& h = B->cur;
+    const int nw = B->n_worlds;
+    std::vector<std::vector<int>> add_of((size_t)nw);
+    for (size_t q = 0; q < B->added.size(); q++) add_of[(size_t)B->added_world[q]].push_back((int)q);
+    out = HostBodies();
+    out.off.assign((size_t)nw + 1, 0);
+    auto app = [](std::vector<double>& dst, const std::vector<double>& src, size_t first, size_t count, int per) {
+        dst.insert(dst.end(), src.begin() + (ptrdiff_t)(first * per), src.begin() + (ptrdiff_t)((first + count) * per));
+    };
+    for (int w = 0; w < nw; w++) {
+        const size_t f = (size_t)h.off[w], c = (size_t)(h.off[w + 1] - h.off[w]);
+        out.shape.insert(out.shape.end(), h.shape.begin() + (ptrdiff_t)f, h.shape.begin() + (ptrdiff_t)(f + c));
+        app(out.dims, h.dims, f, c, 3); app(out.mass, h.mass, f, c, 1); app(out.iinv, h.iinv, f, c, 3); app(out.force, h.force, f, c, 3);
+        app(out.torque, h.torque, f, c, 3); app(out.e, h.e, f, c, 1); app(out.muk, h.muk, f, c, 1); app(out.mus, h.mus, f, c, 1);
+        for (int q : add_of[(size_t)w]) {
+            const HostBodies& a = B->added[(size_t)q];
+            out.shape.push_back(a.shape[0]);
+            app(out.dims, a.dims, 0, 1, 3); app(out.mass, a.mass, 0, 1, 1); app(out.iinv, a.iinv, 0, 1, 3); app(out.force, a.force, 0, 1, 3);
+            app(out.torque, a.torque, 0, 1, 3); app(out.e, a.e, 0, 1, 1); app(out.muk, a.muk, 0, 1, 1); app(out.mus, a.mus, 0, 1, 1);
+        }
+        out.off[(size_t)w + 1] = (int32_t)out.mass.size();
+    }
+    const size_t n = out.mass.size();
+    if ((int)n != B->n_bodies) return fail(PS_ERR_INVALID_OPERATION, "internal: %zu merged bodies, %d on the device", n, B->n_bodies);
+    out.pos.assign(3 * n, 0.0); out.vel.assign(3 * n, 0.0); out.rot.assign(9 * n, 0.0); out.L.assign(3 * n, 0.0);
+    if (n == 0) return PS_OK;
+    return ps_batch_get_state(B, 0, nw, out.pos.data(), out.vel.data(), out.rot.data(), out.L.data());
 }
 
 void copy_view(HostBodies& h, const ps_bodies_view* v)
@@ -776,7 +846,7 @@ int ps_batch_destroy(void* handle)
 
 static void fill_kargs(Batch* B, KArgs& a, int n_steps)
 {
-    a.dyn = B->d_dyn; a.par = B->d_par; a.off = B->d_off; a.stats = B->d_stats;
+    a.dyn = B->d_dyn; a.par = B->d_par; a.off = B->d_off; a.cnt = B->d_cnt; a.stats = B->d_stats;
     a.n_worlds = B->n_worlds; a.n_steps = n_steps;
     a.sp.eps = B->cfg.epsilon; a.sp.baumgarte = B->cfg.baumgarte; a.sp.slop = B->cfg.allowed_penetration;
     a.sp.max_corr = B->cfg.max_correction_velocity; a.sp.dt = B->cfg.dt;
@@ -870,7 +940,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
 {
     using namespace psw;
     WArgs a{};
-    a.n_worlds = B->n_worlds; a.n_bodies = B->n_bodies; a.max_n = B->max_n; a.off = B->d_off; a.body_world = B->d_body_world;
+    a.n_worlds = B->n_worlds; a.n_bodies = B->n_slots; a.max_n = B->max_n; a.off = B->d_off; a.cnt = B->d_cnt; a.body_world = B->d_body_world;
     a.dyn = B->d_dyn; a.cur = B->d_cur; a.pred = B->d_pred; a.par = B->d_par; a.S = B->d_S; a.cull = B->d_cull;
     a.pvalid = B->d_pvalid; a.nhit = B->d_nhit; a.nprev = B->d_hitcnt; a.isstat = B->d_isstat; a.isbox = B->d_isbox;
     a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off;
@@ -883,7 +953,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     a.nlev = B->d_nlev; a.team_max = B->team_max;
     a.sp = ka.sp; a.margin_ncap = ka.margin_ncap;
     a.margin_scale = ka.margin_scale;
-    const int nb = B->n_bodies, nw = B->n_worlds;
+    const int nb = B->n_slots, nw = B->n_worlds;
     const int gb = (nb + 127) / 128, gw = (nw + 63) / 64, gl = (nw + psw::kLvlWorlds - 1) / psw::kLvlWorlds;
     const bool prof = getenv("PS_B200_WIDE_PROF") != nullptr;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
@@ -1113,13 +1183,13 @@ int ps_batch_get_state_device(void* handle, int32_t w0, int32_t w1, double* d_po
     int rc = check_range(B, w0, w1);
     if (rc) return rc;
     CK(cudaSetDevice(B->device));
-    int b0 = B->cur.off[w0], n = B->cur.off[w1] - b0;
+    int b0 = B->abi_off[w0], n = B->abi_off[w1] - b0;
     if (n == 0) return PS_OK;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : B->stream;
     bool capturing = false;
     rc = foreign_enter(B, st, &capturing);
     if (rc) return rc;
-    unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_off, w0, w1, d_pos, d_vel, d_rot, d_ang_mom, B->d_dyn, b0);
+    unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_abi_off, B->d_off, w0, w1, d_pos, d_vel, d_rot, d_ang_mom, B->d_dyn);
     CK(cudaGetLastError());
     return foreign_leave(B, st, capturing);
 }
@@ -1132,12 +1202,12 @@ int ps_batch_get_state(void* handle, int32_t w0, int32_t w1, double* pos, double
     int rc = check_range(B, w0, w1);
     if (rc) return rc;
     CK(cudaSetDevice(B->device));
-    int b0 = B->cur.off[w0], n = B->cur.off[w1] - b0;
+    int b0 = B->abi_off[w0], n = B->abi_off[w1] - b0;
     if (n == 0) return PS_OK;
     double* sp = B->d_stage + (size_t)b0 * kDynF;  // this range's staging slice: pos | vel | rot | L
     double *dp = sp, *dv = sp + 3 * (size_t)n, *dr = sp + 6 * (size_t)n, *dl = sp + 15 * (size_t)n;
-    unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, B->stream>>>(B->d_off, w0, w1, pos ? dp : nullptr, vel ? dv : nullptr,
-                                                               rot ? dr : nullptr, ang_mom ? dl : nullptr, B->d_dyn, b0);
+    unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, B->stream>>>(B->d_abi_off, B->d_off, w0, w1, pos ? dp : nullptr, vel ? dv : nullptr,
+                                                               rot ? dr : nullptr, ang_mom ? dl : nullptr, B->d_dyn);
     CK(cudaGetLastError());
     if (pos) CK(cudaMemcpyAsync(pos, dp, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, B->stream));
     if (vel) CK(cudaMemcpyAsync(vel, dv, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, B->stream));
@@ -1157,7 +1227,7 @@ int ps_batch_set_state(void* handle, int32_t w0, int32_t w1, const double* pos, 
     if (rc) return rc;
     if (!pos || !vel || !rot || !ang_mom) return fail(PS_ERR_INVALID_ARGUMENT, "state array is null");
     CK(cudaSetDevice(B->device));
-    int b0 = B->cur.off[w0], n = B->cur.off[w1] - b0;
+    int b0 = B->abi_off[w0], n = B->abi_off[w1] - b0;
     if (n == 0) return PS_OK;
     double* sp = B->d_stage + (size_t)b0 * kDynF;
     double *dp = sp, *dv = sp + 3 * (size_t)n, *dr = sp + 6 * (size_t)n, *dl = sp + 15 * (size_t)n;
@@ -1165,7 +1235,7 @@ int ps_batch_set_state(void* handle, int32_t w0, int32_t w1, const double* pos, 
     CK(cudaMemcpyAsync(dv, vel, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, B->stream));
     CK(cudaMemcpyAsync(dr, rot, 9 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, B->stream));
     CK(cudaMemcpyAsync(dl, ang_mom, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, B->stream));
-    pack_dyn_kernel<<<(n + 255) / 256, 256, 0, B->stream>>>(B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn, b0);
+    pack_dyn_kernel<<<(n + 255) / 256, 256, 0, B->stream>>>(B->d_abi_off, B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(B->stream));
     return PS_OK;
@@ -1207,7 +1277,7 @@ int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, cons
     CK(cudaEventRecord(B->chunk_start, B->stream));  // after whatever the handle's own stream still holds
     for (int k = 0; k < chunks; k++) {
         const int w0 = k * per, w1 = std::min(B->n_worlds, w0 + per);
-        const int b0 = B->cur.off[w0], n = B->cur.off[w1] - b0;
+        const int b0 = B->abi_off[w0], n = B->abi_off[w1] - b0;
         cudaStream_t st = B->chunk_streams[k];
         CK(cudaStreamWaitEvent(st, B->chunk_start, 0));
         if (n > 0) {
@@ -1217,11 +1287,11 @@ int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, cons
             CK(cudaMemcpyAsync(dv, vel_in + 3 * (size_t)b0, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(dr, rot_in + 9 * (size_t)b0, 9 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(dl, ang_mom_in + 3 * (size_t)b0, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
-            pack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn, b0);
+            pack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_abi_off, B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn);
             KArgs ak = a;
             ak.world_base = w0; ak.n_worlds = w1;
             launch_fused(B, ak, st);
-            unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn, b0);
+            unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_abi_off, B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn);
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(pos_out + 3 * (size_t)b0, dp, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(vel_out + 3 * (size_t)b0, dv, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1292,11 +1362,11 @@ int ps_batch_get_candidates(void* handle, int32_t world, int32_t* n_pairs, int32
     }
     // Dummy order (BroadPhase.fs:33-39) filtered by canIntersect (CollisionResolver.fs:58-60): a function of
     // the body set only, so it is produced here from the static flags.
-    int o = B->cur.off[world], N = B->cur.off[world + 1] - o;
+    int o = B->cap_off[world], N = B->cnt[world];
     int n = 0;
     for (int i = 0; i < N; i++)
         for (int j = i + 1; j < N; j++) {
-            if (std::isinf(B->cur.mass[o + i]) && std::isinf(B->cur.mass[o + j])) continue;
+            if (std::isinf(B->slot_mass[o + i]) && std::isinf(B->slot_mass[o + j])) continue;
             if (pair_ids && n < pair_capacity) { pair_ids[2 * n] = i; pair_ids[2 * n + 1] = j; }
             n++;
         }
@@ -1311,7 +1381,7 @@ int ps_batch_apply_impulse(void* handle, int32_t world, int32_t body, const doub
     Batch* B = (Batch*)handle;
     PS_REFUSE_IF_BROKEN(B);
     if (world < 0 || world >= B->n_worlds) return fail(PS_ERR_OUT_OF_RANGE, "world %d outside [0,%d)", world, B->n_worlds);
-    int N = B->cur.off[world + 1] - B->cur.off[world];
+    int N = B->cnt[world];
     if (body < 0 || body >= N) return fail(PS_ERR_OUT_OF_RANGE, "body %d outside [0,%d)", body, N);  // KeyNotFoundException
     if (!impulse || !offset) return fail(PS_ERR_INVALID_ARGUMENT, "impulse/offset is null");
     CK(cudaSetDevice(B->device));
@@ -1338,30 +1408,82 @@ int ps_batch_add_body(void* handle, int32_t world, const ps_bodies_view* one)
     // Everything that can refuse the body is checked BEFORE anything changes (a failed call leaves the batch as it was):
     // the per-world size limit, and in SpatialTree mode the tree's space (BroadPhase.onNewObjectAdded throws
     // "out of space bounds", BroadPhase.fs:83-98 / SpatialTree.fs:171-172).
-    HostBodies& h = B->cur;
-    if (h.off[world + 1] - h.off[world] + 1 > 1024)
-        return fail(PS_ERR_INVALID_ARGUMENT, "world %d would have %d bodies; the per-world stepper takes at most 1024", world, h.off[world + 1] - h.off[world] + 1);
+    const int N0 = B->cnt[world];
+    if (N0 + 1 > 1024)
+        return fail(PS_ERR_INVALID_ARGUMENT, "world %d would have %d bodies; the per-world stepper takes at most 1024", world, N0 + 1);
+    double e6[6];
     if (B->tree_mode) {
-        double e6[6];
         body_extent6(nb.pos.data(), nb.rot.data(), nb.dims.data(), nb.shape[0] == 0, B->cfg.aabb_mode, e6);
         pst::Ext<3> oe;
         for (int k = 0; k < 3; k++) { oe.size[k] = e6[k]; oe.pos[k] = e6[3 + k]; }
         if (!B->trees[world].in_space(oe))
-            return fail(PS_ERR_INVALID_ARGUMENT, "world %d: object %d out of space bounds", world, h.off[world + 1] - h.off[world]);
+            return fail(PS_ERR_INVALID_ARGUMENT, "world %d: object %d out of space bounds", world, N0);
     }
-    // pull the live state, splice the body in as id = max id + 1 of that world (SimulatorState.fs:90-92), re-upload
-    rc = ps_batch_get_state(B, 0, B->n_worlds, h.pos.data(), h.vel.data(), h.rot.data(), h.L.data());
+    CK(cudaSetDevice(B->device));
+    const bool is_static = std::isinf(nb.mass[0]);
+    if (N0 < B->cap_off[world + 1] - B->cap_off[world]) {
+        // ---- the world has a spare slot: the new body (id = max id + 1, SimulatorState.fs:90-92) is a record write ------
+        const int g = B->cap_off[world] + N0;
+        int nstat = 0;
+        for (int q = 0; q < N0; q++) nstat += std::isinf(B->slot_mass[B->cap_off[world] + q]) ? 1 : 0;
+        double rec[kParF + kDynF];
+        par_record(nb, 0, rec);
+        double* d = rec + kParF;
+        for (int k = 0; k < 3; k++) { d[k] = nb.pos[k]; d[3 + k] = nb.vel[k]; d[15 + k] = nb.L[k]; }
+        for (int k = 0; k < 9; k++) d[6 + k] = nb.rot[k];
+        const unsigned char flags[2] = {(unsigned char)(is_static ? std::min(nstat + 1, kMaxStatics) : 0), (unsigned char)(nb.shape[0] != 0)};
+        const unsigned char af = (unsigned char)((nstat + (is_static ? 1 : 0)) > kMaxStatics);
+        const int newcnt = N0 + 1;
+        for (int w = world + 1; w <= B->n_worlds; w++) B->abi_off[w]++;
+        cudaStream_t st = B->stream;
+        CK(cudaMemcpyAsync(B->d_par + (size_t)g * kParF, rec, kParF * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(B->d_dyn + (size_t)g * kDynF, d, kDynF * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(B->d_isstat + g, &flags[0], 1, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(B->d_isbox + g, &flags[1], 1, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(B->d_hitcnt + g, 0, 1, st));
+        CK(cudaMemcpyAsync(B->d_always_fused + world, &af, 1, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(B->d_cnt + world, &newcnt, sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(B->d_abi_off + world + 1, B->abi_off.data() + world + 1, (size_t)(B->n_worlds - world) * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        B->cnt[world] = newcnt;
+        B->slot_mass[g] = nb.mass[0];
+        B->n_bodies++;
+        if (!is_static) B->n_dynamic++;
+        B->added.push_back(nb);
+        B->added_world.push_back(world);
+        B->est_valid = false;  // (grid estimates of the device-counted rounds: harmless if stale, but a changed batch starts afresh)
+        if (B->tree_mode) {  // BroadPhase.onNewObjectAdded (BroadPhase.fs:83-98): the new id joins the existing tree
+            rc = tree_pull_extents(B, B->stream);  // a split re-files the leaf's objects by their CURRENT extents
+            if (rc) return rc;
+            const int o = B->cap_off[world];
+            if (!B->trees[world].insert(N0, [&](int x) { return ext_of(B, o + x); }))
+                return fail(PS_ERR_INVALID_ARGUMENT, "world %d: object %d out of space bounds", world, N0);  // (ruled out above: same extent, same test)
+            B->h_cand_off.assign((size_t)B->n_worlds + 1, 0);
+            B->h_cand.clear();
+        }
+        return PS_OK;
+    }
+    // ---- the world is full: pull the live state, splice every body added so far and this one into the compact
+    //      description, and lay the batch out again (with fresh spare slots) --------------------------------------------
+    HostBodies merged;
+    rc = merged_description(B, merged);
     if (rc) return rc;
     std::vector<WorldStats> keep(B->n_worlds);
     CK(cudaMemcpy(keep.data(), B->d_stats, keep.size() * sizeof(WorldStats), cudaMemcpyDeviceToHost));
-    const HostBodies before = h;
-    int at = h.off[world + 1];
-    auto ins = [&](std::vector<double>& dst, const std::vector<double>& src, int per) { dst.insert(dst.begin() + (size_t)per * at, src.begin(), src.end()); };
-    h.shape.insert(h.shape.begin() + at, nb.shape[0]);
-    ins(h.dims, nb.dims, 3); ins(h.mass, nb.mass, 1); ins(h.iinv, nb.iinv, 3); ins(h.pos, nb.pos, 3); ins(h.vel, nb.vel, 3);
-    ins(h.rot, nb.rot, 9); ins(h.L, nb.L, 3); ins(h.force, nb.force, 3); ins(h.torque, nb.torque, 3); ins(h.e, nb.e, 1);
-    ins(h.muk, nb.muk, 1); ins(h.mus, nb.mus, 1);
-    for (int w = world + 1; w <= B->n_worlds; w++) h.off[w]++;
+    std::vector<pst::Tree<3>> trees_keep;
+    if (B->tree_mode) trees_keep = B->trees;
+    const HostBodies before = merged;
+    {
+        HostBodies& h = merged;
+        const int at = h.off[world + 1];
+        auto ins = [&](std::vector<double>& dst, const std::vector<double>& src, int per) { dst.insert(dst.begin() + (size_t)per * at, src.begin(), src.end()); };
+        h.shape.insert(h.shape.begin() + at, nb.shape[0]);
+        ins(h.dims, nb.dims, 3); ins(h.mass, nb.mass, 1); ins(h.iinv, nb.iinv, 3); ins(h.pos, nb.pos, 3); ins(h.vel, nb.vel, 3);
+        ins(h.rot, nb.rot, 9); ins(h.L, nb.L, 3); ins(h.force, nb.force, 3); ins(h.torque, nb.torque, 3); ins(h.e, nb.e, 1);
+        ins(h.muk, nb.muk, 1); ins(h.mus, nb.mus, 1);
+        for (int w = world + 1; w <= B->n_worlds; w++) h.off[w]++;
+    }
+    B->cur = merged;
     rc = upload(B, true);
     if (rc) {  // (shared-memory limit of a grown world, out of device memory): back to the batch as it was
         const std::string why = g_err;
@@ -1374,12 +1496,12 @@ int ps_batch_add_body(void* handle, int32_t world, const ps_bodies_view* one)
         return fail(rc, "%s", why.c_str());
     }
     CK(cudaMemcpy(B->d_stats, keep.data(), keep.size() * sizeof(WorldStats), cudaMemcpyHostToDevice));
-    if (B->tree_mode) {  // BroadPhase.onNewObjectAdded (BroadPhase.fs:83-98): the new id joins the existing tree
+    if (B->tree_mode) {
         rc = tree_pull_extents(B, B->stream);
         if (rc) return rc;
-        const int o = h.off[world], id = h.off[world + 1] - o - 1;
+        const int o = B->cap_off[world], id = B->cnt[world] - 1;
         if (!B->trees[world].insert(id, [&](int x) { return ext_of(B, o + x); }))
-            return fail(PS_ERR_INVALID_ARGUMENT, "world %d: object %d out of space bounds", world, id);  // (ruled out above: same extent, same test)
+            return fail(PS_ERR_INVALID_ARGUMENT, "world %d: object %d out of space bounds", world, id);  // (ruled out above)
         B->h_cand_off.assign((size_t)B->n_worlds + 1, 0);
         B->h_cand.clear();
     }
@@ -1407,7 +1529,7 @@ int ps_batch_stats(void* handle, ps_stats* out)
     CK(cudaMemsetAsync(B->d_stats_sum, 0, sizeof(ps_stats), B->stream));
     if (B->n_worlds > 0) {
         int blocks = std::min(64, (B->n_worlds + 127) / 128);
-        stats_reduce_kernel<<<blocks, 128, 0, B->stream>>>(B->d_stats, B->d_off, B->d_par, B->n_worlds, B->d_stats_sum);
+        stats_reduce_kernel<<<blocks, 128, 0, B->stream>>>(B->d_stats, B->d_off, B->d_cnt, B->d_par, B->n_worlds, B->d_stats_sum);
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(out, B->d_stats_sum, sizeof(ps_stats), cudaMemcpyDeviceToHost, B->stream));

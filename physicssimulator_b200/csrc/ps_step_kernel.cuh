@@ -83,7 +83,7 @@ struct RecContact {
 struct KArgs {
     double* dyn;          // [total_bodies*18], body-major: dyn[(off+b)*18 + f]  f: x 0-2, v 3-5, R 6-14, L 15-17
     const double* par;    // [total_bodies*16], body-major
-    const int* off;       // n_worlds+1
+    const int* off; const int* cnt;       // n_worlds+1
     WorldStats* stats;    // n_worlds
     unsigned char* hitcnt;  // [total_bodies] colliding pairs each body was in during its last step (margin model)
     double* cur;          // [total_bodies*18] working copy of the state during a step
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
     const int w = live ? wraw : 0;
     BlockShared& bs = bs_all[tile];
     const int off = a.off[w];
-    const int N = live ? a.off[w + 1] - off : 0;
+    const int N = live ? a.cnt[w] : 0;  // bodies of the world; off[] is the CAPACITY prefix (spare slots for AddObject)
     Ctx c;
     c.N = N; c.w = w; c.a = &a; c.bs = &bs;
     carve(smem_raw + (size_t)tile * smem_bytes(a.max_n), N, c.s);

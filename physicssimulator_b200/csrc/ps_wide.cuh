@@ -46,8 +46,9 @@ struct __align__(16) Entry {  // one near pair of the batch, sorted by (level, k
 
 struct WArgs {
     int n_worlds, n_bodies, max_n;
-    const int* off;
-    const int* body_world;       // [NB]
+    const int* off;              // per world: first SLOT (capacity prefix: a world owns spare slots for AddObject)
+    const int* cnt;              // per world: bodies
+    const int* body_world;       // [NB] world of every slot
     double* dyn; double* cur; double* pred; const double* par; double* S; double* cull;
     unsigned char* pvalid; unsigned char* nhit; unsigned char* nprev; const unsigned char* isstat; const unsigned char* isbox;  // [NB]
     int* row;                    // per world N+1 at off+w
@@ -104,7 +105,7 @@ __device__ __forceinline__ void count_pair(const WArgs& a, int w, unsigned hit, 
 }
 
 PSD unsigned* w_near(const WArgs& a, int w) { return reinterpret_cast<unsigned*>(a.lists + a.lists_off[w]); }
-PSD size_t w_np(const WArgs& a, int w) { size_t N = (size_t)(a.off[w + 1] - a.off[w]); return N * (N > 0 ? N - 1 : 0) / 2; }
+PSD size_t w_np(const WArgs& a, int w) { size_t N = (size_t)a.cnt[w]; return N * (N > 0 ? N - 1 : 0) / 2; }
 PSD unsigned short* w_level(const WArgs& a, int w) { return reinterpret_cast<unsigned short*>(a.lists + a.lists_off[w] + 4 * w_np(a, w)); }
 PSD unsigned char* w_hit(const WArgs& a, int w) { return a.lists + a.lists_off[w] + 8 * w_np(a, w); }
 
@@ -158,8 +159,9 @@ __global__ void __launch_bounds__(kTile) wide_predict(WArgs a)
         pst_tma::bulk_s2g(a.cur + (size_t)g0 * kDynF, s_in, bytes);
         pst_tma::bulk_commit();
     }
-    if (t < n) {
-        const int w = a.body_world[g], o = a.off[w], N = a.off[w + 1] - o, b = g - o;
+    const int wq = t < n ? a.body_world[g] : 0;
+    if (t < n && g - a.off[wq] < a.cnt[wq]) {  // (a spare slot holds no body)
+        const int w = wq, o = a.off[w], N = a.cnt[w], b = g - o;
         Dyn cur, pr;
         ld_dyn(s_in, 0, t, cur);
         integrate(cur, p, a.sp, pr);
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(128) wide_near_count(WArgs a)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= a.n_bodies) return;
-    const int w = a.body_world[g], o = a.off[w], N = a.off[w + 1] - o, i = g - o;
+    const int w = a.body_world[g], o = a.off[w], N = a.cnt[w], i = g - o;
+    if (i >= N) return;
     const double* cu = a.cull + (size_t)o * kCullF;
     int cn = 0;
     for (int j = i + 1; j < N; j++) cn += wide_near_test(a, cu, o, N, i, j) ? 1 : 0;
@@ -218,7 +221,7 @@ __global__ void wide_near_scan(WArgs a)  // thread per world
 {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.n_worlds) return;
-    const int o = a.off[w], N = a.off[w + 1] - o;
+    const int o = a.off[w], N = a.cnt[w];
     int* row = a.row + o + w;
     int acc = 0;
     for (int i = 0; i < N; i++) { int t = row[i]; row[i] = acc; acc += t; }
@@ -229,7 +232,8 @@ __global__ void __launch_bounds__(128) wide_near_fill(WArgs a)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= a.n_bodies) return;
-    const int w = a.body_world[g], o = a.off[w], N = a.off[w + 1] - o, i = g - o;
+    const int w = a.body_world[g], o = a.off[w], N = a.cnt[w], i = g - o;
+    if (i >= N) return;
     const double* cu = a.cull + (size_t)o * kCullF;
     unsigned* near = w_near(a, w);
     unsigned char* hit = w_hit(a, w);
@@ -547,7 +551,7 @@ __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first
     const Entry& e = a.entries[a.hitlist[KIND == 3 ? first + c2 - 1u - t : first + t]];
     const int w = e.w;
     if (a.wflags[w]) return;
-    const int o = a.off[w], N = a.off[w + 1] - o;
+    const int o = a.off[w], N = a.cnt[w];
     const int i = e.ij & 0xffff, j = e.ij >> 16;
     Par pi, pj; Dyn di, dj;
     ld_par(a.par, 0, o + i, pi);
@@ -810,7 +814,8 @@ __global__ void __launch_bounds__(128) wide_verify(WArgs a)
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= a.n_bodies) return;
     const int w = a.body_world[g];
-    const int o = a.off[w], N = a.off[w + 1] - o, b = g - o;
+    const int o = a.off[w], N = a.cnt[w], b = g - o;
+    if (b >= N) return;
     const double* cu = a.cull + (size_t)o * kCullF;
     const double d2 = cu[6 * N + b], m2 = cu[5 * N + b];
     if (d2 <= m2) return;
@@ -839,7 +844,7 @@ __global__ void __launch_bounds__(128) wide_static_fold(WArgs a)
     if (!a.isstat[g]) return;
     const int w = a.body_world[g];
     if (a.wflags[w]) return;
-    const int o = a.off[w], N = a.off[w + 1] - o, b = g - o, K = a.K[w];
+    const int o = a.off[w], N = a.cnt[w], b = g - o, K = a.K[w];
     Par p; ld_par(a.par, 0, g, p);
     double* cb = a.cur + (size_t)g * kDynF;
     double* pb = a.pred + (size_t)g * kDynF;
@@ -885,14 +890,16 @@ __global__ void __launch_bounds__(kTile) wide_final(WArgs a)
     const int t = threadIdx.x, g = g0 + t;
     int w = 0;
     bool flagged = false;
+    bool body = false;
     if (t < n) {
         w = a.body_world[g];
+        body = g - a.off[w] < a.cnt[w];  // (a spare slot holds no body: its record travels with the tile, unread)
         flagged = a.wflags[w] != 0;  // the fused kernel redoes this world from the published state
         if (flagged) any_flagged = 1;
-        else a.nprev[g] = a.nhit[g];
+        else if (body) a.nprev[g] = a.nhit[g];
     }
     pst_tma::mbar_wait(&bar, 0);
-    if (t < n && !flagged) {
+    if (body && !flagged) {
         const double* q = s_t + (size_t)t * kDynF;
         bool bad = false;
 #pragma unroll

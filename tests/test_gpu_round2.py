@@ -163,6 +163,30 @@ def test_step_async_under_graph_capture():
     ref.Step(10)
     assert_state_bits(ref.State(), sim.State(), "graph replay of the fused step")
     sim.close(); ref.close()
+    # the batch-wide path: its rounds are counted on the device (no host round trip), so a step can be captured too
+    import os as _os
+    _os.environ["PS_B200_PATH"] = "wide"
+    try:
+        built3, cfg3 = _built(scenes.c3_mixed128, 0, 12, n_boxes=12, n_spheres=12)
+        wsim = BatchSimulator(None, cfg3, device=0, _prebuilt=built3)
+        wref = BatchSimulator(None, cfg3, device=0, _prebuilt=built3)
+        assert wsim.batch.schedule()["path"] == "wide"
+        wsim.Step(40); wref.Step(40)
+        gw = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s):
+            gw.capture_begin()
+            wsim.batch.step_async(1, s.cuda_stream)
+            gw.capture_end()
+        torch.cuda.synchronize()
+        for _ in range(6):
+            gw.replay()
+        torch.cuda.synchronize()
+        wref.Step(6)
+        assert_state_bits(wref.State(), wsim.State(), "graph replay of the batch-wide step")
+        wsim.close(); wref.close()
+    finally:
+        del _os.environ["PS_B200_PATH"]
     protos, tcfg = scenes.stack_scene()
     tree = BatchSimulator([protos], tcfg, device=0)
     g2 = torch.cuda.CUDAGraph()
@@ -261,3 +285,80 @@ def test_mass_and_static_inertia_are_validated():
     bad["inertia_inv"][stat] = (0.0, 0.5, 0.0)
     with pytest.raises(ValueError):
         _native.Batch(bad, off, to_native_config(Configuration()), device=0)
+
+
+def _add_to_both(sim, oracles, world, proto):
+    one = P.empty_bodies(1)
+    P.build_into(one, 0, proto)
+    new_id = sim.AddObject(world, proto)
+    assert oracles[world].add_body(one) == new_id
+    return new_id
+
+
+def test_add_body_is_incremental_and_exact():
+    """Simulator.AddObject (SimulatorState.fs:89-107) on a large batch: a world with a spare slot takes the body as a
+    record write (100 bodies into a 4096-world batch in a few milliseconds, not a re-upload each), a full world triggers
+    ONE re-layout; either way the batch steps on exactly like the oracle worlds that got the same bodies"""
+    import time
+    from oracle.oracle import OracleWorld
+    built, cfg = _built(scenes.c2_spheres64, 0, 4096)
+    sim = BatchSimulator(None, cfg, device=0, _prebuilt=built)
+    sim.Step(20)
+    touched = [17 * q % 4096 for q in range(100)]          # 100 different worlds
+    oracles = {w: OracleWorld(built[w], to_native_config(cfg)) for w in set(touched) | {5}}
+    for o in oracles.values():
+        o.step(20)
+    rng = scenes.SplitMix64(99)
+    protos = [P.createDefaultSphere(rng.uniform(0.2, 0.4)).With(Position=(rng.uniform(-2, 2), rng.uniform(-2, 2), 6.0 + rng.uniform(0, 1)), Mass=rng.uniform(1, 5))
+              for _ in touched]
+    t0 = time.perf_counter()
+    for w, p in zip(touched, protos):
+        sim.AddObject(w, p)
+    dt = time.perf_counter() - t0
+    for w, p in zip(touched, protos):
+        one = P.empty_bodies(1); P.build_into(one, 0, p)
+        assert oracles[w].add_body(one) == 65
+    assert dt < 0.25, f"100 AddObject calls took {dt * 1e3:.1f} ms"   # (a re-upload of this batch per call is ~100x that)
+    # fill world 5 beyond its spare slots: the fifth addition lays the batch out again
+    for k in range(7):
+        _add_to_both(sim, oracles, 5, P.createDefaultCube(0.4).With(Position=(0.3 * k - 1.0, 0.5, 7.0 + 0.6 * k), Mass=3.0))
+    sim.Step(60)
+    st = sim.Stats()
+    assert st["nan_worlds"] == 0
+    for w, o in oracles.items():
+        o.step(60)
+        got, ref = sim.WorldState(w), o.get_state()
+        assert len(got["pos"]) == len(ref["pos"])
+        for k in ("pos", "vel", "rot"):
+            assert same_bits(got[k], ref[k]), f"world {w} {k} after AddObject"
+    assert sim.batch.num_bodies()[0] == 4096 * 65 + 107
+    sim.close()
+    print(f"100 AddObject calls on 4096 worlds: {dt * 1e3:.2f} ms")
+
+
+def test_add_body_without_spare_slots_and_on_the_wide_path(monkeypatch):
+    """PS_B200_SPARE=0: every addition is a re-layout (the general route); the batch-wide path sees added bodies too"""
+    from oracle.oracle import OracleWorld
+    monkeypatch.setenv("PS_B200_SPARE", "0")
+    monkeypatch.setenv("PS_B200_PATH", "wide")
+    worlds = [scenes.c3_mixed128(w, n_boxes=6, n_spheres=6)[0] for w in range(9)]   # 13 bodies: N / 16 = 0 spare slots
+    cfg = scenes.c3_mixed128(0)[1]
+    sim = BatchSimulator(worlds, cfg, device=0)
+    oracles = [OracleWorld(P.build_world(p), to_native_config(cfg)) for p in worlds]
+    sim.Step(15)
+    for o in oracles:
+        o.step(15)
+    _add_to_both(sim, oracles, 3, P.createDefaultCube(0.5).With(Position=(0.0, 0.0, 5.0), Mass=20.0))
+    _add_to_both(sim, oracles, 3, P.createDefaultSphere(0.3).With(Position=(0.2, 0.1, 6.5), Mass=2.0))
+    _add_to_both(sim, oracles, 8, P.createDefaultBox(3.0, 3.0, 0.2).With(Position=(0.0, 0.0, 3.0), Mass=P.INFINITE, UseGravity=False))  # a second static body
+    monkeypatch.setenv("PS_B200_SPARE", "4")
+    _add_to_both(sim, oracles, 8, P.createDefaultSphere(0.3).With(Position=(0.5, 0.5, 8.0), Mass=2.0))  # re-layout, now with spare slots
+    _add_to_both(sim, oracles, 8, P.createDefaultSphere(0.25).With(Position=(-0.5, 0.5, 9.0), Mass=2.0))  # record write
+    sim.Step(80)
+    for w, o in enumerate(oracles):
+        o.step(80)
+        got, ref = sim.WorldState(w), o.get_state()
+        dyn = ~np.isinf(np.concatenate([sim._worlds[w]["mass"]]))
+        for k in ("pos", "vel", "rot"):
+            assert same_bits(got[k][dyn], ref[k][dyn]), f"world {w} {k}"
+    sim.close()
