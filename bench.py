@@ -138,6 +138,27 @@ def _native_joints(built, joints):
     return out
 
 
+def bind_near_gpu(local):
+    """pin this rank to the CPU cores of its GPU's NUMA node BEFORE any pinned host buffer is allocated (first touch puts
+    the pages on that node): the end-to-end leg moves the whole state over PCIe both ways every step"""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{dev}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"pci": dev, "numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001  (containers without sysfs PCI entries: stay unbound, say so)
+        return {"unbound": str(e)[:80]}
+
+
 def workload_config(name, per_gpu, settle, world, sched=None):
     """the `config` object of the JSON line: identical keys in both arms (ours / --impl reference)"""
     return {"workload": f"{name}: {WORKLOADS[name][3]}", "worlds_per_gpu": per_gpu, "dynamic_bodies_per_world": WORKLOADS[name][2],
@@ -336,6 +357,10 @@ def run_workload(name, args, rank, local, world, main_line):
            "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": bytes_state, "d2h_bytes_per_step": bytes_state,
                    "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
                    "what": "ps_batch_step_host(pinned host state in, 1 step, pinned host state out) per step: H2D + step + D2H inside the timed region, pipelined over world chunks"}}
+    copy_ms = max(res["e2e"]["ms_per_step"] - kernel_ms, 1e-9)
+    res["e2e"]["copy_GBps_both_ways"] = 2 * bytes_state / (copy_ms * 1e-3) / 1e9
+    res["e2e"]["bound"] = ("host<->device copies: (e2e - device step) time moves h2d + d2h bytes at the rate above; a step of the batch-wide path is one "
+                           "dependent chain of rounds over the WHOLE batch, so the copies cannot hide behind it chunk by chunk (the fused path does that)")
     if e2e_seq_s is not None:
         res["e2e"]["sequential_calls_value_this_rank"] = n_dyn * per_gpu * e2e_steps / e2e_seq_s
         res["e2e"]["sequential_calls_what"] = "ps_batch_set_state + ps_batch_step(1) + ps_batch_get_state, one after the other (informational)"
@@ -375,6 +400,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
     torch.cuda.set_device(local)
+    affinity = bind_near_gpu(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name = args.workload
@@ -432,6 +458,7 @@ def main():
             "stats": r["stats"],
             "valid": r["stats"]["nan_worlds"] == 0,
             "wall_s_timed_region": r["wall"],
+            "affinity_rank0": affinity,
         }
         if r["stats"]["nan_worlds"]:
             line["invalid_reason"] = f"{r['stats']['nan_worlds']} worlds hold NaN/inf state: the rate is not a meaningful workload rate"

@@ -159,9 +159,10 @@ int ps_batch_step(void* handle, int32_t n_steps);
 /* same, but on a caller stream (cudaStream_t passed as void*) and without the final synchronise.  The call orders
  * the caller's stream after everything the handle's own stream holds, and the handle's stream (so
  * ps_batch_synchronize and every later call on the handle) after the work launched here.  CUDA-graph capture of the
- * caller's stream: supported for batches that step without a host round trip (ps_batch_schedule reports
- * host_syncs_per_step = 0: the fused kernel and the device-driven batch-wide path); a SpatialTree-order batch returns
- * PS_ERR_INVALID_OPERATION while capturing.  During a capture the two orderings above are the capture's business. */
+ * caller's stream: supported for every Dummy-order batch — the fused kernel is one launch, the batch-wide path counts its
+ * rounds on the device (no host round trip inside a step); a SpatialTree-order batch (one host round trip per step for
+ * the tree) returns PS_ERR_INVALID_OPERATION while capturing.  During a capture the two orderings above are the
+ * capture's business. */
 int ps_batch_step_async(void* handle, int32_t n_steps, void* cuda_stream);
 int ps_batch_synchronize(void* handle);
 
@@ -196,7 +197,10 @@ int ps_batch_get_candidates(void* handle, int32_t world, int32_t* n_pairs, int32
 /* Simulator.ApplyImpulse (Simulator.fs:101-111 -> RigidBody.fs:194-197) */
 int ps_batch_apply_impulse(void* handle, int32_t world, int32_t body, const double impulse[3],
                            const double offset[3]);
-/* Simulator.AddObject (Simulator.fs:91-99): id = max id + 1 (SimulatorState.fs:90-92); `one` holds 1 body */
+/* Simulator.AddObject (Simulator.fs:91-99): id = max id + 1 (SimulatorState.fs:90-92); `one` holds 1 body.
+ * Every world owns a few spare slots on the device: while one is free the new body is a record write (tens of
+ * microseconds, whatever the batch size); a full world lays the batch out again once.  Refusals (more than 1024 bodies,
+ * a body outside the SpatialTree's space) leave the batch as it was. */
 int ps_batch_add_body(void* handle, int32_t world, const ps_bodies_view* one);
 /* Simulator.Reset (Simulator.fs:113-121): back to the state given at create; added bodies are dropped */
 int ps_batch_reset(void* handle);

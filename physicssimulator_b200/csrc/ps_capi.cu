@@ -112,6 +112,7 @@ struct Batch {
     bool est_pending = false, est_valid = false;
     std::vector<unsigned> est;       // host copy the launches are sized from
     int rounds_grid = 0;       // CTAs of the cooperative rounds kernel (all resident at once)
+    int sm_count = 148;
     unsigned team_max = 0;     // box-box survivors per round up to which every survivor gets a team of 8 lanes
     unsigned long long* d_tmp_pen = nullptr;
     double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // PS_B200_WIDE_PROF: setup, integrate, ss, sb, bb, resolve, tail, fused
@@ -471,6 +472,7 @@ int upload(Batch* B, bool with_state)
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psw::wide_rounds, 128, 0));
             CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, B->device));
             CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, B->device));
+            B->sm_count = sms;
             B->rounds_grid = per_sm * sms;
             B->wide_device_rounds = coop != 0 && B->rounds_grid > 0;
             if (const char* e = getenv("PS_B200_WIDE_HOST_ROUNDS")) { if (atoi(e) != 0) B->wide_device_rounds = false; }  // tuning/profiling: one launch per stage and round, driven by the host
@@ -539,8 +541,10 @@ int upload(Batch* B, bool with_state)
         for (int w = 0; w < B->n_worlds; w++) {
             std::vector<int> seen(h.off[w + 1] - h.off[w], 0);
             for (int q = joff[w + 1] - 1; q >= joff[w]; q--) {
-                if (!seen[ja[q]]) { last[q] |= 1; seen[ja[q]] = 1; }
-                if (!seen[jb[q]]) { last[q] |= 2; seen[jb[q]] = 1; }
+                // targets of the two results: lower id, higher id (Q15); within a joint the second write comes last
+                const int t1 = std::min(ja[q], jb[q]), t2 = std::max(ja[q], jb[q]);
+                if (t1 != t2 && !seen[t2]) { last[q] |= 2; seen[t2] = 1; }
+                if (!seen[t1]) { last[q] |= 1; seen[t1] = 1; }
             }
         }
         CK(cudaMalloc(&B->d_joff, joff.size() * sizeof(int)));
@@ -774,9 +778,10 @@ int ps_batch_create(void** handle, const ps_bodies_view* bodies, const ps_joints
             int N = B->init.off[w + 1] - B->init.off[w];
             int a = B->joints.a[q], b = B->joints.b[q];
             if (a < 0 || b < 0 || a >= N || b >= N) { delete B; return fail(PS_ERR_OUT_OF_RANGE, "joint %d: body id out of range", q); }
-            // changePhysicalObjects pairs id-sorted objects with pair-ordered results (Q15): a > b would swap
-            // the two bodies; that is rejected instead of reproduced.
-            if (a >= b) { delete B; return fail(PS_ERR_INVALID_ARGUMENT, "joint %d: body_a must be < body_b", q); }
+            // a > b is taken as given: changePhysicalObjects' pairing of id-sorted objects with joint-ordered results (quirk
+            // Q15: the two bodies swap states) is reproduced by the step kernel.  a == b: the reference zips ONE object
+            // with TWO results and List.zip throws ArgumentException (SimulatorState.fs:153-160).
+            if (a == b) { delete B; return fail(PS_ERR_INVALID_ARGUMENT, "joint %d: a body cannot be joined to itself (List.zip: lists of different lengths)", q); }
         }
     }
     B->cur = B->init;
@@ -985,14 +990,12 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         CK(cudaStreamIsCapturing(st, &cap));
         const bool capturing = cap != cudaStreamCaptureStatusNone;
-        if (B->est_pending && cudaEventQuery(B->est_ready) == cudaSuccess) {
+        if (!capturing && B->est_pending && cudaEventQuery(B->est_ready) == cudaSuccess) {  // (an event query would invalidate a capture)
             B->est.assign(B->h_est, B->h_est + 3 * kBuckets + 8);
             B->est_pending = false;
             B->est_valid = true;
         }
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, B->device);
-        const unsigned dflt = (unsigned)sms * 8;   // no estimate yet: a grid that fills the device, strides do the rest
+        const unsigned dflt = (unsigned)std::max(1, B->sm_count) * 8;   // no estimate yet: a grid that fills the device, strides do the rest
         auto blocks = [&](unsigned n, unsigned per) { return (unsigned)(((unsigned long long)n * 9 / 8 + per - 1) / per) + 4u; };  // estimate + 12 %
         int r_launch = 48;
         const unsigned* hb = B->est_valid ? B->est.data() : nullptr;

@@ -895,8 +895,12 @@ __global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
                         apply_impulse(o1, p1, la, imp);
                         apply_impulse(o2, p2, lb, -imp);
                     }
-                    if (lastf & 1) { st_dyn(s.pred, N, ba, o1); s.last[ba] = 1; }
-                    if (lastf & 2) { st_dyn(s.pred, N, bb, o2); s.last[bb] = 1; }
+                    // changePhysicalObjects (SimulatorState.fs:149-162) pairs the objects in ASCENDING ID order with the
+                    // results in joint order (quirk Q15): the first result goes to the lower id, the second to the higher
+                    // one — for a joint given as (a > b) the two bodies swap states; a self joint keeps the first result
+                    const int t1 = ba < bb ? ba : bb, t2 = ba < bb ? bb : ba;
+                    if (lastf & 1) { st_dyn(s.pred, N, t1, o1); s.last[t1] = 1; }
+                    if ((lastf & 2) && ba != bb) { st_dyn(s.pred, N, t2, o2); s.last[t2] = 1; }
                 }
             }
             __syncwarp();

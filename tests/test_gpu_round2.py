@@ -362,3 +362,31 @@ def test_add_body_without_spare_slots_and_on_the_wide_path(monkeypatch):
         for k in ("pos", "vel", "rot"):
             assert same_bits(got[k][dyn], ref[k][dyn]), f"world {w} {k}"
     sim.close()
+
+
+def test_joints_given_as_hi_lo_swap_the_bodies_like_the_reference():
+    """Q15 (SimulatorState.fs:153-160): changePhysicalObjects zips the id-SORTED objects with the joint-ORDERED results, so a
+    joint given as (a > b) hands each body the other's restored state; reproduced, not rejected.  A self joint throws."""
+    from oracle.oracle import OracleWorld
+    worlds, joints = [], []
+    for w in range(4):
+        p, cfg, j = scenes.c4_chain32(w, n_links=9)
+        j = [(b, a, anchor) if k % 3 == 1 else (a, b, anchor) for k, (a, b, anchor) in enumerate(j)]  # every third joint reversed
+        worlds.append(p)
+        joints.append(j)
+    sim = BatchSimulator(worlds, cfg, joints=joints, device=0)
+    oracles = []
+    for p, js in zip(worlds, joints):
+        b = P.build_world(p)
+        oracles.append(OracleWorld(b, to_native_config(cfg), joints=[(a, bb) + P.ball_socket_local_anchors(b, a, bb, anchor) for (a, bb, anchor) in js]))
+    for n in (1, 7, 40):
+        sim.Step(n)
+        for w, o in enumerate(oracles):
+            o.step(n)
+            got, ref = sim.WorldState(w), o.get_state()
+            for k in ("pos", "vel", "rot"):
+                assert same_bits(got[k], ref[k]), f"reversed joints: world {w} {k} after +{n}"
+    sim.close()
+    p, cfg, j = scenes.c4_chain32(0, n_links=4)
+    with pytest.raises(ValueError):
+        BatchSimulator([p], cfg, joints=[[(2, 2, j[0][2])]], device=0)
