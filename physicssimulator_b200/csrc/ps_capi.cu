@@ -97,7 +97,7 @@ struct Batch {
     int* d_body_world = nullptr;
     unsigned char *d_pvalid = nullptr, *d_nhit = nullptr, *d_isstat = nullptr, *d_isbox = nullptr, *d_always_fused = nullptr;
     int *d_K = nullptr, *d_maxl = nullptr;
-    unsigned *d_wflags = nullptr, *d_bucket = nullptr, *d_bucket_cur = nullptr, *d_hit_cnt = nullptr, *d_hitlist = nullptr, *d_cpool_cur = nullptr;
+    unsigned *d_wflags = nullptr, *d_bucket = nullptr, *d_bucket_cur = nullptr, *d_hit_cnt = nullptr, *d_hitlist = nullptr, *d_hitlist2 = nullptr, *d_cpool_cur = nullptr;
     psw::Entry* d_entries = nullptr;
     Contact* d_cpool = nullptr;
     unsigned entries_cap = 0, cpool_cap = 0;
@@ -287,7 +287,7 @@ void free_device(Batch* B)
     dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cost); dfree(B->d_perm); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
-    dfree(B->d_hitlist); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev); dfree(B->d_cnt); dfree(B->d_abi_off);
+    dfree(B->d_hitlist); dfree(B->d_hitlist2); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev); dfree(B->d_cnt); dfree(B->d_abi_off);
     if (B->h_bucket) { cudaFreeHost(B->h_bucket); B->h_bucket = nullptr; }
     if (B->h_est) { cudaFreeHost(B->h_est); B->h_est = nullptr; }
     if (B->est_ready) { cudaEventDestroy(B->est_ready); B->est_ready = nullptr; }
@@ -453,11 +453,12 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_always_fused, nw));
         CK(cudaMalloc(&B->d_K, nw * sizeof(int))); CK(cudaMalloc(&B->d_maxl, nw * sizeof(int))); CK(cudaMalloc(&B->d_wflags, nw * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_bucket, (psw::kBuckets + 1) * sizeof(unsigned))); CK(cudaMalloc(&B->d_bucket_cur, psw::kBuckets * sizeof(unsigned)));
-        CK(cudaMalloc(&B->d_hit_cnt, psw::kBuckets * sizeof(unsigned))); CK(cudaMalloc(&B->d_cpool_cur, (psw::kWideMaxLevels + 2) * sizeof(unsigned)));
+        CK(cudaMalloc(&B->d_hit_cnt, (size_t)(psw::kWideMaxLevels + 2) * psw::kHitSlots * sizeof(unsigned))); CK(cudaMalloc(&B->d_cpool_cur, (psw::kWideMaxLevels + 2) * sizeof(unsigned)));
         B->entries_cap = (unsigned)std::min<size_t>(16 * nb + 1024, 400u << 20);
         B->cpool_cap = (unsigned)std::min<size_t>(4 * nb + 4096, 200u << 20);
         CK(cudaMalloc(&B->d_entries, (size_t)B->entries_cap * sizeof(psw::Entry)));
         CK(cudaMalloc(&B->d_hitlist, (size_t)B->entries_cap * sizeof(unsigned)));
+        CK(cudaMalloc(&B->d_hitlist2, (size_t)B->entries_cap * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_cpool, (size_t)B->cpool_cap * sizeof(Contact)));
         CK(cudaMallocHost(&B->h_bucket, (psw::kBuckets + 1) * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_tmp, nw * 6 * sizeof(unsigned)));
@@ -465,7 +466,7 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_surv_cnt, (psw::kWideMaxLevels + 2) * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_tmp_pen, nw * sizeof(unsigned long long)));
         CK(cudaMalloc(&B->d_nlev, sizeof(int)));
-        CK(cudaMallocHost(&B->h_est, (size_t)(3 * psw::kBuckets + 8) * sizeof(unsigned)));
+        CK(cudaMallocHost(&B->h_est, (size_t)(4 * psw::kBuckets + 8) * sizeof(unsigned)));
         CK(cudaEventCreateWithFlags(&B->est_ready, cudaEventDisableTiming));
         {   // the rounds of a step run in one cooperative launch whose CTAs must all be resident
             int per_sm = 0, sms = 0, coop = 0;
@@ -828,14 +829,14 @@ int ps_batch_destroy(void* handle)
     }
 #endif
     if (getenv("PS_B200_WIDE_PROF") && !B->prof_round.empty()) {
-        std::vector<unsigned> hc(psw::kBuckets), sc(psw::kWideMaxLevels + 2);
+        std::vector<unsigned> hc((size_t)(psw::kWideMaxLevels + 2) * psw::kHitSlots), sc(psw::kWideMaxLevels + 2);
         cudaMemcpy(hc.data(), B->d_hit_cnt, hc.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
         cudaMemcpy(sc.data(), B->d_surv_cnt, sc.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[ps_b200 wide profile] last step, per round: pairs ss/sb/bb | bb survivors | hits ss/sb/bb | ms detect, bb, resolve\n");
         for (size_t r = 0; r * 6 < B->prof_round.size(); r++) {
             const float* q = &B->prof_round[r * 6];
             fprintf(stderr, "  round %3zu: %7.0f %7.0f %7.0f | %7u | %7u %7u %7u | %.3f %.3f %.3f\n", r + 1, q[0], q[1], q[2], sc[r + 1],
-                    hc[(r + 1) * 4], hc[(r + 1) * 4 + 1], hc[(r + 1) * 4 + 2] + hc[(r + 1) * 4 + 3], q[3], q[4], q[5]);
+                    hc[(r + 1) * 8], hc[(r + 1) * 8 + 1], hc[(r + 1) * 8 + 2] + hc[(r + 1) * 8 + 3] + hc[(r + 1) * 8 + 4] + hc[(r + 1) * 8 + 5], q[3], q[4], q[5]);
         }
     }
     free_device(B);
@@ -951,7 +952,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off;
     a.K = B->d_K; a.maxl = B->d_maxl; a.wflags = B->d_wflags; a.always_fused = B->d_always_fused;
     a.bucket = B->d_bucket; a.bucket_cur = B->d_bucket_cur; a.entries = B->d_entries; a.entries_cap = B->entries_cap;
-    a.hit_cnt = B->d_hit_cnt; a.hitlist = B->d_hitlist; a.cpool = B->d_cpool; a.cpool_cap = B->cpool_cap; a.cpool_cur = B->d_cpool_cur;
+    a.hit_cnt = B->d_hit_cnt; a.hitlist = B->d_hitlist; a.hitlist2 = B->d_hitlist2; a.cpool = B->d_cpool; a.cpool_cap = B->cpool_cap; a.cpool_cur = B->d_cpool_cur;
     a.stats = B->d_stats; a.tmp = B->d_tmp; a.tmp_pen = B->d_tmp_pen; a.surv = B->d_surv; a.surv_cnt = B->d_surv_cnt;
     a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
@@ -991,7 +992,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
         CK(cudaStreamIsCapturing(st, &cap));
         const bool capturing = cap != cudaStreamCaptureStatusNone;
         if (!capturing && B->est_pending && cudaEventQuery(B->est_ready) == cudaSuccess) {  // (an event query would invalidate a capture)
-            B->est.assign(B->h_est, B->h_est + 3 * kBuckets + 8);
+            B->est.assign(B->h_est, B->h_est + 4 * kBuckets + 8);
             B->est_pending = false;
             B->est_valid = true;
         }
@@ -1000,7 +1001,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
         int r_launch = 48;
         const unsigned* hb = B->est_valid ? B->est.data() : nullptr;
         const unsigned* hh = hb ? hb + kBuckets + 1 : nullptr;      // hit counts per (level, kind)
-        const unsigned* hs = hb ? hb + 2 * kBuckets + 1 : nullptr;  // survivors per level
+        const unsigned* hs = hb ? hb + 3 * kBuckets + 1 : nullptr;  // survivors per level
         if (hb) {
             int top = 0;
             for (int r = 1; r <= kWideMaxLevels; r++) if (hb[(r + 1) * 4] > hb[r * 4]) top = r;
@@ -1013,7 +1014,8 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
                 g1 = blocks(c0, 128) + blocks(c1, 128) + blocks(c2, 128);
                 ns_est = hs[r];
                 g2 = blocks(ns_est, 128); g2t = blocks(ns_est, 16);
-                g3 = blocks(hh[r * 4], 128) + blocks(hh[r * 4 + 1], 128) + blocks(hh[r * 4 + 2], 128) + blocks(hh[r * 4 + 3], 128);
+                g3 = 0;
+                for (int k = 0; k < 6; k++) g3 += blocks(hh[r * psw::kHitSlots + k], 128);
             }
             wide_round_detect_d<<<g1, 128, 0, st>>>(a, r);
             if (ns_est <= B->team_max) wide_round_bb_team_d<<<g2t, 128, 0, st>>>(a, r);
@@ -1029,8 +1031,8 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
         }
         if (!capturing && !B->est_pending) {  // this step's counts, for the grids of a later step
             CK(cudaMemcpyAsync(B->h_est, B->d_bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(B->h_est + kBuckets + 1, B->d_hit_cnt, kBuckets * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(B->h_est + 2 * kBuckets + 1, B->d_surv_cnt, (kWideMaxLevels + 2) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(B->h_est + kBuckets + 1, B->d_hit_cnt, (size_t)(kWideMaxLevels + 2) * kHitSlots * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(B->h_est + 3 * kBuckets + 1, B->d_surv_cnt, (kWideMaxLevels + 2) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(B->est_ready, st));
             B->est_pending = true;
         }

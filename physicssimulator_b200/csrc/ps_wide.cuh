@@ -36,6 +36,7 @@ using namespace psk;
 
 constexpr int kWideMaxLevels = 1022;
 constexpr int kBuckets = (kWideMaxLevels + 2) * 4;
+constexpr int kHitSlots = 8;  // hit counters per level (6 used)
 
 struct __align__(16) Entry {  // one near pair of the batch, sorted by (level, kind); written and read as one uint4
     int w;           // world
@@ -59,8 +60,9 @@ struct WArgs {
     unsigned* bucket;            // [kBuckets+1] counts, then exclusive starts
     unsigned* bucket_cur;        // [kBuckets]
     Entry* entries; unsigned entries_cap;
-    unsigned* hit_cnt;           // per (level, kind) bucket
-    unsigned* hitlist;           // [entries_cap], a bucket's hits are listed from the bucket's start
+    unsigned* hit_cnt;           // [level][kHitSlots]: sphere-sphere, sphere-box, box manifolds by size class A, B, C, D
+    unsigned* hitlist;           // [entries_cap], a bucket's hits are listed from the bucket's start (box: class A; class D from its end)
+    unsigned* hitlist2;          // [entries_cap], box buckets only: class B from the start, class C from the end
     Contact* cpool; unsigned cpool_cap; unsigned* cpool_cur;  // cursor per level
     unsigned* surv;              // [entries_cap] box-box pairs the quick test could not separate (listed from the bucket's start)
     unsigned* surv_cnt;          // per level
@@ -115,7 +117,7 @@ __global__ void wide_reset(WArgs a)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t <= kBuckets) a.bucket[t] = 0;
     if (t < kBuckets) a.bucket_cur[t] = 0;
-    if (t < kBuckets) a.hit_cnt[t] = 0;
+    for (int q = t; q < (kWideMaxLevels + 2) * kHitSlots; q += gridDim.x * blockDim.x) a.hit_cnt[q] = 0;
     if (t < kWideMaxLevels + 2) { a.cpool_cur[t] = 0; a.surv_cnt[t] = 0; }
     if (t == 0) a.nlev[0] = 0;
     if (t < a.n_worlds) {
@@ -412,20 +414,25 @@ __device__ __forceinline__ void wide_bb_quick_body(const WArgs& a, unsigned firs
 }
 
 // a colliding pair whose nc contacts sit at cpool[cf ..): entry, the round's hit list, max penetration, recording
-constexpr int kSmallManifold = 2;
 __device__ __forceinline__ void wide_publish_hit(const WArgs& a, Entry& e, unsigned ei, unsigned first, unsigned bucket_count, int level, int kind, int w,
                                                  int i, int j, int nc, unsigned cf, double mp)
 {
     e.knc |= (unsigned)nc << 24; e.cfirst = cf;
-    // Box pairs: a warp of the solve runs as long as its largest manifold, so manifolds of one or two contacts (edge
-    // contacts, corners) and larger ones (faces) are listed apart — small ones from the front of the bucket's region of
-    // the hit list, large ones from its back (the region holds every box pair of the round; hit_cnt[4 level + 3] counts
-    // the large ones).  ncu before: 16 of 32 threads per instruction in the solve.
-    if (kind == 2 && nc > kSmallManifold) {
-        const unsigned slot = agg_reserve(&a.hit_cnt[level * 4 + 3], 1u);
-        a.hitlist[first + bucket_count - 1u - slot] = ei;
+    // Box pairs: a warp of the solve walks as many contacts as its LARGEST manifold holds (the walk is warp-uniform), so the
+    // manifolds are listed by size class — A: 1-2 contacts (edge contacts, corners), B: 3-4 (a face), C: 5-6, D: 7 and more —
+    // each class in its own stretch: A from the front and D from the back of the box bucket's region of the hit list, B
+    // and C the same way in a second list.  (ncu before any sorting: 16 of 32 threads per instruction in the solve; with
+    // two classes every "large" warp still ran the 8-contact walk.)
+    if (kind == 2) {
+        const int cls = nc <= 2 ? 0 : (nc <= 4 ? 1 : (nc <= 6 ? 2 : 3));
+        unsigned slot = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++)  // (agg_reserve pools the lanes that arrive together on ONE counter: one class at a time)
+            if (cls == c) slot = agg_reserve(&a.hit_cnt[level * kHitSlots + 2 + c], 1u);
+        unsigned* list = (cls == 0 || cls == 3) ? a.hitlist : a.hitlist2;
+        list[(cls >= 2) ? first + bucket_count - 1u - slot : first + slot] = ei;
     } else {
-        const unsigned slot = agg_reserve(&a.hit_cnt[level * 4 + kind], 1u);
+        const unsigned slot = agg_reserve(&a.hit_cnt[level * kHitSlots + kind], 1u);
         a.hitlist[first + slot] = ei;
     }
     const unsigned long long mpb = (unsigned long long)__double_as_longlong(mp);
@@ -542,13 +549,29 @@ static __device__ __noinline__ void wide_resolve_literal(const WArgs& a, int gi,
 // solve + write-back: thread per colliding pair of bucket (level, kind).  A body the solve changed is integrated
 // again right here (its next use — the next pair or the final sweep — needs exactly this predicted copy), which
 // keeps that work in a dense kernel; its margin only matters if a later near pair will test it.
+// entry of hit t of slot KIND of a round: 0 sphere-sphere, 1 sphere-box, 2..5 box manifolds of size class A..D
+// (wide_publish_hit); false past the end
+__device__ __forceinline__ bool wide_pick_hit(const WArgs& a, int kind, unsigned first, unsigned c2, int level, unsigned t, unsigned& ei)
+{
+    if (t >= a.hit_cnt[level * kHitSlots + kind]) return false;
+    const unsigned* list = (kind == 3 || kind == 4) ? a.hitlist2 : a.hitlist;
+    ei = list[kind >= 4 ? first + c2 - 1u - t : first + t];
+    return true;
+}
+template <bool BOX>
+__device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, int level);
 template <int KIND>
 __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first, unsigned c2, int level, unsigned t)
 {
-    // KIND 3 = the large box manifolds, listed from the back of the box bucket's region (wide_publish_hit)
+    unsigned ei;
+    if (wide_pick_hit(a, KIND, first, c2, level, t, ei)) wide_resolve_entry<(KIND >= 2)>(a, ei, level);
+}
+template <bool BOX>
+__device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, int level)
+{
+    constexpr int KIND = BOX ? 2 : 0;
     PS_CLK_BEGIN(KIND >= 2 && level >= 3)
-    if (t >= a.hit_cnt[level * 4 + KIND]) return;
-    const Entry& e = a.entries[a.hitlist[KIND == 3 ? first + c2 - 1u - t : first + t]];
+    const Entry& e = a.entries[ei];
     const int w = e.w;
     if (a.wflags[w]) return;
     const int o = a.off[w], N = a.cnt[w];
@@ -632,12 +655,14 @@ __global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_resolve(WArgs a,
 {
     const unsigned b0 = (c0 + 127) / 128, b1 = (c1 + 127) / 128;
     const unsigned blk = blockIdx.x;
-    // (host-driven form: the box bucket's CTAs cover its small manifolds from the front and its large ones from the back)
+    // (host-driven form: thread t of the box bucket takes manifold t of every size class)
     if (blk < b0) wide_resolve_body<0>(a, first, 0u, level, blk * 128 + threadIdx.x);
     else if (blk < b0 + b1) wide_resolve_body<1>(a, first + c0, 0u, level, (blk - b0) * 128 + threadIdx.x);
     else {
-        wide_resolve_body<2>(a, first + c0 + c1, c2, level, (blk - b0 - b1) * 128 + threadIdx.x);
+        wide_resolve_body<5>(a, first + c0 + c1, c2, level, (blk - b0 - b1) * 128 + threadIdx.x);
+        wide_resolve_body<4>(a, first + c0 + c1, c2, level, (blk - b0 - b1) * 128 + threadIdx.x);
         wide_resolve_body<3>(a, first + c0 + c1, c2, level, (blk - b0 - b1) * 128 + threadIdx.x);
+        wide_resolve_body<2>(a, first + c0 + c1, c2, level, (blk - b0 - b1) * 128 + threadIdx.x);
     }
 }
 
@@ -741,13 +766,20 @@ __global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_resolve_d(WArgs 
 {
     if (r > a.nlev[0] || a.bucket[kBuckets] > a.entries_cap) return;
     const RoundCounts q = round_counts(a, r);
-    const unsigned h0 = a.hit_cnt[r * 4], h1 = a.hit_cnt[r * 4 + 1], h2 = a.hit_cnt[r * 4 + 2], h3 = a.hit_cnt[r * 4 + 3];
-    const unsigned b0 = (h0 + 127) / 128, b1 = (h1 + 127) / 128, b2 = (h2 + 127) / 128, b3 = (h3 + 127) / 128;
-    for (unsigned blk = blockIdx.x; blk < b0 + b1 + b2 + b3; blk += gridDim.x) {  // the large manifolds first: they are the long ones
-        if (blk < b3) wide_resolve_body<3>(a, q.first + q.c0 + q.c1, q.c2, r, blk * 128 + threadIdx.x);
-        else if (blk < b3 + b2) wide_resolve_body<2>(a, q.first + q.c0 + q.c1, q.c2, r, (blk - b3) * 128 + threadIdx.x);
-        else if (blk < b3 + b2 + b1) wide_resolve_body<1>(a, q.first + q.c0, 0u, r, (blk - b3 - b2) * 128 + threadIdx.x);
-        else wide_resolve_body<0>(a, q.first, 0u, r, (blk - b3 - b2 - b1) * 128 + threadIdx.x);
+    const unsigned* hc = a.hit_cnt + r * kHitSlots;
+    unsigned nb[6], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { nb[k] = (hc[k] + 127) / 128; tot += nb[k]; }
+    const unsigned fbb = q.first + q.c0 + q.c1;
+    for (unsigned blk = blockIdx.x; blk < tot; blk += gridDim.x) {  // the largest manifolds first: they are the long ones
+        unsigned b = blk;
+        int kind = 5;
+        while (kind > 0 && b >= nb[kind]) { b -= nb[kind]; kind--; }
+        const unsigned fk = kind >= 2 ? fbb : (kind == 1 ? q.first + q.c0 : q.first);
+        unsigned ei;
+        if (!wide_pick_hit(a, kind, fk, q.c2, r, b * 128 + threadIdx.x, ei)) continue;
+        if (kind >= 2) wide_resolve_entry<true>(a, ei, r);   // (one copy of each solver in the kernel)
+        else wide_resolve_entry<false>(a, ei, r);
     }
 }
 
@@ -792,14 +824,19 @@ __global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_rounds(WArgs a, int r_
             grid.sync();
         }
         {   // stage 3
-            const unsigned h0 = __ldcg(&a.hit_cnt[r * 4]), h1 = __ldcg(&a.hit_cnt[r * 4 + 1]), h2 = __ldcg(&a.hit_cnt[r * 4 + 2]), h3 = __ldcg(&a.hit_cnt[r * 4 + 3]);
-            const unsigned ch0 = (h0 + 31) / 32, ch1 = (h1 + 31) / 32, ch2 = (h2 + 31) / 32, ch3 = (h3 + 31) / 32;
-            // the large manifolds first: they are the long ones
-            for (unsigned c = gw; c < ch0 + ch1 + ch2 + ch3; c += nw) {
-                if (c < ch3) wide_resolve_body<3>(a, first + c0 + c1, c2, r, c * 32 + lane);
-                else if (c < ch3 + ch2) wide_resolve_body<2>(a, first + c0 + c1, c2, r, (c - ch3) * 32 + lane);
-                else if (c < ch3 + ch2 + ch1) wide_resolve_body<1>(a, first + c0, 0u, r, (c - ch3 - ch2) * 32 + lane);
-                else wide_resolve_body<0>(a, first, 0u, r, (c - ch3 - ch2 - ch1) * 32 + lane);
+            unsigned nch[6], tot = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) { nch[k] = (__ldcg(&a.hit_cnt[r * kHitSlots + k]) + 31) / 32; tot += nch[k]; }
+            const unsigned fbb = first + c0 + c1;
+            for (unsigned c = gw; c < tot; c += nw) {  // the largest manifolds first
+                unsigned b = c;
+                int kind = 5;
+                while (kind > 0 && b >= nch[kind]) { b -= nch[kind]; kind--; }
+                const unsigned fk = kind >= 2 ? fbb : (kind == 1 ? first + c0 : first);
+                unsigned ei;
+                if (!wide_pick_hit(a, kind, fk, c2, r, b * 32 + lane, ei)) continue;
+                if (kind >= 2) wide_resolve_entry<true>(a, ei, r);
+                else wide_resolve_entry<false>(a, ei, r);
             }
         }
         grid.sync();
