@@ -105,6 +105,7 @@ struct Batch {
     unsigned* d_tmp = nullptr;
     unsigned *d_surv = nullptr, *d_surv_cnt = nullptr;
     int* d_nlev = nullptr;
+    int* d_nflag = nullptr;
     // what the rounds of an earlier step held, read back asynchronously and never waited for: sizes the grids of the
     // device-counted round kernels (ps_wide.cuh).  [0..kBuckets] bucket starts, then hit counts, then survivor counts
     unsigned* h_est = nullptr;       // pinned
@@ -287,7 +288,7 @@ void free_device(Batch* B)
     dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cost); dfree(B->d_perm); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
-    dfree(B->d_hitlist); dfree(B->d_hitlist2); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev); dfree(B->d_cnt); dfree(B->d_abi_off);
+    dfree(B->d_hitlist); dfree(B->d_hitlist2); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev); dfree(B->d_nflag); dfree(B->d_cnt); dfree(B->d_abi_off);
     if (B->h_bucket) { cudaFreeHost(B->h_bucket); B->h_bucket = nullptr; }
     if (B->h_est) { cudaFreeHost(B->h_est); B->h_est = nullptr; }
     if (B->est_ready) { cudaEventDestroy(B->est_ready); B->est_ready = nullptr; }
@@ -466,6 +467,7 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_surv_cnt, (psw::kWideMaxLevels + 2) * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_tmp_pen, nw * sizeof(unsigned long long)));
         CK(cudaMalloc(&B->d_nlev, sizeof(int)));
+        CK(cudaMalloc(&B->d_nflag, sizeof(int)));
         CK(cudaMallocHost(&B->h_est, (size_t)(4 * psw::kBuckets + 8) * sizeof(unsigned)));
         CK(cudaEventCreateWithFlags(&B->est_ready, cudaEventDisableTiming));
         {   // the rounds of a step run in one cooperative launch whose CTAs must all be resident
@@ -870,6 +872,7 @@ static void fill_kargs(Batch* B, KArgs& a, int n_steps)
     a.hitcnt = B->d_hitcnt; a.cur = B->d_cur; a.pred = B->d_pred; a.S = B->d_S;
     a.cull = B->d_cull; a.row = B->d_row; a.lists = B->d_lists; a.lists_off = B->d_lists_off; a.lvl = B->d_lvl; a.last = B->d_last;
     a.only_flagged = nullptr;
+    a.redo_count = nullptr; a.redo_lo = 0; a.redo_hi = 0;
     a.world_base = 0;
     a.perm = nullptr;
     a.cost = B->d_cost;
@@ -956,7 +959,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     a.stats = B->d_stats; a.tmp = B->d_tmp; a.tmp_pen = B->d_tmp_pen; a.surv = B->d_surv; a.surv_cnt = B->d_surv_cnt;
     a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
-    a.nlev = B->d_nlev; a.team_max = B->team_max;
+    a.nlev = B->d_nlev; a.nflag = B->d_nflag; a.team_max = B->team_max;
     a.sp = ka.sp; a.margin_ncap = ka.margin_ncap;
     a.margin_scale = ka.margin_scale;
     const int nb = B->n_slots, nw = B->n_worlds;
@@ -1068,9 +1071,25 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     B->launches += 4;
     lap(6);
     // worlds the wide pass gave up on: redo from the published state with the fused kernel
+    // Few flagged worlds: one world per warp (32 lanes each) — a handful of worlds on the batch's narrow tiles would hold the
+    // whole step for as long as ONE world takes on 4 lanes.  Many: the batch's own tile.  The count lives on the device; each
+    // of the two launches returns at once when it is not in its range.
     KArgs kf = ka;
     kf.n_steps = 1;
     kf.only_flagged = B->d_wflags;
+    kf.redo_count = B->d_nflag;
+    const int few = 2048;
+    if (B->threads != 32) {
+        kf.redo_lo = 1; kf.redo_hi = few;
+        const int keep_t = B->threads, keep_m = B->minb;
+        const size_t keep_s = B->smem;
+        B->threads = 32; B->minb = 8; B->smem = smem_bytes(B->max_n);
+        launch_fused(B, kf, st);
+        B->threads = keep_t; B->minb = keep_m; B->smem = keep_s;
+        kf.redo_lo = few; kf.redo_hi = 1 << 30;
+    } else {
+        kf.redo_lo = 1; kf.redo_hi = 1 << 30;
+    }
     launch_fused(B, kf, st);
     lap(7);
     B->prof_steps++;

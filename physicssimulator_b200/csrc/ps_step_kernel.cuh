@@ -119,6 +119,9 @@ struct KArgs {
     // when set: only worlds with a non-zero flag are stepped (the batch-wide path hands its failed worlds over);
     // bit0 margin violated -> start at the 8x margin, bit1 static pose / too many statics -> exact serial walk
     const unsigned* only_flagged;
+    // the redo launch of the batch-wide path comes in two tile widths; each runs only when the number of flagged worlds
+    // (counted on the device) is in its range: few worlds -> all 32 lanes on each, many -> the batch's own tile
+    const int* redo_count; int redo_lo, redo_hi;
     const int* perm;              // slot -> world inside each segment (nullptr: identity)
     unsigned short* cost;         // per world: wavefront passes (+ serially walked pairs) of the last step, saturating
     // SpatialTree candidate order (ps_step_config.broadphase_kind 1): the ordered candidate list of every world for THIS
@@ -455,6 +458,10 @@ __global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BlockShared bs_all[32 / T];
     constexpr unsigned FULL = 0xffffffffu;
+    if (a.redo_count) {  // (grid-uniform)
+        const int nf = *a.redo_count;
+        if (nf < a.redo_lo || nf >= a.redo_hi) return;
+    }
 
     const int tile = threadIdx.x / T;
     const int tid = threadIdx.x % T;
@@ -566,7 +573,16 @@ __global__ void __launch_bounds__(32, MINB) step_kernel(KArgs a)
                     if (on) {
                         st_dyn(s.pred, N, b, pr);
                         s.pvalid[b] = 1;
-                        if (p.is_static && !pose_fixed(cur, pr)) bs.need_serial = 1;
+                        // A static body must not move under integrate() for its pairs to commute.  The reference tests it at
+                        // integrate(current) in EVERY pair and writes that copy back on a hit, so what has to be a fixed point is
+                        // the PREDICTED pose: pose -> P1 = integrate(pose) -> integrate(P1) == P1.  (First step after creation: the
+                        // -0.0 entries of a yaw = pi ground become +0.0 once; every pair of that step already sees P1, and the
+                        // final sweep publishes P1 whether or not the body was hit.)
+                        if (p.is_static && !pose_fixed(cur, pr)) {
+                            Dyn pr2;
+                            integrate_slow(pr, p, sp, pr2);
+                            if (!pose_fixed(pr, pr2)) bs.need_serial = 1;
+                        }
                         s.sx[b] = pr.x.x; s.sx[N + b] = pr.x.y; s.sx[2 * N + b] = pr.x.z;
                         double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
                         double acc = p.inv_mass * sqrt(p.F.x * p.F.x + p.F.y * p.F.y + p.F.z * p.F.z);

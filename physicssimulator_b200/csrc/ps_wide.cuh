@@ -66,6 +66,7 @@ struct WArgs {
     Contact* cpool; unsigned cpool_cap; unsigned* cpool_cur;  // cursor per level
     unsigned* surv;              // [entries_cap] box-box pairs the quick test could not separate (listed from the bucket's start)
     unsigned* surv_cnt;          // per level
+    int* nflag;                  // [1] worlds the wide pass gave up on this step (wide_account)
     int* nlev;                   // [1] highest level that holds a pair (wide_bucket_scan); the device-driven rounds stop there
     unsigned team_max;           // a round with at most this many box-box survivors gives every survivor a team of 8 lanes
     WorldStats* stats;
@@ -119,7 +120,7 @@ __global__ void wide_reset(WArgs a)
     if (t < kBuckets) a.bucket_cur[t] = 0;
     for (int q = t; q < (kWideMaxLevels + 2) * kHitSlots; q += gridDim.x * blockDim.x) a.hit_cnt[q] = 0;
     if (t < kWideMaxLevels + 2) { a.cpool_cur[t] = 0; a.surv_cnt[t] = 0; }
-    if (t == 0) a.nlev[0] = 0;
+    if (t == 0) { a.nlev[0] = 0; a.nflag[0] = 0; }
     if (t < a.n_worlds) {
         a.wflags[t] = a.always_fused[t] ? WF_STATIC : 0u;
         a.K[t] = 0; a.maxl[t] = 0;
@@ -169,7 +170,11 @@ __global__ void __launch_bounds__(kTile) wide_predict(WArgs a)
         integrate(cur, p, a.sp, pr);
         st_dyn(s_pred, 0, t, pr);
         a.pvalid[g] = 1; a.nhit[g] = 0;
-        if (p.is_static && !pose_fixed(cur, pr)) atomicOr(&a.wflags[w], (unsigned)WF_STATIC);
+        if (p.is_static && !pose_fixed(cur, pr)) {  // the PREDICTED pose has to be the fixed point (see ps_step_kernel.cuh, phase A)
+            Dyn pr2;
+            integrate_slow(pr, p, a.sp, pr2);
+            if (!pose_fixed(pr, pr2)) atomicOr(&a.wflags[w], (unsigned)WF_STATIC);
+        }
         double* cu = a.cull + (size_t)o * kCullF;
         cu[b] = pr.x.x; cu[N + b] = pr.x.y; cu[2 * N + b] = pr.x.z;
         double speed = sqrt(pr.v.x * pr.v.x + pr.v.y * pr.v.y + pr.v.z * pr.v.z);
@@ -980,6 +985,7 @@ __global__ void wide_account(WArgs a)
         st.max_pen = fmax(st.max_pen, __longlong_as_double((long long)a.tmp_pen[w]));
         return;
     }
+    atomicAdd(a.nflag, 1);
     if (a.always_fused[w]) return;
     st.fallback++;
     if (f & WF_STATIC) st.fb_static++;
