@@ -106,6 +106,8 @@ struct Batch {
     unsigned *d_surv = nullptr, *d_surv_cnt = nullptr;
     int* d_nlev = nullptr;
     int* d_nflag = nullptr;
+    int* d_stat_slots = nullptr;   // slots of the static bodies
+    int n_stat_slots = 0;
     // what the rounds of an earlier step held, read back asynchronously and never waited for: sizes the grids of the
     // device-counted round kernels (ps_wide.cuh).  [0..kBuckets] bucket starts, then hit counts, then survivor counts
     unsigned* h_est = nullptr;       // pinned
@@ -288,7 +290,7 @@ void free_device(Batch* B)
     dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cost); dfree(B->d_perm); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
-    dfree(B->d_hitlist); dfree(B->d_hitlist2); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev); dfree(B->d_nflag); dfree(B->d_cnt); dfree(B->d_abi_off);
+    dfree(B->d_hitlist); dfree(B->d_hitlist2); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev); dfree(B->d_nflag); dfree(B->d_stat_slots); dfree(B->d_cnt); dfree(B->d_abi_off);
     if (B->h_bucket) { cudaFreeHost(B->h_bucket); B->h_bucket = nullptr; }
     if (B->h_est) { cudaFreeHost(B->h_est); B->h_est = nullptr; }
     if (B->est_ready) { cudaEventDestroy(B->est_ready); B->est_ready = nullptr; }
@@ -488,6 +490,16 @@ int upload(Batch* B, bool with_state)
         CK(cudaMemcpy(B->d_isbox, isbox.data(), nb, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B->d_always_fused, af.data(), nw, cudaMemcpyHostToDevice));
         CK(cudaFuncSetAttribute(psw::wide_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psw::lvl_smem_bytes(B->max_n)));
+        CK(cudaFuncSetAttribute(psw::wide_near_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psw::near_smem_bytes(B->max_n)));
+        {   // the slots the static fold visits (a static body added later goes through a re-layout, which rebuilds this list)
+            std::vector<int> ss;
+            for (int w = 0; w < B->n_worlds; w++)
+                for (int b = 0; b < B->cnt[w]; b++)
+                    if (std::isinf(B->slot_mass[B->cap_off[w] + b])) ss.push_back(B->cap_off[w] + b);
+            B->n_stat_slots = (int)ss.size();
+            CK(cudaMalloc(&B->d_stat_slots, std::max<size_t>(ss.size(), 1) * sizeof(int)));
+            if (!ss.empty()) CK(cudaMemcpy(B->d_stat_slots, ss.data(), ss.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
         CK(cudaFuncSetAttribute(psw::wide_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psw::predict_smem_bytes()));
         CK(cudaFuncSetAttribute(psw::wide_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psw::kTileBytes));
         // the wide path pays one pass through memory per stage and ~5 launches per level: it wins when the batch
@@ -980,13 +992,11 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     const int greset = (std::max(nw, kBuckets + 1) + 255) / 256;
     wide_reset<<<greset, 256, 0, st>>>(a);
     wide_predict<<<gb, psw::kTile, psw::predict_smem_bytes(), st>>>(a);
-    wide_near_count<<<gb, 128, 0, st>>>(a);
-    wide_near_scan<<<gw, 64, 0, st>>>(a);
-    wide_near_fill<<<gb, 128, 0, st>>>(a);
+    wide_near_list<<<nw, psw::kNearT, psw::near_smem_bytes(B->max_n), st>>>(a);
     wide_levels<<<gl, psw::kLvlThreads, psw::lvl_smem_bytes(B->max_n), st>>>(a);
     wide_bucket_scan<<<1, 32, 0, st>>>(a);
     wide_scatter<<<gl, psw::kLvlThreads, 0, st>>>(a);
-    B->launches += 8;
+    B->launches += 6;
     if (B->wide_device_rounds && !prof) {
         // Device-counted rounds: no host round trip.  Grids are sized from the counts an earlier step left (if its
         // read-back has arrived; the host never waits for it), every kernel reads the real counts on the device and walks
@@ -1065,7 +1075,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     }
     }
     wide_verify<<<gb, 128, 0, st>>>(a);
-    wide_static_fold<<<gb, 128, 0, st>>>(a);
+    if (B->n_stat_slots > 0) wide_static_fold<<<(B->n_stat_slots * 32 + 127) / 128, 128, 0, st>>>(a, B->d_stat_slots, B->n_stat_slots);
     wide_final<<<gb, psw::kTile, psw::kTileBytes, st>>>(a);
     wide_account<<<gw, 64, 0, st>>>(a);
     B->launches += 4;
@@ -1445,7 +1455,7 @@ int ps_batch_add_body(void* handle, int32_t world, const ps_bodies_view* one)
     }
     CK(cudaSetDevice(B->device));
     const bool is_static = std::isinf(nb.mass[0]);
-    if (N0 < B->cap_off[world + 1] - B->cap_off[world]) {
+    if (N0 < B->cap_off[world + 1] - B->cap_off[world] && !is_static) {  // (a static body: re-layout, the static-fold list is rebuilt)
         // ---- the world has a spare slot: the new body (id = max id + 1, SimulatorState.fs:90-92) is a record write ------
         const int g = B->cap_off[world] + N0;
         int nstat = 0;
