@@ -842,6 +842,13 @@ int ps_batch_destroy(void* handle)
             }
     }
 #endif
+    if (getenv("PS_B200_WIDE_PROF") && B->wide && B->d_tmp) {
+        std::vector<unsigned> tm((size_t)B->n_worlds * 6);
+        cudaMemcpy(tm.data(), B->d_tmp, tm.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
+        unsigned long long lit = 0, hits = 0;
+        for (int w = 0; w < B->n_worlds; w++) { lit += tm[(size_t)w * 6 + 2]; hits += ((*(unsigned long long*)&tm[(size_t)w * 6]) >> 20) & 0xfffffull; }
+        fprintf(stderr, "[ps_b200 wide profile] last step: %llu of %llu colliding pairs were solved again by the literal routine\n", lit, hits);
+    }
     if (getenv("PS_B200_WIDE_PROF") && !B->prof_round.empty()) {
         std::vector<unsigned> hc((size_t)(psw::kWideMaxLevels + 2) * psw::kHitSlots), sc(psw::kWideMaxLevels + 2);
         cudaMemcpy(hc.data(), B->d_hit_cnt, hc.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
@@ -1020,6 +1027,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
             for (int r = 1; r <= kWideMaxLevels; r++) if (hb[(r + 1) * 4] > hb[r * 4]) top = r;
             r_launch = std::min(kWideMaxLevels, top + 3);
         }
+        if (const char* e = getenv("PS_B200_COOP_ALL")) { if (atoi(e) != 0) r_launch = 0; }  // tuning: every round in the cooperative kernel
         for (int r = 1; r <= r_launch; r++) {
             unsigned g1 = dflt, g2 = dflt, g2t = dflt, g3 = dflt, ns_est = ~0u;
             if (hb) {

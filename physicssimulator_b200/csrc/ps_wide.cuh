@@ -681,6 +681,7 @@ __device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, 
     }
     if (!ok) {  // a quotient outside the short division's range, a non-finite accumulator: the literal routine, same inputs
         PS_COLD_PATH;
+        atomicAdd(&a.tmp[6 * (size_t)w + 2], 1u);  // (counted: PS_B200_WIDE_PROF prints the share of pairs that took this route)
         wide_resolve_literal(a, o + i, o + j, si, sj, a.cpool + e.cfirst, (int)(e.knc >> 24), di, dj);
     }
     w_hit(a, w)[e.knc & 0xffffffu] = 1;
