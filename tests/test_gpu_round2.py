@@ -390,3 +390,44 @@ def test_joints_given_as_hi_lo_swap_the_bodies_like_the_reference():
     p, cfg, j = scenes.c4_chain32(0, n_links=4)
     with pytest.raises(ValueError):
         BatchSimulator([p], cfg, joints=[[(2, 2, j[0][2])]], device=0)
+
+
+def test_wide_path_on_ragged_worlds(monkeypatch):
+    """the batch-wide path on worlds of very different sizes in one batch: empty, one body, a few, more than one CTA's rows
+    (150) and more than the bit-mask rows of the near-list kernel hold (300: the two-walk route) — against the oracle"""
+    from oracle.oracle import OracleWorld
+    monkeypatch.setenv("PS_B200_PATH", "wide")
+    rng = scenes.SplitMix64(4242)
+
+    def pile(n, boxes):
+        protos = [P.createDefaultBox(60, 60, 1).With(Mass=P.INFINITE, UseGravity=False, Position=(0, 0, -0.5), Yaw=np.pi)]
+        side = int(np.ceil(np.sqrt(max(n, 1))))
+        for k in range(n):
+            pos = ((k % side - side / 2) * 0.9 + rng.uniform(-0.05, 0.05), (k // side - side / 2) * 0.9 + rng.uniform(-0.05, 0.05), 0.6 + 0.5 * (k % 3))
+            if boxes and k % 4 == 0:
+                protos.append(P.createDefaultBox(0.5, 0.4, 0.45).With(Position=pos, Mass=8.0, Yaw=rng.uniform(-1, 1)))
+            else:
+                protos.append(P.createDefaultSphere(0.3 + 0.1 * (k % 2)).With(Position=pos, Mass=3.0))
+        return protos
+
+    worlds = [[], pile(0, False), pile(1, False), pile(7, True), pile(149, True), pile(299, False), pile(40, True)]
+    cfg = Configuration()
+    sim = BatchSimulator(worlds, cfg, device=0, record_contacts=True)
+    assert sim.batch.schedule()["path"] == "wide"
+    oracles = [OracleWorld(P.build_world(p), to_native_config(cfg)) if p else None for p in worlds]
+    for n in (1, 14, 25):
+        sim.Step(n)
+        for w, o in enumerate(oracles):
+            if o is None:
+                assert len(sim.WorldState(w)["pos"]) == 0
+                continue
+            o.step(n)
+            got, ref = sim.WorldState(w), o.get_state()
+            dyn = ~np.isinf(P.build_world(worlds[w])["mass"])
+            for k in ("pos", "vel", "rot"):
+                assert same_bits(got[k][dyn], ref[k][dyn]), f"ragged wide batch: world {w} ({len(worlds[w])} bodies) {k} after +{n}"
+            c_gpu, c_ref = sim.Collisions(w), o.contacts()
+            assert np.array_equal(c_gpu["pairs"], c_ref["pairs"]) and np.array_equal(c_gpu["feature"], c_ref["feature"]), f"world {w}: contact sets"
+    st = sim.Stats()
+    assert st["nan_worlds"] == 0 and st["contact_overflow"] == 0
+    sim.close()
