@@ -431,3 +431,53 @@ def test_wide_path_on_ragged_worlds(monkeypatch):
     st = sim.Stats()
     assert st["nan_worlds"] == 0 and st["contact_overflow"] == 0
     sim.close()
+
+
+@pytest.mark.parametrize("path", ["fused", "wide"])
+@pytest.mark.parametrize("integrator,friction", [(0, True), (1, True), (0, False)])
+def test_random_worlds_both_paths(monkeypatch, path, integrator, friction):
+    """120 small random worlds in one batch — boxes and spheres at random poses and velocities, axis-aligned and rotated,
+    interpenetrating at creation, a second static body in some — both step paths, both integrators, friction on and off:
+    states, colliding sets and feature ids against the oracle"""
+    from common import StepConfiguration
+    from oracle.oracle import OracleWorld
+    monkeypatch.setenv("PS_B200_PATH", path)
+    rng = scenes.SplitMix64(1000 + 10 * integrator + (1 if friction else 0))
+    worlds = []
+    for w in range(120):
+        protos = [P.createDefaultBox(8, 8, 1).With(Mass=P.INFINITE, UseGravity=False, Position=(0, 0, -0.5), Yaw=(np.pi if w % 2 else 0.0))]
+        if w % 7 == 3:
+            protos.append(P.createDefaultBox(1.0, 3.0, 0.6).With(Mass=P.INFINITE, UseGravity=False, Position=(1.5, 0.0, 0.3), Yaw=0.4))
+        aligned = w % 3 == 0
+        for k in range(3 + w % 6):
+            ang = (lambda: 0.0) if aligned else (lambda: rng.uniform(-3.1, 3.1))
+            pos = (rng.uniform(-1.2, 1.2), rng.uniform(-1.2, 1.2), rng.uniform(0.2, 2.2))
+            if aligned:
+                pos = tuple(round(x * 4) / 4 for x in pos)
+            vel = (rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(-3, 1))
+            if (k + w) % 3 == 0:
+                protos.append(P.createDefaultSphere(rng.uniform(0.15, 0.5)).With(Position=pos, Velocity=vel, Mass=rng.uniform(0.5, 9)))
+            else:
+                protos.append(P.createDefaultBox(rng.uniform(0.2, 1.0), rng.uniform(0.2, 1.0), rng.uniform(0.2, 1.0)).With(
+                    Position=pos, Velocity=vel, Yaw=ang(), Pitch=ang(), Roll=ang(), Mass=rng.uniform(0.5, 40),
+                    ElasticityCoeff=rng.uniform(0.0, 0.9), KineticFrictionCoeff=rng.uniform(0.0, 1.0)))
+        worlds.append(protos)
+    cfg = Configuration(StepConfig=StepConfiguration(RigidBodyIntegratorKind=integrator, EnableFriction=friction))
+    sim = BatchSimulator(worlds, cfg, device=0, record_contacts=True)
+    assert sim.batch.schedule()["path"] == path
+    oracles = [OracleWorld(P.build_world(p), to_native_config(cfg)) for p in worlds]
+    for n in (1, 4, 25):
+        sim.Step(n)
+        st = sim.State()
+        for w, o in enumerate(oracles):
+            o.step(n)
+            ref = o.get_state()
+            a, b = sim._offsets[w], sim._offsets[w + 1]
+            dyn = ~np.isinf(sim._worlds[w]["mass"])
+            for k in ("pos", "vel", "rot", "ang_mom"):
+                assert same_bits(st[k][a:b][dyn], ref[k][dyn]), f"random worlds {path}/{integrator}/{friction}: world {w} {k} after +{n}"
+            c_gpu, c_ref = sim.Collisions(w), o.contacts()
+            assert np.array_equal(c_gpu["pairs"], c_ref["pairs"]) and np.array_equal(c_gpu["feature"], c_ref["feature"]), f"world {w}: contacts after +{n}"
+    stt = sim.Stats()
+    assert stt["contact_overflow"] == 0 and stt["pairs_colliding"] > 500
+    sim.close()
