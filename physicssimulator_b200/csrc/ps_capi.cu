@@ -1041,7 +1041,8 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
             wide_round_detect_d<<<g1, 128, 0, st>>>(a, r);
             if (ns_est <= B->team_max) wide_round_bb_team_d<<<g2t, 128, 0, st>>>(a, r);
             else wide_round_bb_d<<<g2, 128, 0, st>>>(a, r);
-            wide_round_resolve_d<<<g3, 128, 0, st>>>(a, r);
+            if (hb && g3 > 4000u) wide_round_resolve_d<3><<<g3, 128, 0, st>>>(a, r);  // > ~0.5 M colliding pairs: throughput bound
+            else wide_round_resolve_d<PS_WIDE_MINB><<<g3, 128, 0, st>>>(a, r);
         }
         B->launches += 3 * (long long)r_launch;
         if (r_launch < kWideMaxLevels) {

@@ -842,7 +842,11 @@ __global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_bb_team_d(WArgs 
     for (unsigned blk = blockIdx.x; blk < (ns + 15) / 16; blk += gridDim.x)
         wide_bb_team_body(a, q.first + q.c0 + q.c1, q.c2, r, blk * 16 + threadIdx.x / psc::kTeam, ns, ts_all[threadIdx.x / psc::kTeam]);
 }
-__global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_resolve_d(WArgs a, int r)
+// MINB = resident CTAs per SM the register allocation allows: 2 (255 registers) for the rounds that wait for their longest
+// manifold, 3 (168 registers, 12 warps per SM) for a round that is throughput bound — round 1, every body against the ground:
+// 1.84 -> 1.68 ms; the other rounds are slower with it (110 -> 140 us)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) wide_round_resolve_d(WArgs a, int r)
 {
     if (r > a.nlev[0] || a.bucket[kBuckets] > a.entries_cap) return;
     const RoundCounts q = round_counts(a, r);
