@@ -502,9 +502,14 @@ int upload(Batch* B, bool with_state)
         }
         CK(cudaFuncSetAttribute(psw::wide_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psw::predict_smem_bytes()));
         CK(cudaFuncSetAttribute(psw::wide_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psw::kTileBytes));
-        // the wide path pays one pass through memory per stage and ~5 launches per level: it wins when the batch
-        // is large enough to fill the GPU per round
-        B->wide = !B->cfg.exact_all_pairs && !(B->cfg.restore_joints && !B->joints.a.empty()) && B->n_bodies >= 500000;  // measured: C3 (2.1 M bodies) 24 vs 53 ms per step, C2 (0.27 M bodies) 3.9 vs 3.4 ms
+        // the wide path pays one pass through memory per stage and ~3 launches per level: it wins when the batch fills the
+        // GPU per round, and earlier with boxes (a box pair costs the fused kernel a whole tile's pass).  Measured, ms per
+        // settled step fused / wide: C2 (spheres) 8192 worlds 2.87 / 3.21, 16384 worlds 5.79 / 4.52; C3 (65 boxes + 62
+        // spheres per world) 1024 worlds 4.35 / 5.38, 2048 worlds 8.35 / 5.94, 4096 worlds 13.87 / 7.28.
+        size_t n_box = 0, n_live = 0;
+        for (int w = 0; w < B->n_worlds; w++)
+            for (int b = 0; b < B->cnt[w]; b++) { n_live++; n_box += isbox[B->cap_off[w] + b]; }
+        B->wide = !B->cfg.exact_all_pairs && !(B->cfg.restore_joints && !B->joints.a.empty()) && (n_live - n_box) + 6 * n_box >= 700000;
         if (const char* e = getenv("PS_B200_PATH")) { if (!strcmp(e, "fused")) B->wide = false; else if (!strcmp(e, "wide")) B->wide = !B->cfg.exact_all_pairs && !(B->cfg.restore_joints && !B->joints.a.empty()); }
     }
     CK(cudaMalloc(&B->d_hitcnt, nb));
