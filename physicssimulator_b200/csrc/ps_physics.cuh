@@ -469,18 +469,27 @@ PSD int bb_edge_contact(const OBox& o1, const OBox& o2, d3 sel1, d3 sel2, d3 nor
         d3 bea = mk(0.0, 0.0, 0.0), beb = mk(0.0, 0.0, 0.0);
         // OrientedBox.getEdges: faces 0..5, per face (v3,v0),(v0,v1),(v1,v2),(v2,v3); List.distinct on
         // ordered pairs — every directed edge of a non-degenerate box appears once, so index = 4*f+k.
+        d3 vv[8];  // the box's vertices once (every one is an end of six of the 24 directed edges)
+#pragma unroll (F ? 8 : 1)
+        for (int q = 0; q < 8; q++) vv[q] = box_vertex(ob, q);
 #pragma unroll 1
         for (int f = 0; f < 6; f++)
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
-                d3 a = face_vertex(ob, f, (k + 3) & 3), b = face_vertex(ob, f, k);
+                d3 a = vv[kFaceVert[f][(k + 3) & 3]], b = vv[kFaceVert[f][k]];
                 d3 dd = b - a;
                 d3 cr = cross(dd, axis);  // areParallel: axis |> crossProduct d = d x axis, isZero eps of its norm
                 // Exact shortcut: Hypotenuse never returns less than its larger argument (|x| * sqrt(1 + r*r) >= |x|), so
                 // the norm is >= every |component|; one component above eps decides "not parallel" without the two
                 // divisions and square roots (20 of the 24 edges end here; a NaN norm compares false either way).
                 if (fabs(cr.x) > eps || fabs(cr.y) > eps || fabs(cr.z) > eps) continue;
-                if (!near_eq(eps, 0.0, norm_t<F>(cr))) continue;
+                // and the other way round: with every |component| <= eps / 2 the norm is at most sqrt(3) / 2 eps (1 + 8 ulp) < eps,
+                // "parallel" without the norm as well.  What is left (a component in (eps / 2, eps]) does not occur for a box
+                // edge against a box axis (the cross product is ~1e-16 or an edge length); without this a warp of the batch-wide
+                // kernel ran the two divisions and square roots once per edge for ONE lane each (ncu: 60 % of this routine).
+                const double heps = 0.5 * eps;  // (exact above the subnormals)
+                const bool tiny = eps > 1e-290 && fabs(cr.x) <= heps && fabs(cr.y) <= heps && fabs(cr.z) <= heps;
+                if (!tiny && !near_eq(eps, 0.0, norm_t<F>(cr))) continue;
                 double pa = dot(nrm, a), pb = dot(nrm, b);
                 double key = (pb > pa) ? pb : pa;
                 if (!have || key > bestv) {
