@@ -359,8 +359,9 @@ def run_workload(name, args, rank, local, world, main_line):
                    "what": "ps_batch_step_host(pinned host state in, 1 step, pinned host state out) per step: H2D + step + D2H inside the timed region, pipelined over world chunks"}}
     copy_ms = max(res["e2e"]["ms_per_step"] - kernel_ms, 1e-9)
     res["e2e"]["copy_GBps_both_ways"] = 2 * bytes_state / (copy_ms * 1e-3) / 1e9
-    res["e2e"]["bound"] = ("host<->device copies: (e2e - device step) time moves h2d + d2h bytes at the rate above; a step of the batch-wide path is one "
-                           "dependent chain of rounds over the WHOLE batch, so the copies cannot hide behind it chunk by chunk (the fused path does that)")
+    res["e2e"]["bound"] = ("host<->device copies: (e2e - device step) time moves h2d + d2h bytes at the rate above.  On the batch-wide path the call "
+                           "splits the worlds into 4 chunks, each with its own chain of rounds on its own stream: the copies of one chunk overlap the "
+                           "rounds of the others, but four staggered chains share the GPU less well than one (DESIGN.md 4.3)")
     if e2e_seq_s is not None:
         res["e2e"]["sequential_calls_value_this_rank"] = n_dyn * per_gpu * e2e_steps / e2e_seq_s
         res["e2e"]["sequential_calls_what"] = "ps_batch_set_state + ps_batch_step(1) + ps_batch_get_state, one after the other (informational)"

@@ -174,8 +174,9 @@ int ps_batch_set_state(void* handle, int32_t w0, int32_t w1, const double* pos, 
 /* marshal -> n x Simulator.updateSimulation -> unmarshal in ONE call (Simulator.fs:47-62 seen from a caller whose
  * SimulatorState lives in managed memory): equivalent to ps_batch_set_state(all) + ps_batch_step(n) +
  * ps_batch_get_state(all), but pipelined over chunks of worlds on separate streams so that the host<->device copies
- * of one chunk hide behind the step of the others.  Pinned host buffers make the copies asynchronous; pageable ones
- * work, unpipelined.  in and out may be the same arrays. */
+ * of one chunk hide behind the step of the others (the per-world kernel over a world range; on the batch-wide path every
+ * chunk runs its own chain of rounds with its own counters and a slice of the batch's lists).  Pinned host buffers make the
+ * copies asynchronous; pageable ones work, unpipelined.  in and out may be the same arrays. */
 int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, const double* vel_in,
                        const double* rot_in, const double* ang_mom_in, double* pos_out, double* vel_out,
                        double* rot_out, double* ang_mom_out);

@@ -5,6 +5,7 @@
 // There is no CPU path in this file: every entry point that computes runs a CUDA kernel or fails
 // with PS_ERR_CUDA.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -51,6 +52,22 @@ struct HostBodies {
 struct HostJoints {
     std::vector<int32_t> world, a, b;
     std::vector<double> la, lb;
+};
+
+// ps_batch_step_host on the batch-wide path: a chunk of worlds runs its own chain of rounds on its own stream, so that the
+// copies of one chunk and the (latency-bound) rounds of the others overlap.  A chunk owns the small tables of a pass
+// (buckets, counters, the grid estimates) and a SLICE of the batch's pair / hit / contact lists; everything indexed by world
+// or slot is the batch's.
+struct WideChunk {
+    int w0 = 0, w1 = 0, g0 = 0, g1 = 0;
+    unsigned* d_small = nullptr;  // bucket | bucket_cur | hit_cnt | cpool_cur | surv_cnt | nlev | nflag
+    size_t e_off = 0, c_off = 0;  // first entry / contact of the slice
+    unsigned e_cap = 0, c_cap = 0;
+    int stat_first = 0, stat_count = 0;  // its static bodies in d_stat_slots
+    unsigned* h_est = nullptr;  // pinned
+    cudaEvent_t est_ready = nullptr;
+    bool est_pending = false, est_valid = false;
+    std::vector<unsigned> est;
 };
 
 struct Batch {
@@ -131,6 +148,8 @@ struct Batch {
     ps_stats* d_stats_sum = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_own = nullptr, ev_foreign = nullptr;  // ordering between the handle's stream and a caller's stream
+    std::vector<WideChunk> wchunks;  // ps_batch_step_host on the batch-wide path (built at the first such call)
+    std::vector<int> h_stat_slots;   // host copy of d_stat_slots (ascending)
     std::vector<cudaStream_t> chunk_streams;  // ps_batch_step_host: one stream per world chunk
     std::vector<cudaEvent_t> chunk_done;
     cudaEvent_t chunk_start = nullptr;
@@ -291,6 +310,12 @@ void free_device(Batch* B)
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
     dfree(B->d_hitlist); dfree(B->d_hitlist2); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev); dfree(B->d_nflag); dfree(B->d_stat_slots); dfree(B->d_cnt); dfree(B->d_abi_off);
+    for (WideChunk& c : B->wchunks) {
+        dfree(c.d_small);
+        if (c.h_est) cudaFreeHost(c.h_est);
+        if (c.est_ready) cudaEventDestroy(c.est_ready);
+    }
+    B->wchunks.clear();
     if (B->h_bucket) { cudaFreeHost(B->h_bucket); B->h_bucket = nullptr; }
     if (B->h_est) { cudaFreeHost(B->h_est); B->h_est = nullptr; }
     if (B->est_ready) { cudaEventDestroy(B->est_ready); B->est_ready = nullptr; }
@@ -497,6 +522,7 @@ int upload(Batch* B, bool with_state)
                 for (int b = 0; b < B->cnt[w]; b++)
                     if (std::isinf(B->slot_mass[B->cap_off[w] + b])) ss.push_back(B->cap_off[w] + b);
             B->n_stat_slots = (int)ss.size();
+            B->h_stat_slots = ss;
             CK(cudaMalloc(&B->d_stat_slots, std::max<size_t>(ss.size(), 1) * sizeof(int)));
             if (!ss.empty()) CK(cudaMemcpy(B->d_stat_slots, ss.data(), ss.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
@@ -969,7 +995,7 @@ static void launch_fused(Batch* B, const KArgs& a, cudaStream_t st)
 }
 
 // one step of the batch-wide path (ps_wide.cuh)
-static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
+static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st, WideChunk* ck = nullptr)
 {
     using namespace psw;
     WArgs a{};
@@ -986,9 +1012,33 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     a.nlev = B->d_nlev; a.nflag = B->d_nflag; a.team_max = B->team_max;
     a.sp = ka.sp; a.margin_ncap = ka.margin_ncap;
     a.margin_scale = ka.margin_scale;
-    const int nb = B->n_slots, nw = B->n_worlds;
+    // the whole batch, or one chunk of ps_batch_step_host with its own small tables and its slice of the lists
+    unsigned* h_est = B->h_est;
+    cudaEvent_t est_ready = B->est_ready;
+    bool *est_pending = &B->est_pending, *est_valid = &B->est_valid;
+    std::vector<unsigned>* est = &B->est;
+    const int* d_stat = B->d_stat_slots;
+    int n_stat = B->n_stat_slots;
+    a.w_begin = 0; a.w_end = B->n_worlds; a.g_begin = 0; a.g_end = B->n_slots;
+    if (ck) {
+        unsigned* p = ck->d_small;
+        a.bucket = p; p += kBuckets + 1;
+        a.bucket_cur = p; p += kBuckets;
+        a.hit_cnt = p; p += (kWideMaxLevels + 2) * kHitSlots;
+        a.cpool_cur = p; p += kWideMaxLevels + 2;
+        a.surv_cnt = p; p += kWideMaxLevels + 2;
+        a.nlev = reinterpret_cast<int*>(p); p += 1;
+        a.nflag = reinterpret_cast<int*>(p);
+        a.entries = B->d_entries + ck->e_off; a.entries_cap = ck->e_cap;
+        a.hitlist = B->d_hitlist + ck->e_off; a.hitlist2 = B->d_hitlist2 + ck->e_off; a.surv = B->d_surv + ck->e_off;
+        a.cpool = B->d_cpool + ck->c_off; a.cpool_cap = ck->c_cap;
+        a.w_begin = ck->w0; a.w_end = ck->w1; a.g_begin = ck->g0; a.g_end = ck->g1;
+        h_est = ck->h_est; est_ready = ck->est_ready; est_pending = &ck->est_pending; est_valid = &ck->est_valid; est = &ck->est;
+        d_stat = B->d_stat_slots + ck->stat_first; n_stat = ck->stat_count;
+    }
+    const int nb = a.g_end - a.g_begin, nw = a.w_end - a.w_begin;
     const int gb = (nb + 127) / 128, gw = (nw + 63) / 64, gl = (nw + psw::kLvlWorlds - 1) / psw::kLvlWorlds;
-    const bool prof = getenv("PS_B200_WIDE_PROF") != nullptr;
+    const bool prof = getenv("PS_B200_WIDE_PROF") != nullptr && !ck;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
     float lap_ms = 0.f;
@@ -1016,15 +1066,15 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         CK(cudaStreamIsCapturing(st, &cap));
         const bool capturing = cap != cudaStreamCaptureStatusNone;
-        if (!capturing && B->est_pending && cudaEventQuery(B->est_ready) == cudaSuccess) {  // (an event query would invalidate a capture)
-            B->est.assign(B->h_est, B->h_est + 4 * kBuckets + 8);
-            B->est_pending = false;
-            B->est_valid = true;
+        if (!capturing && *est_pending && cudaEventQuery(est_ready) == cudaSuccess) {  // (an event query would invalidate a capture)
+            est->assign(h_est, h_est + 4 * kBuckets + 8);
+            *est_pending = false;
+            *est_valid = true;
         }
         const unsigned dflt = (unsigned)std::max(1, B->sm_count) * 8;   // no estimate yet: a grid that fills the device, strides do the rest
         auto blocks = [&](unsigned n, unsigned per) { return (unsigned)(((unsigned long long)n * 9 / 8 + per - 1) / per) + 4u; };  // estimate + 12 %
         int r_launch = 48;
-        const unsigned* hb = B->est_valid ? B->est.data() : nullptr;
+        const unsigned* hb = *est_valid ? est->data() : nullptr;
         const unsigned* hh = hb ? hb + kBuckets + 1 : nullptr;      // hit counts per (level, kind)
         const unsigned* hs = hb ? hb + 3 * kBuckets + 1 : nullptr;  // survivors per level
         if (hb) {
@@ -1056,19 +1106,19 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
             CK(cudaLaunchCooperativeKernel((const void*)wide_rounds, dim3((unsigned)B->rounds_grid), dim3(128), args, 0, st));
             B->launches += 1;
         }
-        if (!capturing && !B->est_pending) {  // this step's counts, for the grids of a later step
-            CK(cudaMemcpyAsync(B->h_est, B->d_bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(B->h_est + kBuckets + 1, B->d_hit_cnt, (size_t)(kWideMaxLevels + 2) * kHitSlots * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(B->h_est + 3 * kBuckets + 1, B->d_surv_cnt, (kWideMaxLevels + 2) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            CK(cudaEventRecord(B->est_ready, st));
-            B->est_pending = true;
+        if (!capturing && !*est_pending) {  // this step's counts, for the grids of a later step
+            CK(cudaMemcpyAsync(h_est, a.bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h_est + kBuckets + 1, a.hit_cnt, (size_t)(kWideMaxLevels + 2) * kHitSlots * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h_est + 3 * kBuckets + 1, a.surv_cnt, (kWideMaxLevels + 2) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(est_ready, st));
+            *est_pending = true;
         }
     } else {
-    CK(cudaMemcpyAsync(B->h_bucket, B->d_bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(B->h_bucket, a.bucket, (kBuckets + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     lap(0);
     const unsigned* hb = B->h_bucket;
-    const bool overflow = hb[kBuckets] > B->entries_cap;  // wide_scatter flagged every world: the fused kernel takes the step
+    const bool overflow = hb[kBuckets] > a.entries_cap;  // wide_scatter flagged every world: the fused kernel takes the step
     for (int r = 1; r <= kWideMaxLevels && !overflow; r++) {
         unsigned first = hb[r * 4], total = hb[(r + 1) * 4] - first;
         if (first >= hb[kBuckets]) break;  // no pair at this or any later level
@@ -1089,7 +1139,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     }
     }
     wide_verify<<<gb, 128, 0, st>>>(a);
-    if (B->n_stat_slots > 0) wide_static_fold<<<(B->n_stat_slots * 32 + 127) / 128, 128, 0, st>>>(a, B->d_stat_slots, B->n_stat_slots);
+    if (n_stat > 0) wide_static_fold<<<(n_stat * 32 + 127) / 128, 128, 0, st>>>(a, d_stat, n_stat);
     wide_final<<<gb, psw::kTile, psw::kTileBytes, st>>>(a);
     wide_account<<<gw, 64, 0, st>>>(a);
     B->launches += 4;
@@ -1101,7 +1151,8 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st)
     KArgs kf = ka;
     kf.n_steps = 1;
     kf.only_flagged = B->d_wflags;
-    kf.redo_count = B->d_nflag;
+    kf.redo_count = a.nflag;
+    kf.world_base = a.w_begin; kf.n_worlds = a.w_end;  // (the end of the launched range)
     const int few = 2048;
     if (B->threads != 32) {
         kf.redo_lo = 1; kf.redo_hi = few;
@@ -1293,6 +1344,55 @@ int ps_batch_set_state(void* handle, int32_t w0, int32_t w1, const double* pos, 
 // pipelined over chunks of worlds: chunk k's host->device copy, its step kernel and its device->host copy run on their own
 // stream, so the copies of one chunk hide behind the step of the others (worlds are independent, the step kernel takes a
 // world range).  The batch-wide and SpatialTree paths step the whole batch at once: there the three stages run in sequence.
+}  // extern "C"
+
+// The chunks of ps_batch_step_host on the batch-wide path (see WideChunk).  Measured, C3 with 16 384 worlds, pinned host state
+// in -> one step -> pinned host state out: 1 chunk 24.0 ms, 2 chunks 19.0, 4 chunks 16.3, 8 chunks 18.6.
+static int ensure_wide_chunks(Batch* B)
+{
+    if (!B->wchunks.empty()) return PS_OK;
+    int K = B->n_slots >= 200000 ? 4 : 1;  // (a small batch is one latency-bound chain either way, and its copies are short)
+    if (const char* e = getenv("PS_B200_WIDE_HOST_CHUNKS")) K = std::max(1, std::min(16, atoi(e)));  // tuning knob
+    K = std::min(K, std::max(1, B->n_worlds / 32));
+    const size_t small = (size_t)(psw::kBuckets + 1) + psw::kBuckets + (size_t)(psw::kWideMaxLevels + 2) * (psw::kHitSlots + 2) + 2;
+    std::vector<double> cut((size_t)K + 1, 0.0);  // chunk borders as fractions of the worlds
+    for (int k = 0; k <= K; k++) cut[k] = (double)k / K;
+    if (const char* e = getenv("PS_B200_WIDE_CHUNK_SHAPE")) {  // tuning knob: relative chunk sizes, e.g. "40,30,20,10"
+        std::vector<double> wts;
+        for (const char* q = e; *q;) { wts.push_back(std::max(1e-3, atof(q))); while (*q && *q != ',') q++; if (*q) q++; }
+        if ((int)wts.size() == K) {
+            double tot = 0, acc = 0;
+            for (double x : wts) tot += x;
+            for (int k = 0; k < K; k++) { acc += wts[k]; cut[k + 1] = acc / tot; }
+        }
+    }
+    std::vector<WideChunk> cs((size_t)K);
+    for (int k = 0; k < K; k++) {
+        WideChunk& c = cs[k];
+        c.w0 = k == 0 ? 0 : (int)(B->n_worlds * cut[k]) / 32 * 32;
+        c.w1 = k == K - 1 ? B->n_worlds : (int)(B->n_worlds * cut[k + 1]) / 32 * 32;
+        c.g0 = B->cap_off[c.w0]; c.g1 = B->cap_off[c.w1];
+        const size_t ns = (size_t)std::max(1, B->n_slots);
+        c.e_off = (size_t)B->entries_cap * (size_t)c.g0 / ns;
+        c.e_cap = (unsigned)((size_t)B->entries_cap * (size_t)c.g1 / ns - c.e_off);
+        c.c_off = (size_t)B->cpool_cap * (size_t)c.g0 / ns;
+        c.c_cap = (unsigned)((size_t)B->cpool_cap * (size_t)c.g1 / ns - c.c_off);
+        const auto lo = std::lower_bound(B->h_stat_slots.begin(), B->h_stat_slots.end(), c.g0);
+        const auto hi = std::lower_bound(B->h_stat_slots.begin(), B->h_stat_slots.end(), c.g1);
+        c.stat_first = (int)(lo - B->h_stat_slots.begin()); c.stat_count = (int)(hi - lo);
+    }
+    for (WideChunk& c : cs) {
+        CK(cudaMalloc(&c.d_small, small * sizeof(unsigned)));
+        CK(cudaMemset(c.d_small, 0, small * sizeof(unsigned)));
+        CK(cudaMallocHost(&c.h_est, (size_t)(4 * psw::kBuckets + 8) * sizeof(unsigned)));
+        CK(cudaEventCreateWithFlags(&c.est_ready, cudaEventDisableTiming));
+    }
+    B->wchunks = std::move(cs);
+    return PS_OK;
+}
+
+extern "C" {
+
 int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, const double* vel_in, const double* rot_in,
                        const double* ang_mom_in, double* pos_out, double* vel_out, double* rot_out, double* ang_mom_out)
 {
@@ -1303,9 +1403,17 @@ int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, cons
     if (!pos_in || !vel_in || !rot_in || !ang_mom_in || !pos_out || !vel_out || !rot_out || !ang_mom_out)
         return fail(PS_ERR_INVALID_ARGUMENT, "state array is null");
     if (B->n_worlds == 0) return PS_OK;
+    const auto t_call = std::chrono::steady_clock::now();
     const int per = B->seg;  // chunk = segment (upload(): PS_B200_HOST_CHUNKS, default 8, borders on CTA borders)
     int chunks = per > 0 ? (B->n_worlds + per - 1) / per : 1;
-    if (B->wide || B->tree_mode || chunks <= 1 || n_steps == 0) {
+    const bool wide_chunked = B->wide && B->wide_device_rounds && !B->tree_mode && n_steps > 0 && !getenv("PS_B200_WIDE_PROF");
+    if (wide_chunked) {
+        CK(cudaSetDevice(B->device));
+        int rc = ensure_wide_chunks(B);
+        if (rc) return rc;
+        chunks = (int)B->wchunks.size();
+    }
+    if ((B->wide && !wide_chunked) || B->tree_mode || chunks <= 1 || n_steps == 0) {
         int rc = ps_batch_set_state(handle, 0, B->n_worlds, pos_in, vel_in, rot_in, ang_mom_in);
         if (!rc) rc = ps_batch_step(handle, n_steps);
         if (!rc) rc = ps_batch_get_state(handle, 0, B->n_worlds, pos_out, vel_out, rot_out, ang_mom_out);
@@ -1314,17 +1422,30 @@ int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, cons
     CK(cudaSetDevice(B->device));
     while ((int)B->chunk_streams.size() < chunks) {
         cudaStream_t s; cudaEvent_t e;
-        CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        // an earlier chunk is further along its chain of small latency-bound rounds while a later one is still in its bulk
+        // stages: the earlier one goes first whenever an SM has room
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        int prio = std::min(least, greatest + (int)B->chunk_streams.size());
+        if (const char* e = getenv("PS_B200_CHUNK_PRIO")) { if (atoi(e) == 0) prio = least; }  // tuning knob
+        CK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio));
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         B->chunk_streams.push_back(s); B->chunk_done.push_back(e);
     }
     if (!B->chunk_start) CK(cudaEventCreateWithFlags(&B->chunk_start, cudaEventDisableTiming));
     KArgs a{};
     fill_kargs(B, a, n_steps);
-    a.perm = current_perm(B, n_steps, B->stream);    // (a re-sort runs on the handle's stream, before the chunks start)
+    a.perm = wide_chunked ? nullptr : current_perm(B, n_steps, B->stream);  // (a re-sort runs on the handle's stream, before the chunks start)
     CK(cudaEventRecord(B->chunk_start, B->stream));  // after whatever the handle's own stream still holds
+    static const bool trace = getenv("PS_B200_HOST_TRACE") != nullptr;  // tuning: the timeline of the chunks, host time of the enqueue
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize((size_t)3 * chunks + 1);
+        for (cudaEvent_t& e : tev) CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(tev[3 * chunks], B->stream));
+    }
     for (int k = 0; k < chunks; k++) {
-        const int w0 = k * per, w1 = std::min(B->n_worlds, w0 + per);
+        const int w0 = wide_chunked ? B->wchunks[k].w0 : k * per, w1 = wide_chunked ? B->wchunks[k].w1 : std::min(B->n_worlds, w0 + per);
         const int b0 = B->abi_off[w0], n = B->abi_off[w1] - b0;
         cudaStream_t st = B->chunk_streams[k];
         CK(cudaStreamWaitEvent(st, B->chunk_start, 0));
@@ -1336,9 +1457,18 @@ int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, cons
             CK(cudaMemcpyAsync(dr, rot_in + 9 * (size_t)b0, 9 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(dl, ang_mom_in + 3 * (size_t)b0, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
             pack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_abi_off, B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn);
-            KArgs ak = a;
-            ak.world_base = w0; ak.n_worlds = w1;
-            launch_fused(B, ak, st);
+            if (trace) CK(cudaEventRecord(tev[3 * k], st));
+            if (wide_chunked) {
+                for (int s = 0; s < n_steps; s++) {
+                    int rc = launch_wide_step(B, a, st, &B->wchunks[k]);
+                    if (rc) return rc;
+                }
+            } else {
+                KArgs ak = a;
+                ak.world_base = w0; ak.n_worlds = w1;
+                launch_fused(B, ak, st);
+            }
+            if (trace) CK(cudaEventRecord(tev[3 * k + 1], st));
             unpack_dyn_kernel<<<(n + 255) / 256, 256, 0, st>>>(B->d_abi_off, B->d_off, w0, w1, dp, dv, dr, dl, B->d_dyn);
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(pos_out + 3 * (size_t)b0, dp, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1346,10 +1476,25 @@ int ps_batch_step_host(void* handle, int32_t n_steps, const double* pos_in, cons
             CK(cudaMemcpyAsync(rot_out + 9 * (size_t)b0, dr, 9 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(ang_mom_out + 3 * (size_t)b0, dl, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
         }
+        if (trace) CK(cudaEventRecord(tev[3 * k + 2], st));
         CK(cudaEventRecord(B->chunk_done[k], st));
         CK(cudaStreamWaitEvent(B->stream, B->chunk_done[k], 0));
     }
+    const auto t_enq = std::chrono::steady_clock::now();
     CK(cudaStreamSynchronize(B->stream));
+    if (trace) {
+        const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ps_b200 step_host] %d chunks: enqueue %.3f ms, call %.3f ms\n", chunks,
+                std::chrono::duration<double, std::milli>(t_enq - t_call).count(), std::chrono::duration<double, std::milli>(t_end - t_call).count());
+        for (int k = 0; k < chunks; k++) {
+            float t0 = 0, t1 = 0, t2 = 0;
+            if (cudaEventElapsedTime(&t0, tev[3 * chunks], tev[3 * k]) == cudaSuccess && cudaEventElapsedTime(&t1, tev[3 * chunks], tev[3 * k + 1]) == cudaSuccess &&
+                cudaEventElapsedTime(&t2, tev[3 * chunks], tev[3 * k + 2]) == cudaSuccess)
+                fprintf(stderr, "[ps_b200 step_host]   chunk %d: state on the device at %.2f ms, stepped at %.2f, back on the host at %.2f\n", k, t0, t1, t2);
+        }
+        (void)cudaGetLastError();
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     return PS_OK;
 }
 
@@ -1499,6 +1644,7 @@ int ps_batch_add_body(void* handle, int32_t world, const ps_bodies_view* one)
         if (!is_static) B->n_dynamic++;
         B->added.push_back(nb);
         B->added_world.push_back(world);
+        for (WideChunk& c : B->wchunks) c.est_valid = false;
         B->est_valid = false;  // (grid estimates of the device-counted rounds: harmless if stale, but a changed batch starts afresh)
         if (B->tree_mode) {  // BroadPhase.onNewObjectAdded (BroadPhase.fs:83-98): the new id joins the existing tree
             rc = tree_pull_extents(B, B->stream);  // a split re-files the leaf's objects by their CURRENT extents

@@ -47,6 +47,8 @@ struct __align__(16) Entry {  // one near pair of the batch, sorted by (level, k
 
 struct WArgs {
     int n_worlds, n_bodies, max_n;
+    int w_begin, w_end;          // the worlds this pass steps (the whole batch, or one chunk of ps_batch_step_host) ...
+    int g_begin, g_end;          // ... and their slots; every table below is indexed by absolute world / slot
     const int* off;              // per world: first SLOT (capacity prefix: a world owns spare slots for AddObject)
     const int* cnt;              // per world: bodies
     const int* body_world;       // [NB] world of every slot
@@ -121,13 +123,14 @@ __global__ void wide_reset(WArgs a)
     for (int q = t; q < (kWideMaxLevels + 2) * kHitSlots; q += gridDim.x * blockDim.x) a.hit_cnt[q] = 0;
     if (t < kWideMaxLevels + 2) { a.cpool_cur[t] = 0; a.surv_cnt[t] = 0; }
     if (t == 0) { a.nlev[0] = 0; a.nflag[0] = 0; }
-    if (t < a.n_worlds) {
-        a.wflags[t] = a.always_fused[t] ? WF_STATIC : 0u;
-        a.K[t] = 0; a.maxl[t] = 0;
-        a.stats[t].nan_flag = 0;
-        for (int k = 0; k < 6; k++) a.tmp[6 * t + k] = 0;
-        a.tmp_pen[t] = 0ull;
-        if (a.rec_counts) { a.rec_counts[2 * t] = 0; a.rec_counts[2 * t + 1] = 0; }
+    const int w = a.w_begin + t;
+    if (w < a.w_end) {
+        a.wflags[w] = a.always_fused[w] ? WF_STATIC : 0u;
+        a.K[w] = 0; a.maxl[w] = 0;
+        a.stats[w].nan_flag = 0;
+        for (int k = 0; k < 6; k++) a.tmp[6 * w + k] = 0;
+        a.tmp_pen[w] = 0ull;
+        if (a.rec_counts) { a.rec_counts[2 * w] = 0; a.rec_counts[2 * w + 1] = 0; }
     }
 }
 
@@ -145,8 +148,8 @@ __global__ void __launch_bounds__(kTile) wide_predict(WArgs a)
     __shared__ __align__(8) uint64_t bar;
     double* s_in = reinterpret_cast<double*>(tile_raw);
     double* s_pred = reinterpret_cast<double*>(tile_raw + kTileBytes);
-    const int g0 = blockIdx.x * kTile;
-    const int n = min(kTile, a.n_bodies - g0);
+    const int g0 = a.g_begin + blockIdx.x * kTile;
+    const int n = min(kTile, a.g_end - g0);
     const unsigned bytes = (unsigned)n * kDynF * (unsigned)sizeof(double);
     if (threadIdx.x == 0) pst_tma::mbar_init(&bar, 1);
     __syncthreads();
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(kNearT) wide_near_list(WArgs a)
     extern __shared__ __align__(16) unsigned char near_raw[];
     __shared__ int wsum[kNearT / 32];
     __shared__ int carry;
-    const int w = blockIdx.x;
+    const int w = a.w_begin + blockIdx.x;
     const int o = a.off[w], N = a.cnt[w];
     double* sx = reinterpret_cast<double*>(near_raw);          // centre x | y | z | radius vs sphere | radius vs box
     int* rowcnt = reinterpret_cast<int*>(near_raw + (size_t)a.max_n * 5 * sizeof(double));
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(kLvlThreads) wide_levels(WArgs a)
     __shared__ unsigned hist[kBuckets];
     unsigned short* lastS = reinterpret_cast<unsigned short*>(lv_raw);  // per body: bit15 static | last level
     const int stride = lvl_stride(a.max_n);
-    const int w0 = blockIdx.x * kLvlWorlds, wend = min(w0 + kLvlWorlds, a.n_worlds);
+    const int w0 = a.w_begin + blockIdx.x * kLvlWorlds, wend = min(w0 + kLvlWorlds, a.w_end);
     for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads) hist[b] = 0;
     for (int g = a.off[w0] + (int)threadIdx.x; g < a.off[wend]; g += kLvlThreads) {
         const int w = a.body_world[g];
@@ -447,7 +450,7 @@ __global__ void __launch_bounds__(kLvlThreads) wide_scatter(WArgs a)  // same CT
     __shared__ unsigned cnt[kBuckets];   // pairs of this CTA per bucket, then the CTA's base inside the bucket
     __shared__ unsigned cur[kBuckets];
     for (int b = threadIdx.x; b < kBuckets; b += kLvlThreads) { cnt[b] = 0; cur[b] = 0; }
-    const int w0 = blockIdx.x * kLvlWorlds, wend = min(w0 + kLvlWorlds, a.n_worlds);
+    const int w0 = a.w_begin + blockIdx.x * kLvlWorlds, wend = min(w0 + kLvlWorlds, a.w_end);
     if (a.bucket[kBuckets] > a.entries_cap) {  // the sorted list does not fit: the fused kernel takes the step
         for (int w = w0 + (int)threadIdx.x; w < wend; w += kLvlThreads) atomicOr(&a.wflags[w], (unsigned)WF_CAPACITY);
         return;
@@ -932,8 +935,8 @@ __global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_rounds(WArgs a, int r_
 // fused kernel's wider-margin retry.
 __global__ void __launch_bounds__(128) wide_verify(WArgs a)
 {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.n_bodies) return;
+    int g = a.g_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.g_end) return;
     const int w = a.body_world[g];
     const int o = a.off[w], N = a.cnt[w], b = g - o;
     if (b >= N) return;
@@ -1015,8 +1018,8 @@ __global__ void __launch_bounds__(kTile) wide_final(WArgs a)
     __shared__ __align__(8) uint64_t bar;
     __shared__ int any_flagged;
     double* s_t = reinterpret_cast<double*>(tile_raw);
-    const int g0 = blockIdx.x * kTile;
-    const int n = min(kTile, a.n_bodies - g0);
+    const int g0 = a.g_begin + blockIdx.x * kTile;
+    const int n = min(kTile, a.g_end - g0);
     const unsigned bytes = (unsigned)n * kDynF * (unsigned)sizeof(double);
     if (threadIdx.x == 0) { pst_tma::mbar_init(&bar, 1); any_flagged = 0; }
     __syncthreads();
@@ -1063,8 +1066,8 @@ __global__ void __launch_bounds__(kTile) wide_final(WArgs a)
 // account the worlds handed over to the fused kernel (thread per world)
 __global__ void wide_account(WArgs a)
 {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= a.n_worlds) return;
+    int w = a.w_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.w_end) return;
     unsigned f = a.wflags[w];
     WorldStats& st = a.stats[w];
     const unsigned* tm = a.tmp + 6 * (size_t)w;

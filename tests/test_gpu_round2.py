@@ -481,3 +481,45 @@ def test_random_worlds_both_paths(monkeypatch, path, integrator, friction):
     stt = sim.Stats()
     assert stt["contact_overflow"] == 0 and stt["pairs_colliding"] > 500
     sim.close()
+
+
+@pytest.mark.parametrize("chunks", ["1", "3", "4"])
+def test_step_host_on_the_wide_path_in_chunks(monkeypatch, chunks):
+    """ps_batch_step_host on the batch-wide path: chunks of worlds, each with its own chain of rounds on its own stream and
+    its own slice of the pair / hit / contact lists, must give the bits of set_state + step + get_state on the whole batch —
+    ragged worlds, a world that falls back to the fused kernel (more statics than the wide path takes), several steps per call,
+    in == out, and the whole-batch step and the chunked one alternating on ONE handle."""
+    monkeypatch.setenv("PS_B200_PATH", "wide")
+    monkeypatch.setenv("PS_B200_WIDE_HOST_CHUNKS", chunks)
+    worlds = []
+    for w in range(131):  # not a multiple of 32
+        if w % 17 == 5: worlds.append(scenes.c2_spheres64(w)[0])
+        elif w % 29 == 3: worlds.append([])
+        else: worlds.append(scenes.c3_mixed128(w, n_boxes=5 + w % 7, n_spheres=4 + w % 5)[0])
+    many_statics = [P.createDefaultBox(4, 4, 1).With(Mass=P.INFINITE, UseGravity=False, Position=(5.0 * k, 0, -0.5)) for k in range(6)]
+    many_statics += [P.createDefaultSphere(0.4).With(Position=(5.0 * k, 0, 0.6), Mass=2.0) for k in range(6)]
+    worlds[40] = many_statics
+    cfg = Configuration()
+    a = BatchSimulator(worlds, cfg, device=0)
+    b = BatchSimulator(worlds, cfg, device=0)
+    try:
+        assert b.batch.schedule()["path"] == "wide"
+        a.Step(40); b.Step(40)
+        st = a.State()
+        for n in (1, 3, 2):
+            a.batch.set_state(st); a.batch.step(n); ref = a.batch.get_state()
+            got = b.StepHost(st, n)
+            assert_state_bits(ref, got, f"wide step_host, {chunks} chunks, {n} steps")
+            st = {k: v.copy() for k, v in got.items()}
+            b.Step(1); a.Step(1)  # the whole-batch pass in between uses the same lists
+            assert_state_bits(a.State(), b.State(), "whole-batch step after a chunked one")
+            st = b.State()
+        sa, sb = a.Stats(), b.Stats()
+        for k in ("pairs_tested", "pairs_colliding", "contacts", "steps", "fallback_steps"):
+            assert sa[k] == sb[k], (k, sa[k], sb[k])
+        inplace = {k: v.copy() for k, v in st.items()}
+        b.StepHost(inplace, 1, out=inplace)
+        a.batch.set_state(st); a.batch.step(1)
+        assert_state_bits(a.batch.get_state(), inplace, "wide step_host in place")
+    finally:
+        a.close(); b.close()
