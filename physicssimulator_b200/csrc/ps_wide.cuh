@@ -981,10 +981,19 @@ __global__ void __launch_bounds__(128) wide_static_fold(WArgs a, const int* __re
     const double* Sb = a.S + (size_t)o * 3 * kMaxStatics + 3 * (a.isstat[g] - 1) * N;
     const unsigned* near = w_near(a, w);
     const unsigned char* hit = w_hit(a, w);
-    for (int k0 = 0; k0 < K; k0 += 32) {
+    // The list is sorted by (i, j): nothing behind the rows 0 .. b involves body b.  One 32-way probe bounds the walk (the
+    // ground is body 0 of its world: its pairs are the first ~N of ~3 N entries).
+    int Kb = K;
+    if (K > 64) {
+        const int step = (K + 31) / 32, kp = lane * step;
+        const bool behind = kp < K ? (int)(near[kp] & 0xffff) > b : true;
+        const unsigned mb = __ballot_sync(0xffffffffu, behind);
+        if (mb) Kb = min(K, (__ffs(mb) - 1) * step);
+    }
+    for (int k0 = 0; k0 < Kb; k0 += 32) {
         const int k = k0 + lane;
         int other = -1;
-        if (k < K && hit[k]) {
+        if (k < Kb && hit[k]) {
             const unsigned ij = near[k];
             const int i = ij & 0xffff, j = ij >> 16;
             if (i == b) other = j; else if (j == b) other = i;
