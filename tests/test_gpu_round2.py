@@ -521,5 +521,13 @@ def test_step_host_on_the_wide_path_in_chunks(monkeypatch, chunks):
         b.StepHost(inplace, 1, out=inplace)
         a.batch.set_state(st); a.batch.step(1)
         assert_state_bits(a.batch.get_state(), inplace, "wide step_host in place")
+        # a new body (a dynamic one: a record write; a static one: the batch is laid out again and the chunks with it)
+        for proto in (P.createDefaultSphere(0.3).With(Position=(0.2, 0.1, 4.0), Mass=2.0),
+                      P.createDefaultBox(1, 1, 1).With(Mass=P.INFINITE, UseGravity=False, Position=(3.0, 3.0, 0.5))):
+            for s_ in (a, b): s_.AddObject(9, proto)
+            st = a.State()
+            a.batch.set_state(st); a.batch.step(2); ref = a.batch.get_state()
+            assert_state_bits(ref, b.StepHost(st, 2), "wide step_host after add_body")
+            b.batch.set_state(ref)
     finally:
         a.close(); b.close()
