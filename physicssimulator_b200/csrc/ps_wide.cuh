@@ -268,12 +268,26 @@ __global__ void __launch_bounds__(kNearT) wide_near_list(WArgs a)
             int cn = 0;
             if (use_mask) {
                 unsigned* m = mask + (size_t)i * mw;
+                // near_ij with the row's own values in registers (the mask stores in between made the compiler re-read them
+                // from shared memory for every pair: 8 of the 11 loads of a test) and the "both static" case as a predicate
+                const double xi = sx[i], yi = sx[N + i], zi = sx[2 * N + i], r3i = sx[3 * N + i], r4i = sx[4 * N + i];
+                const bool si = sstat[i] != 0;
+                const double* rjv = sx + (sbox[i] ? 4 * N : 3 * N);
                 for (int q = 0; q < mw; q++) {
                     unsigned bits = 0;
                     const int j0 = q * 32;
-                    if (j0 + 31 > i)
-                        for (int j = (j0 > i + 1 ? j0 : i + 1); j < N && j < j0 + 32; j++)
-                            if (near_ij(i, j)) bits |= 1u << (j - j0);
+                    if (j0 + 31 > i) {
+                        const int jb = j0 > i + 1 ? j0 : i + 1, je = N < j0 + 32 ? N : j0 + 32;
+#pragma unroll 4
+                        for (int j = jb; j < je; j++) {
+                            const double dx = xi - sx[j], dy = yi - sx[N + j], dz = zi - sx[2 * N + j];
+                            const double dd = dx * dx + dy * dy + dz * dz;
+                            const double ri = sbox[j] ? r4i : r3i;
+                            const double r = ri + rjv[j];
+                            const bool nr = !(dd > r * r) && !(si && sstat[j]);
+                            bits |= (nr ? 1u : 0u) << (j - j0);
+                        }
+                    }
                     m[q] = bits;
                     cn += __popc(bits);
                 }
