@@ -1074,6 +1074,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st, WideChun
         const unsigned dflt = (unsigned)std::max(1, B->sm_count) * 8;   // no estimate yet: a grid that fills the device, strides do the rest
         auto blocks = [&](unsigned n, unsigned per) { return (unsigned)(((unsigned long long)n * 9 / 8 + per - 1) / per) + 4u; };  // estimate + 12 %
         int r_launch = 48;
+        static const bool paired = !(getenv("PS_B200_RESOLVE_PAIRED") && atoi(getenv("PS_B200_RESOLVE_PAIRED")) == 0);  // tuning knob
         const unsigned* hb = *est_valid ? est->data() : nullptr;
         const unsigned* hh = hb ? hb + kBuckets + 1 : nullptr;      // hit counts per (level, kind)
         const unsigned* hs = hb ? hb + 3 * kBuckets + 1 : nullptr;  // survivors per level
@@ -1084,7 +1085,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st, WideChun
         }
         if (const char* e = getenv("PS_B200_COOP_ALL")) { if (atoi(e) != 0) r_launch = 0; }  // tuning: every round in the cooperative kernel
         for (int r = 1; r <= r_launch; r++) {
-            unsigned g1 = dflt, g2 = dflt, g2t = dflt, g3 = dflt, ns_est = ~0u;
+            unsigned g1 = dflt, g2 = dflt, g2t = dflt, g3 = dflt, g3p = dflt, ns_est = ~0u;
             if (hb) {
                 const unsigned c0 = hb[r * 4 + 1] - hb[r * 4], c1 = hb[r * 4 + 2] - hb[r * 4 + 1], c2 = hb[r * 4 + 3] - hb[r * 4 + 2];
                 g1 = blocks(c0, 128) + blocks(c1, 128) + blocks(c2, 128);
@@ -1092,12 +1093,14 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st, WideChun
                 g2 = blocks(ns_est, 128); g2t = blocks(ns_est, 16);
                 g3 = 0;
                 for (int k = 0; k < 6; k++) g3 += blocks(hh[r * psw::kHitSlots + k], 128);
+                g3p = g3 + blocks(hh[r * psw::kHitSlots + 4], 128) + blocks(hh[r * psw::kHitSlots + 5], 128);  // classes C, D on two lanes each
             }
             wide_round_detect_d<<<g1, 128, 0, st>>>(a, r);
             if (ns_est <= B->team_max) wide_round_bb_team_d<<<g2t, 128, 0, st>>>(a, r);
             else wide_round_bb_d<<<g2, 128, 0, st>>>(a, r);
-            if (hb && g3 > 4000u) wide_round_resolve_d<3><<<g3, 128, 0, st>>>(a, r);  // > ~0.5 M colliding pairs: throughput bound
-            else wide_round_resolve_d<PS_WIDE_MINB><<<g3, 128, 0, st>>>(a, r);
+            if (hb && g3 > 4000u) wide_round_resolve_d<3, false><<<g3, 128, 0, st>>>(a, r);  // > ~0.5 M colliding pairs: throughput bound
+            else if (paired) wide_round_resolve_d<PS_WIDE_MINB, true><<<g3p, 128, 0, st>>>(a, r);
+            else wide_round_resolve_d<PS_WIDE_MINB, false><<<g3, 128, 0, st>>>(a, r);
         }
         B->launches += 3 * (long long)r_launch;
         if (r_launch < kWideMaxLevels) {

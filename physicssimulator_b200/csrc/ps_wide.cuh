@@ -655,15 +655,18 @@ __device__ __forceinline__ bool wide_pick_hit(const WArgs& a, int kind, unsigned
     return true;
 }
 template <bool BOX>
-__device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, int level);
+__device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, int level, int only_side = -1);
 template <int KIND>
 __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first, unsigned c2, int level, unsigned t)
 {
     unsigned ei;
     if (wide_pick_hit(a, KIND, first, c2, level, t, ei)) wide_resolve_entry<(KIND >= 2)>(a, ei, level);
 }
+// only_side >= 0: TWO neighbouring lanes hold this pair and run the same solve on the same inputs; each writes back and
+// re-integrates ONE of the two bodies (measured on the manifolds of 7 and more contacts that end a round: loads 9 K cycles,
+// contact setup 18 K, iterations 148 K, write-back + two re-integrations 32 K)
 template <bool BOX>
-__device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, int level)
+__device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, int level, int only_side)
 {
     constexpr int KIND = BOX ? 2 : 0;
     PS_CLK_BEGIN(KIND >= 2 && level >= 3)
@@ -698,7 +701,7 @@ __device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, 
     }
     if (!ok) {  // a quotient outside the short division's range, a non-finite accumulator: the literal routine, same inputs
         PS_COLD_PATH;
-        atomicAdd(&a.tmp[6 * (size_t)w + 2], 1u);  // (counted: PS_B200_WIDE_PROF prints the share of pairs that took this route)
+        if (only_side <= 0) atomicAdd(&a.tmp[6 * (size_t)w + 2], 1u);  // (counted: PS_B200_WIDE_PROF prints the share of pairs that took this route)
         wide_resolve_literal(a, o + i, o + j, si, sj, a.cpool + e.cfirst, (int)(e.knc >> 24), di, dj);
     }
     w_hit(a, w)[e.knc & 0xffffffu] = 1;
@@ -707,7 +710,8 @@ __device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, 
     // (measured: the two re-integrations as one two-lane straight-line computation (integrate_2) spill in this kernel —
     //  round 1 of C3 1.88 -> 2.01 ms, the other rounds unchanged — so they stay the literal routine, one after the other)
 #pragma unroll 1
-    for (int side = 0; side < 2; side++) {
+    for (int pass = 0; pass < (only_side >= 0 ? 1 : 2); pass++) {
+        const int side = only_side >= 0 ? only_side : pass;  // (two lanes: both in the same pass, each with its own body)
         const int b = side ? j : i, other = side ? i : j;
         const bool stat = side ? sj : si;
         Dyn& d = side ? dj : di;
@@ -862,7 +866,8 @@ __global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_bb_team_d(WArgs 
 // MINB = resident CTAs per SM the register allocation allows: 2 (255 registers) for the rounds that wait for their longest
 // manifold, 3 (168 registers, 12 warps per SM) for a round that is throughput bound — round 1, every body against the ground:
 // 1.84 -> 1.68 ms; the other rounds are slower with it (110 -> 140 us)
-template <int MINB>
+// PAIRED: the manifolds of 5 and more contacts (classes C, D: the threads a latency-bound round waits for) get two lanes each
+template <int MINB, bool PAIRED>
 __global__ void __launch_bounds__(128, MINB) wide_round_resolve_d(WArgs a, int r)
 {
     if (r > a.nlev[0] || a.bucket[kBuckets] > a.entries_cap) return;
@@ -870,16 +875,18 @@ __global__ void __launch_bounds__(128, MINB) wide_round_resolve_d(WArgs a, int r
     const unsigned* hc = a.hit_cnt + r * kHitSlots;
     unsigned nb[6], tot = 0;
 #pragma unroll
-    for (int k = 0; k < 6; k++) { nb[k] = (hc[k] + 127) / 128; tot += nb[k]; }
+    for (int k = 0; k < 6; k++) { nb[k] = (hc[k] * ((PAIRED && k >= 4) ? 2u : 1u) + 127) / 128; tot += nb[k]; }
     const unsigned fbb = q.first + q.c0 + q.c1;
     for (unsigned blk = blockIdx.x; blk < tot; blk += gridDim.x) {  // the largest manifolds first: they are the long ones
         unsigned b = blk;
         int kind = 5;
         while (kind > 0 && b >= nb[kind]) { b -= nb[kind]; kind--; }
         const unsigned fk = kind >= 2 ? fbb : (kind == 1 ? q.first + q.c0 : q.first);
-        unsigned ei;
-        if (!wide_pick_hit(a, kind, fk, q.c2, r, b * 128 + threadIdx.x, ei)) continue;
-        if (kind >= 2) wide_resolve_entry<true>(a, ei, r);   // (one copy of each solver in the kernel)
+        unsigned ei, t = b * 128 + threadIdx.x;
+        int only = -1;
+        if (PAIRED && kind >= 4) { only = (int)(t & 1u); t >>= 1; }
+        if (!wide_pick_hit(a, kind, fk, q.c2, r, t, ei)) continue;
+        if (kind >= 2) wide_resolve_entry<true>(a, ei, r, only);   // (one copy of each solver in the kernel)
         else wide_resolve_entry<false>(a, ei, r);
     }
 }
