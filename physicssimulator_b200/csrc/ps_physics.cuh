@@ -1102,6 +1102,115 @@ PSD bool resolve_s(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact
     return ok;
 }
 
+#if defined(__CUDACC__)
+// ---- the same solve on TWO neighbouring lanes of a warp: lane `second == false` carries body 1, the other body 2 ------------
+// What a round of the batch-wide step waits for is ONE thread's walk through the iterations of its largest manifold (measured,
+// manifolds of 7 and more contacts: 148 K cycles of iterations, ~430 instructions per contact-iteration, an FP64 instruction
+// costs a warp two issue cycles whatever its lanes).  Three quarters of a contact-iteration is the same code on the data of
+// body 1 and of body 2 (velocity at the contact point, applying the impulse): each lane does it for its own body, the two
+// point velocities are exchanged by shuffles (vRel = u2 - u1 on both lanes), the impulse arithmetic in between is done by both
+// lanes on identical operands.  Every operation is an operation of resolve_s on the same operands: same bits.
+struct CPFast2 {
+    d3 n, r;  // r: the contact offset of the lane's own body
+    double bias, mN, mT0, mT1, yN, yT0, yT1, accN, accT0, accT1;
+};
+PSD d3 shfl_pair(unsigned m, d3 v) { return mk(__shfl_xor_sync(m, v.x, 1), __shfl_xor_sync(m, v.y, 1), __shfl_xor_sync(m, v.z, 1)); }
+PSD d3 sel3(bool c, d3 a, d3 b) { return mk(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
+PSD void solve_contact_s2(unsigned m, bool second, d3& v, d3& L, const m33& Iw, double im, const SolveS& c, CPFast2& d, bool& ok)
+{
+    const bool live = !(d.mN == 0.0);
+    const d3 u = v + cross(mulMV(Iw, L), d.r);
+    const d3 uo = shfl_pair(m, u);
+    const d3 vrel = sel3(second, u, uo) - sel3(second, uo, u);  // velocity_at(body 2) - velocity_at(body 1)
+    const double vn = dot(vrel, d.n);
+    bool okq = true;
+    const double j = div_by_s(c.e1 * vn + d.bias, d.mN, d.yN, okq);
+    ok = ok && (okq || !live);
+    const double old = d.accN;
+    const double acc = fmax_s(0.0, fmin_s(old + j, c.inf));
+    d3 P = scale_s(-(acc - old), d.n);
+    d.accN = live ? acc : old;
+    P = mk(live ? P.x : 0.0, live ? P.y : 0.0, live ? P.z : 0.0);
+    const d3 Pl = sel3(second, -P, P);  // body 1 takes P, body 2 takes -P
+    v = v + scale_s(im, Pl);
+    L = L + cross(d.r, Pl);
+    if (c.friction) {
+        const d3 w = v + cross(mulMV(Iw, L), d.r);
+        const d3 wo = shfl_pair(m, w);
+        const d3 vr = sel3(second, w, wo) - sel3(second, wo, w);
+        const double maxF = c.mu * d.accN;
+        const double j0 = div_by_s(dot(c.t0, vr), d.mT0, d.yT0, ok);
+        const double j1 = div_by_s(dot(c.t1, vr), d.mT1, d.yT1, ok);
+        const double o0 = d.accT0, o1 = d.accT1;
+        d.accT0 = fmax_s(-maxF, fmin_s(o0 + j0, maxF));
+        d.accT1 = fmax_s(-maxF, fmin_s(o1 + j1, maxF));
+        const d3 P0 = scale_s(d.accT0 - o0, c.t0);
+        const d3 P1 = scale_s(d.accT1 - o1, c.t1);
+        const d3 Q0 = sel3(second, -P0, P0), Q1 = sel3(second, -P1, P1);
+        v = v + scale_s(im, Q0);
+        v = v + scale_s(im, Q1);
+        L = L + cross(d.r, Q0);
+        L = L + cross(d.r, Q1);
+    }
+}
+// act: the lanes of the warp that are in this call (pairs of neighbours, all converged at the call)
+PSD bool resolve_s2(unsigned act, bool second, Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* cs, int nc, CPFast2* cp,
+                    const StepParams& sp)
+{
+    const m33 Iw1 = inertia_inv_world(b1.R, p1.iinv);
+    const m33 Iw2 = inertia_inv_world(b2.R, p2.iinv);
+    SolveS c;
+    tangents(cs[0].n, c.t0, c.t1);
+    {
+        const SolveConst sc = solve_const(p1, p2, sp);
+        c.im1 = p1.inv_mass; c.im2 = p2.inv_mass; c.e1 = -(sc.e + 1.0); c.mu = sc.mu; c.inf = sc.inf; c.friction = sc.friction != 0;
+    }
+    bool ok = true;
+    CPFast2 d;
+#pragma unroll 1
+    for (int k = 0; k < nc; k++) {  // (both lanes set up every contact: the effective masses need both bodies)
+        CPData q;
+        const Contact ck = cs[k];
+        contact_setup(b1, p1, Iw1, b2, p2, Iw2, ck, c.t0, c.t1, sp, q);
+        d.n = ck.n; d.r = sel3(second, q.r2, q.r1);
+        d.bias = q.bias; d.mN = q.mN; d.mT0 = q.mT0; d.mT1 = q.mT1;
+        d.yN = recip_seed(q.mN); d.yT0 = recip_seed(q.mT0); d.yT1 = recip_seed(q.mT1);
+        d.accN = 0.0; d.accT0 = 0.0; d.accT1 = 0.0;
+        cp[k] = d;
+    }
+    m33 Iw;
+#pragma unroll
+    for (int q = 0; q < 9; q++) Iw.a[q] = second ? Iw2.a[q] : Iw1.a[q];
+    const double im = second ? p2.inv_mass : p1.inv_mass;
+    d3 v = sel3(second, b2.v, b1.v), L = sel3(second, b2.L, b1.L);
+#if defined(__CUDA_ARCH__)
+    const int ncmax = __reduce_max_sync(act, nc);  // the walk of resolve_s: one index for all lanes
+#else
+    const int ncmax = nc;
+#endif
+    d = cp[ncmax - 1];
+#pragma unroll 1
+    for (int it = 0; it < sp.iterations; it++) {
+#pragma unroll 1
+        for (int kk = ncmax - 1; kk >= 0; kk--) {
+            const CPFast2 nx = cp[kk > 0 ? kk - 1 : ncmax - 1];
+            const unsigned m = __ballot_sync(act, kk < nc);  // (the two lanes of a pair hold the same nc)
+            if (kk < nc) {
+                solve_contact_s2(m, second, v, L, Iw, im, c, d, ok);
+                cp[kk].accN = d.accN;
+                cp[kk].accT0 = d.accT0;
+                cp[kk].accT1 = d.accT1;
+            }
+            if (ncmax > 1) d = nx;
+        }
+    }
+    ok = ok && (__shfl_xor_sync(act, ok ? 1 : 0, 1) != 0);
+    if (second) { b2.v = v; b2.L = L; }
+    else { b1.v = v; b1.L = L; }
+    return ok;
+}
+#endif
+
 PSN void resolve(Dyn& b1, const Par& p1, Dyn& b2, const Par& p2, const Contact* cs, int nc, CPData* cp,
                  const StepParams& sp)
 {

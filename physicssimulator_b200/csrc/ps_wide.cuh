@@ -655,7 +655,7 @@ __device__ __forceinline__ bool wide_pick_hit(const WArgs& a, int kind, unsigned
     return true;
 }
 template <bool BOX>
-__device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, int level, int only_side = -1);
+__device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, int level, int only_side = -1, unsigned act = 0u);
 template <int KIND>
 __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first, unsigned c2, int level, unsigned t)
 {
@@ -666,13 +666,15 @@ __device__ __forceinline__ void wide_resolve_body(const WArgs& a, unsigned first
 // re-integrates ONE of the two bodies (measured on the manifolds of 7 and more contacts that end a round: loads 9 K cycles,
 // contact setup 18 K, iterations 148 K, write-back + two re-integrations 32 K)
 template <bool BOX>
-__device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, int level, int only_side)
+__device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, int level, int only_side, unsigned act)
 {
     constexpr int KIND = BOX ? 2 : 0;
     PS_CLK_BEGIN(KIND >= 2 && level >= 3)
     const Entry& e = a.entries[ei];
     const int w = e.w;
-    if (a.wflags[w]) return;
+    const bool gone = a.wflags[w] != 0;
+    if (BOX && only_side >= 0) act = __ballot_sync(act, !gone);  // (the two lanes of a pair read the same flag)
+    if (gone) return;
     const int o = a.off[w], N = a.cnt[w];
     const int i = e.ij & 0xffff, j = e.ij >> 16;
     Par pi, pj; Dyn di, dj;
@@ -692,6 +694,11 @@ __device__ __forceinline__ void wide_resolve_entry(const WArgs& a, unsigned ei, 
         CPFast cp[PS_MAX_CONTACTS];
         PS_CLK(13)
         const Contact* cs = a.cpool + e.cfirst;  // the manifold is read where the narrow phase left it
+        if (only_side >= 0) {  // two lanes per manifold: each carries one body through the iterations (ps_physics.cuh, resolve_s2)
+            const unsigned act2 = __ballot_sync(act, !s1);
+            if (s1) ok = resolve_s<0, true>(di, pi, dj, pj, cs, nc, cp, a.sp);
+            else ok = resolve_s2(act2, only_side != 0, di, pi, dj, pj, cs, nc, reinterpret_cast<CPFast2*>(cp), a.sp);
+        } else
         ok = s1 ? resolve_s<0, true>(di, pi, dj, pj, cs, nc, cp, a.sp) : resolve_s<0, false>(di, pi, dj, pj, cs, nc, cp, a.sp);
         PS_CLK(14)
     } else {  // sphere pairs always carry exactly one contact
@@ -885,8 +892,10 @@ __global__ void __launch_bounds__(128, MINB) wide_round_resolve_d(WArgs a, int r
         unsigned ei, t = b * 128 + threadIdx.x;
         int only = -1;
         if (PAIRED && kind >= 4) { only = (int)(t & 1u); t >>= 1; }
-        if (!wide_pick_hit(a, kind, fk, q.c2, r, t, ei)) continue;
-        if (kind >= 2) wide_resolve_entry<true>(a, ei, r, only);   // (one copy of each solver in the kernel)
+        const bool have = wide_pick_hit(a, kind, fk, q.c2, r, t, ei);
+        const unsigned act = __ballot_sync(0xffffffffu, have);  // (the CTA is converged here: kind and b are CTA-uniform)
+        if (!have) continue;
+        if (kind >= 2) wide_resolve_entry<true>(a, ei, r, only, act);   // (one copy of each solver in the kernel)
         else wide_resolve_entry<false>(a, ei, r);
     }
 }
