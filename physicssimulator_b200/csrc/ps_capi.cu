@@ -1093,7 +1093,8 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st, WideChun
                 g2 = blocks(ns_est, 128); g2t = blocks(ns_est, 16);
                 g3 = 0;
                 for (int k = 0; k < 6; k++) g3 += blocks(hh[r * psw::kHitSlots + k], 128);
-                g3p = g3 + blocks(hh[r * psw::kHitSlots + 4], 128) + blocks(hh[r * psw::kHitSlots + 5], 128);  // classes C, D on two lanes each
+                g3p = g3;
+                for (int k = psw::kPairedFrom; k < 6; k++) g3p += blocks(hh[r * psw::kHitSlots + k], 128);  // the large classes on two lanes each
             }
             wide_round_detect_d<<<g1, 128, 0, st>>>(a, r);
             if (ns_est <= B->team_max) wide_round_bb_team_d<<<g2t, 128, 0, st>>>(a, r);

@@ -873,7 +873,15 @@ __global__ void __launch_bounds__(128, PS_WIDE_MINB) wide_round_bb_team_d(WArgs 
 // MINB = resident CTAs per SM the register allocation allows: 2 (255 registers) for the rounds that wait for their longest
 // manifold, 3 (168 registers, 12 warps per SM) for a round that is throughput bound — round 1, every body against the ground:
 // 1.84 -> 1.68 ms; the other rounds are slower with it (110 -> 140 us)
-// PAIRED: the manifolds of 5 and more contacts (classes C, D: the threads a latency-bound round waits for) get two lanes each
+// PAIRED (the rounds that wait for their slowest thread): a box manifold gets two neighbouring lanes.  Each lane carries one of
+// the two bodies through the iterations (resolve_s2) and writes back and re-integrates that body.  Measured per phase on the
+// manifolds of 7 and more contacts, one lane each: loads 9 K cycles, contact setup 18 K, iterations 148 K, write-back + two
+// re-integrations 32 K.  kPairedFrom = first hit slot that is paired; C3, ms per step: nothing paired 11.86, classes C and D (4)
+// 11.64, B too (3) 11.66, every box manifold (2) 11.49, sphere pairs too (0) 11.64.
+#ifndef PS_PAIRED_FROM
+#define PS_PAIRED_FROM 2
+#endif
+constexpr int kPairedFrom = PS_PAIRED_FROM;
 template <int MINB, bool PAIRED>
 __global__ void __launch_bounds__(128, MINB) wide_round_resolve_d(WArgs a, int r)
 {
@@ -882,7 +890,7 @@ __global__ void __launch_bounds__(128, MINB) wide_round_resolve_d(WArgs a, int r
     const unsigned* hc = a.hit_cnt + r * kHitSlots;
     unsigned nb[6], tot = 0;
 #pragma unroll
-    for (int k = 0; k < 6; k++) { nb[k] = (hc[k] * ((PAIRED && k >= 4) ? 2u : 1u) + 127) / 128; tot += nb[k]; }
+    for (int k = 0; k < 6; k++) { nb[k] = (hc[k] * ((PAIRED && k >= kPairedFrom) ? 2u : 1u) + 127) / 128; tot += nb[k]; }
     const unsigned fbb = q.first + q.c0 + q.c1;
     for (unsigned blk = blockIdx.x; blk < tot; blk += gridDim.x) {  // the largest manifolds first: they are the long ones
         unsigned b = blk;
@@ -891,12 +899,12 @@ __global__ void __launch_bounds__(128, MINB) wide_round_resolve_d(WArgs a, int r
         const unsigned fk = kind >= 2 ? fbb : (kind == 1 ? q.first + q.c0 : q.first);
         unsigned ei, t = b * 128 + threadIdx.x;
         int only = -1;
-        if (PAIRED && kind >= 4) { only = (int)(t & 1u); t >>= 1; }
+        if (PAIRED && kind >= kPairedFrom) { only = (int)(t & 1u); t >>= 1; }
         const bool have = wide_pick_hit(a, kind, fk, q.c2, r, t, ei);
         const unsigned act = __ballot_sync(0xffffffffu, have);  // (the CTA is converged here: kind and b are CTA-uniform)
         if (!have) continue;
         if (kind >= 2) wide_resolve_entry<true>(a, ei, r, only, act);   // (one copy of each solver in the kernel)
-        else wide_resolve_entry<false>(a, ei, r);
+        else wide_resolve_entry<false>(a, ei, r, only);
     }
 }
 
