@@ -1074,6 +1074,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st, WideChun
         const unsigned dflt = (unsigned)std::max(1, B->sm_count) * 8;   // no estimate yet: a grid that fills the device, strides do the rest
         auto blocks = [&](unsigned n, unsigned per) { return (unsigned)(((unsigned long long)n * 9 / 8 + per - 1) / per) + 4u; };  // estimate + 12 %
         int r_launch = 48;
+        static const unsigned big_g3 = getenv("PS_B200_RESOLVE_BIG_CTAS") ? (unsigned)atoi(getenv("PS_B200_RESOLVE_BIG_CTAS")) : 1200u;  // tuning knob (measured, C3: 4000 11.48, 1500 11.46, 900 11.45, 500 11.57 ms per step): CTAs from which a round's solve is the 168-register one-lane build
         static const bool paired = !(getenv("PS_B200_RESOLVE_PAIRED") && atoi(getenv("PS_B200_RESOLVE_PAIRED")) == 0);  // tuning knob
         const unsigned* hb = *est_valid ? est->data() : nullptr;
         const unsigned* hh = hb ? hb + kBuckets + 1 : nullptr;      // hit counts per (level, kind)
@@ -1099,7 +1100,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st, WideChun
             wide_round_detect_d<<<g1, 128, 0, st>>>(a, r);
             if (ns_est <= B->team_max) wide_round_bb_team_d<<<g2t, 128, 0, st>>>(a, r);
             else wide_round_bb_d<<<g2, 128, 0, st>>>(a, r);
-            if (hb && g3 > 4000u) wide_round_resolve_d<3, false><<<g3, 128, 0, st>>>(a, r);  // > ~0.5 M colliding pairs: throughput bound
+            if (hb && g3 > big_g3) wide_round_resolve_d<3, false><<<g3, 128, 0, st>>>(a, r);  // many colliding pairs: throughput bound
             else if (paired) wide_round_resolve_d<PS_WIDE_MINB, true><<<g3p, 128, 0, st>>>(a, r);
             else wide_round_resolve_d<PS_WIDE_MINB, false><<<g3, 128, 0, st>>>(a, r);
         }
