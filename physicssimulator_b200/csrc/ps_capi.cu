@@ -1015,7 +1015,7 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st, WideChun
     a.nlev = B->d_nlev; a.nflag = B->d_nflag; a.team_max = B->team_max;
     a.sp = ka.sp; a.margin_ncap = ka.margin_ncap;
     a.margin_scale = ka.margin_scale;
-    a.margin_vnear = 1.0;  // C3 rollout, ms per step in the windows of steps 50-75 / 75-100 / 225-250 and world-steps redone by the fused kernel: 0: 21.3 / 29.6 / 11.30, 753 / 9709; 1: 18.5 / 29.5 / 11.33, 117 / 5369; 2: 19.2 / 28.0 / 11.42, 21 / 1817 (and 0.7-1.3 ms more while everything is still falling)
+    a.margin_vnear = 0.0;
     if (const char* e = getenv("PS_B200_VNEAR")) a.margin_vnear = atof(e);  // tuning knob
     // the whole batch, or one chunk of ps_batch_step_host with its own small tables and its slice of the lists
     unsigned* h_est = B->h_est;
