@@ -135,7 +135,6 @@ struct Batch {
     int sm_count = 148;
     unsigned team_max = 0;     // box-box survivors per round up to which every survivor gets a team of 8 lanes
     unsigned long long* d_tmp_pen = nullptr;
-    float *d_speed = nullptr, *d_vnear = nullptr;  // [n_slots] (ps_wide.cuh, margin_vnear)
     double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // PS_B200_WIDE_PROF: setup, integrate, ss, sb, bb, resolve, tail, fused
     long long prof_steps = 0, prof_rounds = 0;
     std::vector<float> prof_round;  // last profiled step: per round c0, c1, c2, detect ms, bb ms, resolve ms
@@ -310,7 +309,7 @@ void free_device(Batch* B)
     dfree(B->d_dyn); dfree(B->d_par); dfree(B->d_stage); dfree(B->d_off); dfree(B->d_stats); dfree(B->d_hitcnt); dfree(B->d_cost); dfree(B->d_perm); dfree(B->d_cur); dfree(B->d_pred); dfree(B->d_S); dfree(B->d_cull); dfree(B->d_row); dfree(B->d_lists); dfree(B->d_lists_off); dfree(B->d_lvl); dfree(B->d_last);
     dfree(B->d_body_world); dfree(B->d_pvalid); dfree(B->d_nhit); dfree(B->d_isstat); dfree(B->d_isbox); dfree(B->d_always_fused);
     dfree(B->d_K); dfree(B->d_maxl); dfree(B->d_wflags); dfree(B->d_bucket); dfree(B->d_bucket_cur); dfree(B->d_hit_cnt);
-    dfree(B->d_hitlist); dfree(B->d_hitlist2); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_speed); dfree(B->d_vnear); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev); dfree(B->d_nflag); dfree(B->d_stat_slots); dfree(B->d_cnt); dfree(B->d_abi_off);
+    dfree(B->d_hitlist); dfree(B->d_hitlist2); dfree(B->d_cpool_cur); dfree(B->d_entries); dfree(B->d_cpool); dfree(B->d_tmp); dfree(B->d_tmp_pen); dfree(B->d_surv); dfree(B->d_surv_cnt); dfree(B->d_nlev); dfree(B->d_nflag); dfree(B->d_stat_slots); dfree(B->d_cnt); dfree(B->d_abi_off);
     for (WideChunk& c : B->wchunks) {
         dfree(c.d_small);
         if (c.h_est) cudaFreeHost(c.h_est);
@@ -494,8 +493,6 @@ int upload(Batch* B, bool with_state)
         CK(cudaMalloc(&B->d_surv, (size_t)B->entries_cap * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_surv_cnt, (psw::kWideMaxLevels + 2) * sizeof(unsigned)));
         CK(cudaMalloc(&B->d_tmp_pen, nw * sizeof(unsigned long long)));
-        CK(cudaMalloc(&B->d_speed, nb * sizeof(float))); CK(cudaMalloc(&B->d_vnear, nb * sizeof(float)));
-        CK(cudaMemset(B->d_speed, 0, nb * sizeof(float))); CK(cudaMemset(B->d_vnear, 0, nb * sizeof(float)));
         CK(cudaMalloc(&B->d_nlev, sizeof(int)));
         CK(cudaMalloc(&B->d_nflag, sizeof(int)));
         CK(cudaMallocHost(&B->h_est, (size_t)(4 * psw::kBuckets + 8) * sizeof(unsigned)));
@@ -1009,14 +1006,12 @@ static int launch_wide_step(Batch* B, const KArgs& ka, cudaStream_t st, WideChun
     a.K = B->d_K; a.maxl = B->d_maxl; a.wflags = B->d_wflags; a.always_fused = B->d_always_fused;
     a.bucket = B->d_bucket; a.bucket_cur = B->d_bucket_cur; a.entries = B->d_entries; a.entries_cap = B->entries_cap;
     a.hit_cnt = B->d_hit_cnt; a.hitlist = B->d_hitlist; a.hitlist2 = B->d_hitlist2; a.cpool = B->d_cpool; a.cpool_cap = B->cpool_cap; a.cpool_cur = B->d_cpool_cur;
-    a.stats = B->d_stats; a.tmp = B->d_tmp; a.tmp_pen = B->d_tmp_pen; a.speed = B->d_speed; a.vnear = B->d_vnear; a.surv = B->d_surv; a.surv_cnt = B->d_surv_cnt;
+    a.stats = B->d_stats; a.tmp = B->d_tmp; a.tmp_pen = B->d_tmp_pen; a.surv = B->d_surv; a.surv_cnt = B->d_surv_cnt;
     a.rec_pairs = B->d_rec_pairs; a.rec_contacts = B->d_rec_contacts; a.rec_counts = B->d_rec_counts;
     a.rec_pair_cap = B->rec_pair_cap; a.rec_contact_cap = B->rec_contact_cap;
     a.nlev = B->d_nlev; a.nflag = B->d_nflag; a.team_max = B->team_max;
     a.sp = ka.sp; a.margin_ncap = ka.margin_ncap;
     a.margin_scale = ka.margin_scale;
-    a.margin_vnear = 0.0;
-    if (const char* e = getenv("PS_B200_VNEAR")) a.margin_vnear = atof(e);  // tuning knob
     // the whole batch, or one chunk of ps_batch_step_host with its own small tables and its slice of the lists
     unsigned* h_est = B->h_est;
     cudaEvent_t est_ready = B->est_ready;

@@ -78,12 +78,6 @@ struct WArgs {
     StepParams sp;
     int margin_ncap;
     double margin_scale;         // safety factor on the motion margin (a violated margin costs a whole fused redo)
-    // room for a body at rest to be hit by a fast one: + margin_vnear x dt x (largest speed among the body's near partners of
-    // the previous step).  A fast body is near everything it may reach within two steps (its own margin holds its speed), so
-    // its targets learn of it a step before the impact.
-    double margin_vnear;
-    float* speed;                // [NB] predicted speed of this step (wide_predict -> wide_near_list)
-    float* vnear;                // [NB] largest speed among the near partners (wide_near_list -> the next step's wide_predict)
 };
 
 enum { WF_MARGIN = 1, WF_STATIC = 2, WF_CAPACITY = 4 };
@@ -191,8 +185,7 @@ __global__ void __launch_bounds__(kTile) wide_predict(WArgs a)
         int np_ = a.nprev[g];
         double nn = (double)(np_ < a.margin_ncap ? np_ : a.margin_ncap) + 2.0;
         const double mscale = a.margin_scale * (a.stats[w].boost > 0 ? 2.0 : 1.0);
-        a.speed[g] = (speed == speed) ? fminf((float)speed, 1.0e6f) : 0.0f;
-        double m = p.is_static ? 0.0 : mscale * (0.01 + nn * a.sp.dt * (speed + nn * acc * a.sp.dt + 0.5) + a.margin_vnear * a.sp.dt * (double)a.vnear[g]);
+        double m = p.is_static ? 0.0 : mscale * (0.01 + nn * a.sp.dt * (speed + nn * acc * a.sp.dt + 0.5));
         if (!(m == m)) m = 0.0;
         double rs, rb;
         if (p.shape == 0) { rs = p.dims[0]; rb = 1.7320508075688774 * p.dims[0]; }
@@ -234,7 +227,7 @@ constexpr int kNearMaskN = 256;
 __host__ __device__ inline size_t near_smem_bytes(int max_n)
 {
     const size_t words = max_n <= kNearMaskN ? (size_t)max_n * ((max_n + 31) / 32) : 0;
-    return (size_t)max_n * (5 * sizeof(double) + 2 + sizeof(int) + sizeof(float) + sizeof(int)) + words * sizeof(unsigned) + 48;
+    return (size_t)max_n * (5 * sizeof(double) + 2 + sizeof(int)) + words * sizeof(unsigned) + 32;
 }
 __global__ void __launch_bounds__(kNearT) wide_near_list(WArgs a)
 {
@@ -250,13 +243,10 @@ __global__ void __launch_bounds__(kNearT) wide_near_list(WArgs a)
     const int mw = (a.max_n + 31) / 32;  // mask words per row
     unsigned char* sbox = reinterpret_cast<unsigned char*>(mask + (use_mask ? (size_t)a.max_n * mw : 0));
     unsigned char* sstat = sbox + a.max_n;
-    float* sv = reinterpret_cast<float*>((reinterpret_cast<size_t>(sstat + a.max_n) + 15) & ~(size_t)15);  // speeds
-    int* svn = reinterpret_cast<int*>(sv + a.max_n);  // largest partner speed (bits of a non-negative float order like ints)
     const double* cu = a.cull + (size_t)o * kCullF;
     for (int b = threadIdx.x; b < N; b += kNearT) {
         sx[b] = cu[b]; sx[N + b] = cu[N + b]; sx[2 * N + b] = cu[2 * N + b]; sx[3 * N + b] = cu[3 * N + b]; sx[4 * N + b] = cu[4 * N + b];
         sbox[b] = a.isbox[o + b]; sstat[b] = a.isstat[o + b];
-        sv[b] = a.speed[o + b]; svn[b] = 0;
     }
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
@@ -340,9 +330,6 @@ __global__ void __launch_bounds__(kNearT) wide_near_list(WArgs a)
                         near[q] = (unsigned)i | ((unsigned)j << 16);
                         hit[q] = 0;
                         q++;
-                        const int vi = __float_as_int(sv[i]), vj = __float_as_int(sv[j]);
-                        if (vj > svn[i]) atomicMax(&svn[i], vj);  // (the plain read only spares atomics)
-                        if (vi > svn[j]) atomicMax(&svn[j], vi);
                     }
                 }
             } else {
@@ -355,8 +342,6 @@ __global__ void __launch_bounds__(kNearT) wide_near_list(WArgs a)
             }
         }
     if (threadIdx.x == 0) a.K[w] = carry;
-    __syncthreads();
-    for (int b = threadIdx.x; b < N; b += kNearT) a.vnear[o + b] = __int_as_float(svn[b]);
 }
 
 // ---- C: levels + buckets ---------------------------------------------------------------------------------
